@@ -1,0 +1,340 @@
+/*
+ * oracle.c - CPU restatement of the adsbdec `-f` hot path.  TEST INFRASTRUCTURE ONLY.
+ * See oracle.h for scope, citations and how this file is pinned.
+ *
+ * Build with -ffp-contract=off: every fused multiply-add below is explicit.
+ */
+#include "oracle.h"
+
+#include <fcntl.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+enum {
+	PULSE = 5,                 /* adsbdec.h:1  PULSEW, 0.5 us at 10 MS/s */
+	LOOKAHEAD = 240 * PULSE,   /* adsbdec.h:3  DECOFFSET */
+	NTAPS = 14,                /* air.c:32     DSFLTLEN */
+	AMP_FLUSH = 8196 * PULSE,  /* air.c:47     APBUFFSZ */
+	READ_SAMPLES = 1024 * 1024 /* air.c:218    IQBUFFSZ */
+};
+
+/* air.c:36-45: one period of the triangular low-pass.  The reference stores it
+ * twice back to back so that a rotated window can be read without a modulo. */
+static const float taps[NTAPS] = {
+	0.012627f, 0.025254f, 0.037881f, 0.050508f, 0.063135f, 0.075761f, 0.088388f,
+	0.088388f, 0.075761f, 0.063135f, 0.050508f, 0.037881f, 0.025254f, 0.012627f,
+};
+
+struct oracle_ctx {
+	int accept_df18;
+	int fma_contract;
+	/* front end state (air.c:33-34, 49-50) */
+	float ring[NTAPS];
+	uint32_t ring_pos;
+	float amp[AMP_FLUSH + 4];
+	uint32_t amp_fill;
+	uint64_t amp_base;          /* absolute index of amp[0] */
+	/* demod state (demod.c:86) */
+	uint64_t ts;
+	/* stats (valid.c:30-31) */
+	uint32_t tried[32], passed[32];
+	/* results */
+	oracle_frame_t *frames;
+	size_t nframes, capframes;
+	/* optional amp tap */
+	float *tap_dst;
+	size_t tap_cap, tap_n;
+};
+
+/* ---- CRC-24, crc.h:1-42 ------------------------------------------------- */
+
+static uint32_t crc_tab[256];
+static int crc_ready;
+
+static void crc_build(void)
+{
+	/* crc.h:1-34 is the byte-wise table of the Mode S generator 0x1FFF409. */
+	for (int b = 0; b < 256; b++) {
+		uint32_t r = (uint32_t)b << 16;
+		for (int k = 0; k < 8; k++)
+			r = (r & 0x800000) ? ((r << 1) ^ 0xFFF409) : (r << 1);
+		crc_tab[b] = r & 0xFFFFFF;
+	}
+	crc_ready = 1;
+}
+
+const uint32_t *oracle_crc_table(void)
+{
+	if (!crc_ready)
+		crc_build();
+	return crc_tab;
+}
+
+/* valid.c:48-50 / 70-72: CRC over all but the last three bytes, XOR the last
+ * three in, keep 24 bits.  (crc.h:36-38 lets the register grow past 24 bits and
+ * masks once at the end, crc.h:40-42; masking every step is the same value.) */
+static uint32_t syndrome(const uint8_t *msg, int len)
+{
+	uint32_t r = 0;
+	for (int i = 0; i < len - 3; i++)
+		r = ((r << 8) ^ crc_tab[msg[i] ^ ((r >> 16) & 0xFF)]) & 0xFFFFFF;
+	return r ^ ((uint32_t)msg[len - 3] << 16 | (uint32_t)msg[len - 2] << 8 | msg[len - 1]);
+}
+
+/* ---- demodulator, demod.c ----------------------------------------------- */
+
+static void emit(oracle_ctx *c, const uint8_t *msg, int len, uint32_t pw, uint64_t n)
+{
+	if (c->nframes == c->capframes) {
+		c->capframes = c->capframes ? 2 * c->capframes : 1024;
+		c->frames = realloc(c->frames, c->capframes * sizeof *c->frames);
+	}
+	oracle_frame_t *f = &c->frames[c->nframes++];
+	memset(f, 0, sizeof *f);
+	f->ts = c->ts;
+	f->n = n;
+	f->pw = pw;
+	f->len = len;
+	memcpy(f->bytes, msg, (size_t)len);
+}
+
+/* demod.c:31-44: bit k of a byte is "pulse in first half-microsecond". */
+static inline int ppm_bit(const float *a, int at)
+{
+	return a[at] > a[at + PULSE];
+}
+
+/* demod.c:84-144.  Returns how many samples were consumed. */
+static int scan(oracle_ctx *c, const float *a, int have)
+{
+	int at = 0;
+	while (at < have - LOOKAHEAD) {
+		c->ts++;                                                   /* demod.c:99 */
+		/* demod.c:102-105: float sums truncated to int */
+		int p1 = (int)(a[at] + a[at + 2 * PULSE]);
+		int s1 = (int)(a[at + PULSE] + a[at + 3 * PULSE]);
+		int p2 = (int)(a[at + 7 * PULSE] + a[at + 9 * PULSE]);
+		int s2 = (int)(a[at + 6 * PULSE] + a[at + 8 * PULSE]);
+		if (!(p1 > 2 * s1 && p2 > 2 * s2)) {                       /* demod.c:107 */
+			at++;
+			continue;
+		}
+		/* demod.c:46-81: only 10001xxx, 10010xxx (-a) and 01011xxx survive */
+		int d = at + 16 * PULSE;
+		int b7 = ppm_bit(a, d), b6 = ppm_bit(a, d + 10), b5 = ppm_bit(a, d + 20);
+		int b4 = ppm_bit(a, d + 30), b3 = ppm_bit(a, d + 40);
+		int len = 0;
+		if (b7 && !b6 && !b5) {
+			if (b4 && !b3 && c->accept_df18)
+				len = 14;       /* DF18 */
+			else if (!b4 && b3)
+				len = 14;       /* DF17 */
+		} else if (!b7 && b6 && !b5 && b4 && b3) {
+			len = 7;            /* DF11 */
+		}
+		if (!len) {
+			at++;
+			continue;
+		}
+		uint8_t msg[14];
+		for (int i = 0; i < len; i++) {
+			int v = 0;
+			for (int k = 0; k < 8; k++)
+				v = (v << 1) | ppm_bit(a, d + 80 * i + 10 * k);
+			msg[i] = (uint8_t)v;
+		}
+		int df = msg[0] >> 3;
+		c->tried[df]++;                                            /* valid.c:46, 68 */
+		if (syndrome(msg, len) == 0) {
+			c->passed[df]++;
+			emit(c, msg, len, (uint32_t)((p1 + p2) / 4), c->amp_base + (uint64_t)at);
+			at = d + 80 * len;                                     /* demod.c:128, 134 */
+			continue;
+		}
+		at++;
+	}
+	return at;
+}
+
+/* ---- envelope front end, air.c:54-101 ----------------------------------- */
+
+static inline void ring_put(oracle_ctx *c, float v)
+{
+	c->ring[c->ring_pos % NTAPS] = v;   /* air.c:65: uint32 counter, modulo 14 */
+	c->ring_pos++;
+}
+
+static inline float envelope(const oracle_ctx *c)
+{
+	/* air.c:68-74: ascending ring slot; even slots feed I, odd slots feed Q;
+	 * tap for slot k is taps[(k - ring_pos) mod 14]. */
+	unsigned rot = NTAPS - c->ring_pos % NTAPS;
+	float si = 0.0f, sq = 0.0f;
+	for (int k = 0; k < NTAPS; k += 2) {
+		float ti = taps[(k + rot) % NTAPS], tq = taps[(k + 1 + rot) % NTAPS];
+		if (c->fma_contract) {
+			si = fmaf(ti, c->ring[k], si);
+			sq = fmaf(tq, c->ring[k + 1], sq);
+		} else {
+			si = si + ti * c->ring[k];
+			sq = sq + tq * c->ring[k + 1];
+		}
+	}
+	/* air.c:76; gcc -O3 on an FMA target rounds Q*Q, then fuses I*I + that */
+	if (c->fma_contract) {
+		float qq = sq * sq;
+		return fmaf(si, si, qq);
+	}
+	float ii = si * si, qq = sq * sq;
+	return ii + qq;
+}
+
+static inline void amp_put(oracle_ctx *c, float v)
+{
+	c->amp[c->amp_fill++] = v;
+	if (c->tap_dst && c->tap_n < c->tap_cap)
+		c->tap_dst[c->tap_n] = v;
+	c->tap_n++;
+}
+
+void oracle_push(oracle_ctx *c, const uint16_t *buf, int len)
+{
+	for (int i = 0; i < len; i += 4) {
+		/* air.c:64-67, 79-82: centre on mid-scale; the second pair of every
+		 * four is negated (fs/4 mixer). */
+		ring_put(c, (float)buf[i] - 2048.0f);
+		ring_put(c, (float)buf[i + 1] - 2048.0f);
+		amp_put(c, envelope(c));
+		ring_put(c, -((float)buf[i + 2] - 2048.0f));
+		ring_put(c, -((float)buf[i + 3] - 2048.0f));
+		amp_put(c, envelope(c));
+		if (c->amp_fill >= AMP_FLUSH) {                            /* air.c:94-99 */
+			int used = scan(c, c->amp, (int)c->amp_fill);
+			if ((uint32_t)used < c->amp_fill)
+				memmove(c->amp, c->amp + used, (c->amp_fill - (uint32_t)used) * sizeof(float));
+			c->amp_fill -= (uint32_t)used;
+			c->amp_base += (uint64_t)used;
+		}
+	}
+}
+
+/* ---- file / memory drivers, air.c:219-246 -------------------------------- */
+
+void oracle_decode_memory(oracle_ctx *c, const void *data, size_t nbytes)
+{
+	/* one reused 2 MiB buffer; a ragged final read leaves earlier data behind it */
+	uint16_t *buf = calloc(READ_SAMPLES + 4, sizeof *buf);
+	const uint8_t *p = data;
+	while (nbytes > 0) {
+		size_t n = nbytes < READ_SAMPLES * sizeof *buf ? nbytes : READ_SAMPLES * sizeof *buf;
+		memcpy(buf, p, n);
+		oracle_push(c, buf, (int)(n / 2));
+		p += n;
+		nbytes -= n;
+	}
+	free(buf);
+}
+
+int oracle_decode_file(oracle_ctx *c, const char *path)
+{
+	int fd = open(path, O_RDONLY);
+	if (fd < 0)
+		return -1;
+	uint16_t *buf = calloc(READ_SAMPLES + 4, sizeof *buf);
+	for (;;) {
+		ssize_t n = read(fd, buf, READ_SAMPLES * sizeof *buf);
+		if (n <= 0)
+			break;
+		oracle_push(c, buf, (int)(n / 2));
+	}
+	free(buf);
+	close(fd);
+	return 0;
+}
+
+/* ---- bookkeeping --------------------------------------------------------- */
+
+oracle_ctx *oracle_new(int accept_df18, int fma_contract)
+{
+	if (!crc_ready)
+		crc_build();
+	oracle_ctx *c = calloc(1, sizeof *c);
+	c->accept_df18 = accept_df18;
+	c->fma_contract = fma_contract;
+	return c;
+}
+
+void oracle_free(oracle_ctx *c)
+{
+	if (c) {
+		free(c->frames);
+		free(c);
+	}
+}
+
+size_t oracle_num_frames(const oracle_ctx *c) { return c->nframes; }
+const oracle_frame_t *oracle_frames(const oracle_ctx *c) { return c->frames; }
+
+void oracle_stats(const oracle_ctx *c, uint32_t try_[3], uint32_t ok[3])
+{
+	static const int dfs[3] = { 11, 17, 18 };
+	for (int i = 0; i < 3; i++) {
+		try_[i] = c->tried[dfs[i]];
+		ok[i] = c->passed[dfs[i]];
+	}
+}
+
+void oracle_record_amp(oracle_ctx *c, float *dst, size_t capacity)
+{
+	c->tap_dst = dst;
+	c->tap_cap = capacity;
+	c->tap_n = 0;
+}
+
+size_t oracle_amp_count(const oracle_ctx *c) { return c->tap_n; }
+
+/* ---- packet text, output.c:204-262 -------------------------------------- */
+
+int oracle_format(const oracle_frame_t *f, int fmt, char *pkt)
+{
+	static const char hex[] = "0123456789ABCDEF";
+	uint64_t ts12 = f->ts * 12 / 10;                               /* output.c:218 */
+	char *p = pkt;
+	if (fmt == 2) {
+		/* output.c:215-217, WITH_AIR build: double sqrt -> nearbyint -> /8/5 -> uint8 */
+		uint8_t lvl = (uint8_t)(nearbyint(sqrt((double)f->pw)) / 8 / 5);
+		*p++ = 0x1a;
+		*p++ = f->len == 7 ? '2' : '3';
+		for (int sh = 40; sh >= 0; sh -= 8) {
+			char ch = (char)(ts12 >> sh);
+			*p++ = ch;
+			if (ch == 0x1a)
+				*p++ = ch;
+		}
+		*p++ = (char)lvl;                                          /* not escaped, output.c:241 */
+		for (int i = 0; i < f->len; i++) {
+			*p++ = (char)f->bytes[i];
+			if (f->bytes[i] == 0x1a)
+				*p++ = 0x1a;
+		}
+		return (int)(p - pkt);
+	}
+	if (fmt == 1) {
+		*p++ = '@';
+		for (int sh = 44; sh >= 0; sh -= 4)
+			*p++ = hex[(ts12 >> sh) & 0xF];
+	} else {
+		*p++ = '*';
+	}
+	for (int i = 0; i < f->len; i++) {
+		*p++ = hex[f->bytes[i] >> 4];
+		*p++ = hex[f->bytes[i] & 0xF];
+	}
+	*p++ = ';';
+	*p++ = '\n';
+	*p = 0;
+	return (int)(p - pkt);
+}
