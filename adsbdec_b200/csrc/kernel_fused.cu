@@ -1,0 +1,501 @@
+// kernel_fused.cu - the B200 hot path: one persistent kernel that takes raw 16-bit samples from
+// HBM and emits CRC-valid Mode S candidates, with the envelope never leaving the SM.
+//
+// What it computes is exactly the per-offset part of the reference (TLeconte/adsbdec):
+//   air.c:59-92    envelope: fs/4 mixer, 14-tap FIR in ring-slot order, |.|^2, decimate by 2
+//   demod.c:102-107 preamble test on int-truncated pair sums
+//   demod.c:46-81  DF11 / DF17 / DF18 gate on the first five bits
+//   demod.c:31-44  PPM bit decisions
+//   valid.c:39-82, crc.h:36-42  CRC-24 syndrome == 0
+// evaluated at EVERY offset; the sequential rules (greedy skip, ts, tail) are applied by the
+// host resolver on the sparse output.
+//
+// How (see DESIGN.md for the arithmetic identities and the roofline):
+//   * a CTA streams a contiguous span of the capture through shared memory in sub-blocks of
+//     S = 28*NT envelope samples; raw samples arrive by 1-D TMA bulk copies (cp.async.bulk +
+//     mbarrier) into a 2-stage ring, one elected thread issuing;
+//   * stage 1 (FIR): each thread owns 28 consecutive outputs.  28 = lcm(4,7): the ring-slot
+//     rotation of the reference's summation order has period 7 outputs, so with spans cut at
+//     phase 0 every FMA's tap and order is a compile-time constant.  I and Q accumulate as the
+//     two halves of packed fma.rn.f32x2 (the even/odd samples of a 32-bit word ARE the I/Q pair);
+//     u16 -> float by the 0x4B000000 magic-number trick (no I2F);
+//   * stage 2 (bits): per offset two decisions, both as sign bits collected by funnel shifts:
+//       P[n] = (int)(a[n]+a[n+10]) > 2*(int)(a[n+5]+a[n+15])   (floor via add.rm with 2^23)
+//       B[n] = a[n] > a[n+5]
+//     transposed inside 8-lane groups (8 runs of 28 = 7 words of 32) into bit arrays;
+//   * stage 3 (gate): word-parallel: preamble = P[n] & P[n+30]; DF gate = five bits of B at
+//     stride 10; survivors go to a shared-memory list;
+//   * stage 4 (slice+CRC): one warp per survivor; lane l pulls frame bits 4l..4l+3 out of B with
+//     one funnel shift, XORs their single-bit syndromes, warp REDUX.XOR gives the syndrome.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.h"
+#include "kernels.h"
+
+namespace adsb {
+
+namespace {
+
+constexpr int R = 28;               // outputs per thread per sub-block
+constexpr int NT = 256;             // threads per CTA
+constexpr int S = R * NT;           // envelope samples per sub-block (7168)
+constexpr int HIST = 8;             // words of FIR history in front of a raw stage (6 needed)
+constexpr int STAGE_WORDS = S + HIST;
+constexpr int NSTAGE = 2;
+constexpr int LAG2 = 8;             // stage 2 works 8 runs behind the FIR front
+constexpr int LAG3 = 1472;          // stage 3/4 work this many offsets behind the FIR front
+constexpr int RUNS = NT + 56;       // envelope ring, in runs of 28 floats
+constexpr int WR = 512;             // bit-array ring, in 32-bit words
+constexpr int WPB = S / 32;         // bit words per sub-block (224)
+constexpr int CAND_CAP = 1024;      // survivors of the DF gate per sub-block
+constexpr int SYN_WORDS = 112;
+
+static_assert(LAG3 % 32 == 0 && LAG3 >= kLookahead + LAG2 * R + 32 + 8, "stage-3 lag");
+static_assert(RUNS * R >= S + LAG3 + R, "envelope ring too small");
+static_assert(WR * 32 >= S + LAG3 + 2 * kLookahead, "bit ring too small");
+static_assert(NT % 8 == 0 && WPB <= NT, "geometry");
+
+struct Smem {
+	uint32_t raw[NSTAGE][STAGE_WORDS];  // 2 x 28704 B
+	float amp[RUNS * R];                // 34944 B
+	uint32_t pbits[WR];
+	uint32_t bbits[WR];
+	uint32_t cand[CAND_CAP];
+	uint32_t syn[SYN_WORDS];            // single-bit syndromes x^(111-b) mod G
+	unsigned long long full[NSTAGE];    // mbarriers
+	unsigned long long try_base;
+	int ncand;
+	int span;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+	return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+	             : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "WAIT_%=:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	    "@p bra DONE_%=;\n"
+	    "bra WAIT_%=;\n"
+	    "DONE_%=:\n"
+	    "}\n" ::"r"(smem_u32(bar)),
+	    "r"(parity)
+	    : "memory");
+}
+
+// 1-D TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes,
+                                            unsigned long long *bar)
+{
+	asm volatile(
+	    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+	        smem_u32(dst)),
+	    "l"(src), "r"(bytes), "r"(smem_u32(bar))
+	    : "memory");
+}
+
+__device__ __forceinline__ int bfe_s1(uint32_t x, int pos)
+{
+	int r;
+	asm("bfe.s32 %0, %1, %2, 1;" : "=r"(r) : "r"(x), "r"(pos));
+	return r;  // 0 or -1
+}
+
+constexpr float kMagic = 8388608.0f;           // 2^23: float(0x4B000000 | x) == 2^23 + x
+constexpr float kMagicMid = 8388608.0f + 2048.0f;
+
+// Valid word range of one raw stage: wanted words [start, start+STAGE_WORDS) clipped to what the
+// window holds, in multiples of 4 words (16 bytes).
+struct StageRange {
+	long long a, b;  // valid abs words [a, b), possibly empty (a >= b)
+};
+
+__device__ __forceinline__ StageRange stage_range(const FusedSpan &sp, long long start)
+{
+	StageRange r;
+	r.a = start > sp.w_lo ? start : sp.w_lo;
+	long long end = start + STAGE_WORDS;
+	r.b = end < sp.w_hi ? end : sp.w_hi;
+	return r;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(NT, 2) k_fused(const FusedParams p)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+	const int tid = threadIdx.x;
+	const int lane = tid & 31;
+	const int warp = tid >> 5;
+
+	// ---- one-time setup --------------------------------------------------
+	if (tid < SYN_WORDS) {
+		// x^(111-tid) mod G, by shifting x^0 up (crc.h's table is the byte-wise form of this)
+		uint32_t r = 1;
+		for (int i = 0; i < 111 - tid; i++)
+			r = (r & 0x800000u) ? ((r << 1) ^ kCrcPoly) & 0xFFFFFFu : (r << 1);
+		sm.syn[tid] = r;
+	}
+	if (tid == 0) {
+		for (int s = 0; s < NSTAGE; s++)
+			mbar_init(&sm.full[s], 1);
+		sm.ncand = 0;
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	uint32_t phase[NSTAGE] = {0, 0};
+
+	// air.c:36-45 taps paired for a 32-bit word of age g (0 = newest): the even sample (I, low
+	// half) has age 2g+1, the odd sample (Q, high half) age 2g; tap = h[13-age] = h[age].
+	const float h[7] = {0.012627f, 0.025254f, 0.037881f, 0.050508f, 0.063135f, 0.075761f, 0.088388f};
+	float2 tp[7];
+#pragma unroll
+	for (int g = 0; g < 7; g++) {
+		const int ai = 2 * g + 1, aq = 2 * g;  // ages
+		tp[g] = make_float2(h[ai < 7 ? ai : 13 - ai], h[aq < 7 ? aq : 13 - aq]);
+	}
+
+	for (;;) {
+		// ---- fetch a span (dynamic scheduler) ----------------------------
+		if (tid == 0)
+			sm.span = atomicAdd(p.span_ticket, 1);
+		__syncthreads();
+		const int span_idx = sm.span;
+		if (span_idx >= p.n_spans)
+			break;
+		const FusedSpan sp = p.spans[span_idx];
+		const long long jb = sp.j_begin;
+		const int nb = sp.n_blocks;
+		const char *raw0 = reinterpret_cast<const char *>(sp.raw_w0);  // address of abs word 0
+
+		auto issue = [&](int kb, int s) {
+			// elected thread: one bulk copy for the valid part of sub-block kb
+			const long long start = jb - HIST + (long long)kb * S;
+			const StageRange r = stage_range(sp, start);
+			if (r.b > r.a) {
+				const uint32_t bytes = (uint32_t)(r.b - r.a) * 4u;
+				mbar_expect_tx(&sm.full[s], bytes);
+				tma_load_1d(&sm.raw[s][r.a - start], raw0 + 4 * r.a, bytes, &sm.full[s]);
+			} else {
+				mbar_arrive(&sm.full[s]);
+			}
+		};
+		if (tid == 0) {
+			issue(0, 0);
+			if (nb > 1)
+				issue(1, 1);
+		}
+
+		int q_fir = tid;  // ring run of this thread's FIR output, (k*NT + tid) % RUNS
+
+		for (int k = 0; k < nb; k++) {
+			const int s = k & 1;
+			// ================= stage 1: envelope ============================
+			{
+				const long long start = jb - HIST + (long long)k * S;
+				const StageRange r = stage_range(sp, start);
+				// words the window does not hold read as mid-scale: before the stream start the
+				// reference's ring is zero (air.c:33), past the end they are never used
+				const int va = (int)((r.a > start ? r.a : start) - start);
+				const int vb = r.b > r.a ? (int)(r.b - start) : va;
+				const bool partial = (va > 0) || (vb < STAGE_WORDS);
+				if (partial) {
+					for (int i = tid; i < STAGE_WORDS; i += NT)
+						if (i < va || i >= vb)
+							sm.raw[s][i] = 0x08000800u;
+				}
+				mbar_wait(&sm.full[s], phase[s]);
+				phase[s] ^= 1;
+				if (partial)
+					__syncthreads();
+
+				uint32_t w[36];
+				const uint4 *src = reinterpret_cast<const uint4 *>(&sm.raw[s][R * tid]);
+#pragma unroll
+				for (int i = 0; i < 9; i++) {
+					const uint4 t = src[i];
+					w[4 * i] = t.x;
+					w[4 * i + 1] = t.y;
+					w[4 * i + 2] = t.z;
+					w[4 * i + 3] = t.w;
+				}
+				// 12-bit domain check (the float tricks below are exact for samples < 4096)
+				uint32_t any = 0;
+#pragma unroll
+				for (int i = HIST; i < 36; i++)
+					any |= w[i];
+				if (any & 0xF000F000u)
+					p.ctr->wide = 1;
+
+				// u16 pair -> (x-2048) * sign as float2.  Word parity == parity of its index here
+				// (jb, S, R*tid are even): odd words are samples t%4 in {2,3}, negated (air.c:79-82)
+				float2 v[36];
+#pragma unroll
+				for (int L = 2; L < 36; L++) {
+					const float lo = __uint_as_float(__byte_perm(w[L], 0x4B000000u, 0x7610));
+					const float hi = __uint_as_float(__byte_perm(w[L], 0x4B000000u, 0x7632));
+					if (L & 1)
+						v[L] = __ffma2_rn(make_float2(lo, hi), make_float2(-1.0f, -1.0f),
+						                  make_float2(kMagicMid, kMagicMid));
+					else
+						v[L] = __fadd2_rn(make_float2(lo, hi), make_float2(-kMagicMid, -kMagicMid));
+				}
+				float4 *dst = reinterpret_cast<float4 *>(&sm.amp[q_fir * R]);
+				float o[4];
+#pragma unroll
+				for (int r_ = 0; r_ < R; r_++) {
+					// air.c:69-74: ascending ring slot.  Pair-slot kap holds the word of age
+					// (phi - kap) mod 7, phi = r_ % 7 by construction of the span start.
+					const int phi = r_ % 7;
+					const int g0 = phi;  // kap = 0
+					float2 acc = __fmul2_rn(tp[g0], v[HIST + r_ - g0]);
+#pragma unroll
+					for (int kap = 1; kap < 7; kap++) {
+						const int g = (phi - kap + 7) % 7;
+						acc = __ffma2_rn(tp[g], v[HIST + r_ - g], acc);
+					}
+					// air.c:76 as compiled by the reference flags: fma(I, I, round(Q*Q))
+					o[r_ & 3] = __fmaf_rn(acc.x, acc.x, __fmul_rn(acc.y, acc.y));
+					if ((r_ & 3) == 3)
+						dst[r_ >> 2] = make_float4(o[0], o[1], o[2], o[3]);
+				}
+			}
+			__syncthreads();  // (1) envelope visible; raw stage s consumed
+			if (tid == 0 && k + NSTAGE < nb)
+				issue(k + NSTAGE, s);
+
+			// ================= stage 2: decision bits ========================
+			{
+				const int g2 = k * NT + tid - LAG2;  // run handled here (uniform sign per 8-lane group)
+				uint32_t P = 0, B = 0;
+				if (g2 >= 0) {
+					int q2 = q_fir - LAG2;
+					if (q2 < 0) q2 += RUNS;
+					int q2n = q2 + 1;
+					if (q2n == RUNS) q2n = 0;
+					float a[44];
+					const float4 *s0 = reinterpret_cast<const float4 *>(&sm.amp[q2 * R]);
+					const float4 *s1 = reinterpret_cast<const float4 *>(&sm.amp[q2n * R]);
+#pragma unroll
+					for (int i = 0; i < 7; i++) {
+						const float4 t = s0[i];
+						a[4 * i] = t.x; a[4 * i + 1] = t.y; a[4 * i + 2] = t.z; a[4 * i + 3] = t.w;
+					}
+#pragma unroll
+					for (int i = 0; i < 4; i++) {
+						const float4 t = s1[i];
+						a[28 + 4 * i] = t.x; a[29 + 4 * i] = t.y; a[30 + 4 * i] = t.z; a[31 + 4 * i] = t.w;
+					}
+					// f[i] = floor(a[i] + a[i+10]) as a float: demod.c:102-105's (int) of a float sum.
+					// add.rm against 2^23 leaves floor(c) in the mantissa (c >= 0, c < 2^22).
+					float f[34];
+#pragma unroll
+					for (int i = 0; i < 34; i += 2) {
+						const float2 c = __fadd2_rn(make_float2(a[i], a[i + 1]), make_float2(a[i + 10], a[i + 11]));
+						const float2 m = __fadd2_rd(c, make_float2(kMagic, kMagic));
+						const float2 ff = __fadd2_rn(m, make_float2(-kMagic, -kMagic));
+						f[i] = ff.x;
+						f[i + 1] = ff.y;
+					}
+#pragma unroll
+					for (int i = 0; i < R; i++) {
+						// demod.c:107 half-test: p > 2*s  <=>  2*s - p < 0  (exact small integers)
+						const float e = __fmaf_rn(f[i + 5], 2.0f, -f[i]);
+						P = __funnelshift_l(__float_as_uint(e), P, 1);
+						// demod.c:34: a[n] > a[n+5]  <=>  a[n+5] - a[n] < 0  (no FTZ: x-y==0 iff x==y)
+						const float d = __fsub_rn(a[i + 5], a[i]);
+						B = __funnelshift_l(__float_as_uint(d), B, 1);
+					}
+				}
+				// 8 runs x 28 bits -> 7 words x 32 bits inside each 8-lane group (MSB = first offset)
+				const int j = lane & 7;
+				const uint32_t Pn = __shfl_down_sync(0xFFFFFFFFu, P, 1, 8);
+				const uint32_t Bn = __shfl_down_sync(0xFFFFFFFFu, B, 1, 8);
+				if (g2 >= 0 && j < 7) {
+					const uint32_t pw_ = (P << (4 + 4 * j)) | (Pn >> (24 - 4 * j));
+					const uint32_t bw_ = (B << (4 + 4 * j)) | (Bn >> (24 - 4 * j));
+					const int wi = (((g2 - j) >> 3) * 7 + j) & (WR - 1);
+					sm.pbits[wi] = pw_;
+					sm.bbits[wi] = bw_;
+				}
+			}
+			__syncthreads();  // (2) bit arrays visible
+
+			// ================= stage 3: preamble AND + DF gate ===============
+			if (tid < WPB) {
+				const int wd = k * WPB + tid - LAG3 / 32;
+				if (wd >= 0) {
+					const uint32_t p0 = sm.pbits[wd & (WR - 1)], p1 = sm.pbits[(wd + 1) & (WR - 1)];
+					const uint32_t b2 = sm.bbits[(wd + 2) & (WR - 1)], b3 = sm.bbits[(wd + 3) & (WR - 1)],
+					               b4 = sm.bbits[(wd + 4) & (WR - 1)];
+					// demod.c:107: both half-tests, 30 samples apart
+					const uint32_t pre = p0 & __funnelshift_l(p1, p0, 30);
+					if (pre) {
+						// first five data bits sit at n+80, +90, +100, +110, +120 (demod.c:110, :46-81)
+						const uint32_t x7 = __funnelshift_l(b3, b2, 16);  // 80  = 64 + 16
+						const uint32_t x6 = __funnelshift_l(b3, b2, 26);  // 90  = 64 + 26
+						const uint32_t x5 = __funnelshift_l(b4, b3, 4);   // 100 = 96 + 4
+						const uint32_t x4 = __funnelshift_l(b4, b3, 14);  // 110 = 96 + 14
+						const uint32_t x3 = __funnelshift_l(b4, b3, 24);  // 120 = 96 + 24
+						const uint32_t m17 = pre & x7 & ~x6 & ~x5 & ~x4 & x3;               // 10001
+						const uint32_t m18 = p.accept_df18 ? (pre & x7 & ~x6 & ~x5 & x4 & ~x3) : 0u;  // 10010
+						const uint32_t m11 = pre & ~x7 & x6 & ~x5 & x4 & x3;                // 01011
+						uint32_t any = m17 | m18 | m11;
+						while (any) {
+							const int i = __clz(any);
+							const uint32_t bit = 0x80000000u >> i;
+							any &= ~bit;
+							const uint32_t n_rel = (uint32_t)wd * 32u + (uint32_t)i;
+							const long long n = jb + (long long)n_rel;
+							if (n >= sp.own_begin && n < sp.own_end) {
+								const uint32_t cls = (m17 & bit) ? kClsDF17 : (m11 & bit) ? kClsDF11 : kClsDF18;
+								const int slot = atomicAdd(&sm.ncand, 1);
+								if (slot < CAND_CAP)
+									sm.cand[slot] = n_rel | (cls << 30);
+							}
+						}
+					}
+				}
+			}
+			__syncthreads();  // (3) survivor list complete
+
+			// ================= stage 4: slice + CRC, one warp per survivor ===
+			int ncand = sm.ncand;
+			if (ncand > CAND_CAP) {
+				if (tid == 0)
+					atomicOr(&p.ctr->overflow, 4u);
+				ncand = CAND_CAP;
+			}
+			if (p.want_tries && tid == 0 && ncand > 0)
+				sm.try_base = atomicAdd(&p.ctr->n_try, (unsigned long long)ncand);
+			for (int ci = warp; ci < ncand; ci += NT / 32) {
+				const uint32_t ent = sm.cand[ci];
+				const uint32_t n_rel = ent & 0x3FFFFFFFu;
+				const uint32_t cls = ent >> 30;
+				const bool is_long = cls != kClsDF11;
+				const int nnib = is_long ? 28 : 14;
+				uint32_t acc = 0, x = 0;
+				if (lane < nnib) {
+					// frame bit b sits at n + 80 + 10 b; this lane takes b = 4*lane .. 4*lane+3
+					const uint32_t pb = n_rel + 80u + 40u * (uint32_t)lane;
+					const uint32_t wi = pb >> 5;
+					const uint32_t w0 = sm.bbits[wi & (WR - 1)], w1 = sm.bbits[(wi + 1) & (WR - 1)];
+					x = __funnelshift_l(w1, w0, pb & 31u);  // bits 31, 21, 11, 1
+					const uint4 sy = *reinterpret_cast<const uint4 *>(&sm.syn[4 * lane + (is_long ? 0 : 56)]);
+					acc = ((uint32_t)bfe_s1(x, 31) & sy.x) ^ ((uint32_t)bfe_s1(x, 21) & sy.y) ^
+					      ((uint32_t)bfe_s1(x, 11) & sy.z) ^ ((uint32_t)bfe_s1(x, 1) & sy.w);
+				}
+				// valid.c:48-52 / :70-74: CRC over all but the last 3 bytes, XOR the last 3, == 0
+				const uint32_t syndrome = __reduce_xor_sync(0xFFFFFFFFu, acc);
+				if (syndrome == 0) {
+					// nibble of this lane, MSB first, then 8 nibbles -> one big-endian word per 8 lanes
+					const uint32_t y = x & 0x80200802u;
+					const uint32_t nib = lane < nnib ? (y * 0x08040201u) >> 28 : 0u;
+					const uint32_t grp = 0xFFu << (lane & 24);
+					const uint32_t word = __reduce_or_sync(grp, nib << (4 * (7 - (lane & 7))));
+					const uint32_t w0 = __shfl_sync(0xFFFFFFFFu, word, 0), w1 = __shfl_sync(0xFFFFFFFFu, word, 8),
+					               w2 = __shfl_sync(0xFFFFFFFFu, word, 16), w3 = __shfl_sync(0xFFFFFFFFu, word, 24);
+					if (lane == 0) {
+						// demod.c:102-105, :127: pw from the int-truncated preamble sums
+						auto amp_at = [&](uint32_t o) -> float {
+							const uint32_t run = o / R;
+							return sm.amp[(run % RUNS) * R + (o - run * R)];
+						};
+						const int p1 = __float2int_rz(__fadd_rn(amp_at(n_rel), amp_at(n_rel + 10)));
+						const int p2 = __float2int_rz(__fadd_rn(amp_at(n_rel + 35), amp_at(n_rel + 45)));
+						const unsigned long long slot = atomicAdd(&p.ctr->n_cand, 1ull);
+						if (slot < p.cand_cap) {
+							uint4 head, body;
+							const unsigned long long n = (unsigned long long)(jb + (long long)n_rel);
+							head.x = (uint32_t)n;
+							head.y = (uint32_t)(n >> 32);
+							head.z = (uint32_t)((p1 + p2) / 4);
+							head.w = is_long ? 14u : 7u;
+							body.x = __byte_perm(w0, 0, 0x0123);  // big-endian word -> byte order in memory
+							body.y = __byte_perm(w1, 0, 0x0123);
+							body.z = __byte_perm(w2, 0, 0x0123);
+							body.w = __byte_perm(w3, 0, 0x0123);
+							if (!is_long) {
+								body.y &= 0x00FFFFFFu;
+								body.z = 0;
+							}
+							body.w &= 0x0000FFFFu;
+							uint4 *out = reinterpret_cast<uint4 *>(&p.cands[slot]);
+							out[0] = head;
+							out[1] = body;
+						} else {
+							atomicOr(&p.ctr->overflow, 1u);
+						}
+					}
+				}
+			}
+			__syncthreads();  // (4) list consumed; envelope ring may advance
+			if (p.want_tries && ncand > 0) {
+				const unsigned long long base = sm.try_base;
+				for (int i = tid; i < ncand; i += NT) {
+					const uint32_t ent = sm.cand[i];
+					const unsigned long long n = (unsigned long long)(jb + (long long)(ent & 0x3FFFFFFFu));
+					if (base + i < p.try_cap)
+						p.tries[base + i] = ((unsigned long long)(ent >> 30) << kTryClsShift) | n;
+					else
+						atomicOr(&p.ctr->overflow, 2u);
+				}
+			}
+			if (tid == 0)
+				sm.ncand = 0;
+			q_fir += NT;
+			if (q_fir >= RUNS) q_fir -= RUNS;
+		}
+		__syncthreads();
+	}
+}
+
+int fused_block_outputs() { return S; }
+int fused_lookback() { return LAG3; }
+int fused_threads() { return NT; }
+size_t fused_smem_bytes() { return sizeof(Smem); }
+
+int fused_prepare(int device)
+{
+	(void)device;
+	if (cudaFuncSetAttribute(k_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_bytes()) !=
+	    cudaSuccess)
+		return -1;
+	int per_sm = 0;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused, NT, fused_smem_bytes()) != cudaSuccess)
+		return -1;
+	return per_sm;
+}
+
+cudaError_t launch_fused(const FusedParams &p, int grid, cudaStream_t st)
+{
+	if (grid <= 0)
+		return cudaSuccess;
+	k_fused<<<grid, NT, fused_smem_bytes(), st>>>(p);
+	return cudaGetLastError();
+}
+
+}  // namespace adsb

@@ -1,0 +1,63 @@
+// kernels.h - launch interface between the host side (api.cu) and the CUDA kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.h"
+
+namespace adsb {
+
+// ---- generic path (kernels_generic.cu) -----------------------------------
+
+cudaError_t launch_envelope_generic(const uint16_t *raw, long long u_raw0, unsigned long long origin,
+                                    long long j0, long long n, float *amp, cudaStream_t st);
+
+cudaError_t launch_scan_generic(const float *amp, long long j_amp0, long long n0, long long count,
+                                int accept_df18, int want_tries, CandRec *cands,
+                                unsigned long long cand_cap, unsigned long long *tries,
+                                unsigned long long try_cap, Counters *ctr, cudaStream_t st);
+
+cudaError_t launch_count_tries(const unsigned long long *tries, unsigned long long n_tries,
+                               const unsigned long long *spans, int n_spans,
+                               unsigned long long scan_end, unsigned long long *next_tries,
+                               unsigned long long next_cap, Counters *ctr, cudaStream_t st);
+
+// ---- fused path (kernel_fused.cu) -----------------------------------------
+
+// One contiguous run of offsets handled by one CTA of the fused kernel ("span").
+// Word W = the 32-bit pair of local samples (2W, 2W+1) = the newest input of envelope sample W.
+struct FusedSpan {
+	unsigned long long raw_w0;  // device address at which word 0 would sit (16-byte aligned; only
+	                            // words in [w_lo, w_hi) are ever dereferenced)
+	long long w_lo, w_hi;       // words present in the window, multiples of 4; words outside read as
+	                            // mid-scale (before the stream start the FIR ring is zero, air.c:33)
+	long long j_begin;          // first envelope sample computed: multiple of 4 and FIR phase 0
+	long long own_begin;        // candidates are emitted for own_begin <= n < own_end
+	long long own_end;
+	int n_blocks;               // sub-blocks to run (each fused_block_outputs() envelope samples)
+	int pad_;
+};
+
+struct FusedParams {
+	const FusedSpan *spans;
+	int n_spans;
+	int accept_df18;
+	int want_tries;
+	CandRec *cands;
+	unsigned long long cand_cap;
+	unsigned long long *tries;
+	unsigned long long try_cap;
+	Counters *ctr;
+	int *span_ticket;      // dynamic span scheduler (zeroed before launch)
+};
+
+// Geometry the host needs to cut spans.
+int fused_block_outputs();      // envelope samples per sub-block
+int fused_lookback();           // offsets emitted lag the FIR front by this many samples
+int fused_threads();
+size_t fused_smem_bytes();
+// Configures the kernel (max dynamic smem) and reports resident CTAs per SM; <0 on error.
+int fused_prepare(int device);
+cudaError_t launch_fused(const FusedParams &p, int grid, cudaStream_t st);
+
+}  // namespace adsb

@@ -1,0 +1,222 @@
+// kernels_generic.cu - the straightforward ("generic") CUDA formulation of the hot path.
+//
+// One thread per envelope sample / per offset, envelope written to HBM.  It is NOT the fast
+// path (kernel_fused.cu is); it exists because it handles every case with no preconditions:
+//   * the uint32 `fidx` wrap of the FIR ring (air.c:34, :65) - the few outputs whose window
+//     straddles a 2^32-sample boundary,
+//   * samples outside the 12-bit ADC range (the fused kernel's float tricks assume < 4096),
+//   * tiny seams between pushed pieces,
+// and because a second, independent formulation is what the fused kernel is differentially
+// tested against on the GPU.
+//
+// Reference citations are file:line into TLeconte/adsbdec.
+#include "common.h"
+#include "kernels.h"
+
+namespace adsb {
+
+__constant__ float c_taps[kTaps] = ADSB_TAPS_INIT;
+
+static __constant__ CrcTable c_crc = make_crc_table();
+
+// Envelope sample j (local index) of a stream whose local sample u has FIR-ring slot
+// (uint32_t)(u + phase_origin) % 14.   air.c:59-76, SURVEY App. A.
+//
+//   raw      : device pointer to local sample u_raw0
+//   u_limit  : local samples [0, u_limit) exist; u < 0 reads as "ring still zero" (air.c:33)
+//   j0, n    : compute amp[j0 .. j0+n)
+//   amp      : output, amp[0] = envelope sample j0
+__global__ void k_envelope_generic(const uint16_t *__restrict__ raw, long long u_raw0,
+                                   unsigned long long phase_origin, long long j0, long long n,
+                                   float *__restrict__ amp)
+{
+	long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	const long long j = j0 + i;
+	const long long T = 2 * j + 1;  // newest input sample of this output
+	// ring_pos after pushing sample T is T+1 (air.c:65: fidx++ after each store)
+	const uint32_t pos = (uint32_t)((unsigned long long)(T + 1) + phase_origin);
+	const uint32_t rot = kTaps - pos % kTaps;  // air.c:68: o = DSFLTLEN - fidx%DSFLTLEN
+	float si = 0.0f, sq = 0.0f;
+#pragma unroll 1
+	for (int k = 0; k < kTaps; k++) {
+		// slot k holds the newest sample u <= T with (uint32)(u+origin)%14 == k; away from a
+		// 2^32 wrap that is within the last 14 samples, across one it can be up to 17 back.
+		float v = 0.0f;
+		for (int back = 0; back < 32; back++) {
+			long long u = T - back;
+			if (u < 0)
+				break;  // never written: static ring is zero
+			if ((uint32_t)((unsigned long long)u + phase_origin) % kTaps == (uint32_t)k) {
+				float x = (float)raw[u - u_raw0] - 2048.0f;  // air.c:64
+				v = (u & 2) ? -x : x;                        // air.c:79-82: 2nd pair of each 4 negated
+				break;
+			}
+		}
+		float tap = c_taps[(k + rot) % kTaps];  // dsfilter[k+o], the table is one period doubled
+		if (k & 1)
+			sq = __fmaf_rn(tap, v, sq);  // air.c:71 (contracted by the reference's -O3 -march=native)
+		else
+			si = __fmaf_rn(tap, v, si);  // air.c:70
+	}
+	amp[i] = __fmaf_rn(si, si, __fmul_rn(sq, sq));  // air.c:76: vmulss q,q ; vfmadd i,i
+}
+
+__device__ __forceinline__ bool ppm(const float *a, int at)
+{
+	return a[at] > a[at + kPulse];  // demod.c:34
+}
+
+// One thread per offset.  amp[0] is envelope sample j_amp0; offsets [n0, n0+count) are owned.
+// Every owned offset needs amp up to n+1195 (demod.c:89: idx < len-DECOFFSET).
+__global__ void k_scan_generic(const float *__restrict__ amp, long long j_amp0, long long n0,
+                               long long count, int accept_df18, int want_tries, CandRec *cands,
+                               unsigned long long cand_cap, unsigned long long *tries,
+                               unsigned long long try_cap, Counters *ctr)
+{
+	long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+	if (i >= count)
+		return;
+	const long long n = n0 + i;
+	const float *a = amp + (n - j_amp0);
+	// demod.c:102-105: float sums truncated to int
+	int p1 = __float2int_rz(__fadd_rn(a[0], a[2 * kPulse]));
+	int s1 = __float2int_rz(__fadd_rn(a[kPulse], a[3 * kPulse]));
+	if (!(p1 > 2 * s1))
+		return;
+	int p2 = __float2int_rz(__fadd_rn(a[7 * kPulse], a[9 * kPulse]));
+	int s2 = __float2int_rz(__fadd_rn(a[6 * kPulse], a[8 * kPulse]));
+	if (!(p2 > 2 * s2))  // demod.c:107
+		return;
+	// demod.c:46-81: only 10001xxx (DF17), 10010xxx (DF18, -a) and 01011xxx (DF11) go on
+	const int d = 16 * kPulse;
+	bool b7 = ppm(a, d), b6 = ppm(a, d + 10), b5 = ppm(a, d + 20), b4 = ppm(a, d + 30),
+	     b3 = ppm(a, d + 40);
+	int len = 0;
+	uint32_t cls = 0;
+	if (b7 && !b6 && !b5) {
+		if (b4 && !b3 && accept_df18) {
+			len = 14;
+			cls = kClsDF18;
+		} else if (!b4 && b3) {
+			len = 14;
+			cls = kClsDF17;
+		}
+	} else if (!b7 && b6 && !b5 && b4 && b3) {
+		len = 7;
+		cls = kClsDF11;
+	}
+	if (!len)
+		return;
+	if (want_tries) {
+		unsigned long long k = atomicAdd(&ctr->n_try, 1ull);
+		if (k < try_cap)
+			tries[k] = ((unsigned long long)cls << kTryClsShift) | (unsigned long long)n;
+		else
+			atomicOr(&ctr->overflow, 2u);
+	}
+	uint8_t msg[14];
+	uint32_t crc = 0;
+	for (int b = 0; b < len; b++) {
+		uint32_t v = 0;
+		for (int k = 0; k < 8; k++)
+			v = (v << 1) | (ppm(a, d + 80 * b + 10 * k) ? 1u : 0u);  // demod.c:31-44
+		msg[b] = (uint8_t)v;
+		if (b < len - 3)
+			crc = (crc << 8) ^ c_crc.v[v ^ ((crc >> 16) & 0xFFu)];  // crc.h:36-38
+	}
+	crc = (crc & 0xFFFFFFu) ^ ((uint32_t)msg[len - 3] << 16 | (uint32_t)msg[len - 2] << 8 |
+	                           (uint32_t)msg[len - 1]);  // crc.h:40-42
+	if (crc != 0)  // valid.c:52, :74
+		return;
+	unsigned long long k = atomicAdd(&ctr->n_cand, 1ull);
+	if (k >= cand_cap) {
+		atomicOr(&ctr->overflow, 1u);
+		return;
+	}
+	CandRec r;
+	r.n = (uint64_t)n;
+	r.pw = (uint32_t)((p1 + p2) / 4);  // demod.c:127
+	r.len = (uint32_t)len;
+#pragma unroll
+	for (int b = 0; b < 16; b++)
+		r.bytes[b] = b < len ? msg[b] : 0;
+	cands[k] = r;
+}
+
+// Stats pass (valid.c:46, :68 as seen by the sequential scan): a try counts iff the scan visits
+// its offset, i.e. n < scan_end and n is not strictly inside an accepted frame's span.
+// Tries at n >= scan_end are carried to the next list.  spans = [start, end) pairs, sorted.
+__global__ void k_count_tries(const unsigned long long *__restrict__ tries, unsigned long long n_tries,
+                              const unsigned long long *__restrict__ spans, int n_spans,
+                              unsigned long long scan_end, unsigned long long *next_tries,
+                              unsigned long long next_cap, Counters *ctr)
+{
+	unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+	if (i >= n_tries)
+		return;
+	unsigned long long e = tries[i];
+	unsigned long long n = e & kTryMask;
+	uint32_t cls = (uint32_t)(e >> kTryClsShift);
+	if (n >= scan_end) {
+		unsigned long long k = atomicAdd(&ctr->n_try_next, 1ull);
+		if (k < next_cap)
+			next_tries[k] = e;
+		else
+			atomicOr(&ctr->overflow, 2u);
+		return;
+	}
+	// last span with start < n
+	int lo = 0, hi = n_spans;
+	while (lo < hi) {
+		int mid = (lo + hi) >> 1;
+		if (spans[2 * mid] < n)
+			lo = mid + 1;
+		else
+			hi = mid;
+	}
+	if (lo > 0 && n < spans[2 * (lo - 1) + 1])
+		return;  // skipped by `idx = lidx` (demod.c:128, :134)
+	atomicAdd(&ctr->stat_try[cls], 1u);
+}
+
+// ---- launch wrappers -----------------------------------------------------
+
+cudaError_t launch_envelope_generic(const uint16_t *raw, long long u_raw0, unsigned long long origin,
+                                    long long j0, long long n, float *amp, cudaStream_t st)
+{
+	if (n <= 0)
+		return cudaSuccess;
+	const int bs = 256;
+	k_envelope_generic<<<(unsigned)((n + bs - 1) / bs), bs, 0, st>>>(raw, u_raw0, origin, j0, n, amp);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_scan_generic(const float *amp, long long j_amp0, long long n0, long long count,
+                                int accept_df18, int want_tries, CandRec *cands,
+                                unsigned long long cand_cap, unsigned long long *tries,
+                                unsigned long long try_cap, Counters *ctr, cudaStream_t st)
+{
+	if (count <= 0)
+		return cudaSuccess;
+	const int bs = 256;
+	k_scan_generic<<<(unsigned)((count + bs - 1) / bs), bs, 0, st>>>(
+	    amp, j_amp0, n0, count, accept_df18, want_tries, cands, cand_cap, tries, try_cap, ctr);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_count_tries(const unsigned long long *tries, unsigned long long n_tries,
+                               const unsigned long long *spans, int n_spans,
+                               unsigned long long scan_end, unsigned long long *next_tries,
+                               unsigned long long next_cap, Counters *ctr, cudaStream_t st)
+{
+	if (n_tries == 0)
+		return cudaSuccess;
+	const int bs = 256;
+	k_count_tries<<<(unsigned)((n_tries + bs - 1) / bs), bs, 0, st>>>(tries, n_tries, spans, n_spans,
+	                                                                 scan_end, next_tries, next_cap, ctr);
+	return cudaGetLastError();
+}
+
+}  // namespace adsb

@@ -1,0 +1,78 @@
+// resolver.cpp - see resolver.h.
+#include "resolver.h"
+
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.h"
+
+namespace adsb {
+
+void Resolver::scan_to(uint64_t cutoff, std::vector<adsbdec_b200_frame_t> &accepted)
+{
+	// One deqframe(ampbuff, len) call whose loop bound len-DECOFFSET is `cutoff` in absolute
+	// offsets (demod.c:89).  idx starts at ampbuff[0] = base_.
+	uint64_t pos = base_;
+	while (!pending_.empty() && pending_.front().n < cutoff) {
+		const adsbdec_b200_candidate_t c = pending_.front();
+		pending_.pop_front();
+		if (c.n < pos)
+			continue;  // inside the frame just accepted: never evaluated (demod.c:128, :134)
+		const uint64_t skip = c.len == 7 ? kSkipShort : kSkipLong;
+		adsbdec_b200_frame_t f;
+		memset(&f, 0, sizeof f);
+		f.n = c.n;
+		f.ts = c.n + 1 - drift_;  // demod.c:99: one tick per loop iteration, not per sample
+		f.pw = c.pw;
+		f.len = (int32_t)c.len;
+		memcpy(f.bytes, c.bytes, c.len);
+		accepted.push_back(f);
+		drift_ += skip - 1;
+		pos = c.n + skip;  // demod.c:110, :119-123: idx = lidx
+	}
+	base_ = std::max(cutoff, pos);  // deqframe returns idx; air.c:96-98 keeps the rest
+	scan_end_ = cutoff;
+}
+
+void Resolver::run_calls(std::vector<adsbdec_b200_frame_t> &accepted)
+{
+	for (;;) {
+		// air.c:94: the test runs after every 2 envelope samples; the call happens at the first
+		// even sample count P with P - base >= APBUFFSZ.
+		uint64_t call_at = base_ + kAmpFlush;
+		call_at += call_at & 1;
+		if (call_at > total_out_)
+			return;
+		const uint64_t cutoff = call_at - kLookahead;
+		if (cutoff > scanned_upto_)
+			return;  // the GPU has not covered this call's offsets yet
+		scan_to(cutoff, accepted);
+	}
+}
+
+void Resolver::feed(const adsbdec_b200_candidate_t *c, size_t count, uint64_t scanned_upto,
+                    uint64_t total_out, std::vector<adsbdec_b200_frame_t> &accepted)
+{
+	for (size_t i = 0; i < count; i++)
+		pending_.push_back(c[i]);
+	scanned_upto_ = std::max(scanned_upto_, scanned_upto);
+	total_out_ = std::max(total_out_, total_out);
+	run_calls(accepted);
+}
+
+void Resolver::finish(std::vector<adsbdec_b200_frame_t> &accepted)
+{
+	run_calls(accepted);
+	if (!emulate_tail_) {
+		// Non-reference mode: scan every offset that has a complete look-ahead.
+		uint64_t cutoff = std::min(scanned_upto_, total_out_ >= (uint64_t)kLookahead
+		                                              ? total_out_ - kLookahead
+		                                              : 0);
+		if (cutoff > scan_end_)
+			scan_to(cutoff, accepted);
+	}
+	pending_.clear();  // the reference drops whatever is left in ampbuff at EOF (air.c:243-244)
+}
+
+}  // namespace adsb

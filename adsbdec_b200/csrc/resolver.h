@@ -1,0 +1,48 @@
+// resolver.h - the sequential half of demod.c:84-144 and air.c:94-99, applied to the sparse
+// list of CRC-valid candidates the GPU returns.
+//
+// The GPU evaluates every offset independently.  What remains sequential in the reference is
+//   * the greedy skip: after an accepted frame the scan resumes behind it (demod.c:128, :134),
+//   * the timestamp: ts counts loop iterations, not samples (demod.c:86, :99),
+//   * the buffer schedule: deqframe runs whenever >= 40980 envelope samples are queued and
+//     leaves the last 1200 unscanned (air.c:94-99, demod.c:89), so the tail of a capture is
+//     never decoded.
+// All three are O(accepted frames) and are done here on the host.
+#pragma once
+#include <stdint.h>
+
+#include <deque>
+#include <vector>
+
+#include "../../include/adsbdec_b200.h"
+
+namespace adsb {
+
+class Resolver {
+public:
+	explicit Resolver(bool emulate_tail) : emulate_tail_(emulate_tail) {}
+
+	// Candidates in non-decreasing n, complete for all n < scanned_upto.
+	void feed(const adsbdec_b200_candidate_t *c, size_t count, uint64_t scanned_upto, uint64_t total_out,
+	          std::vector<adsbdec_b200_frame_t> &accepted);
+	void finish(std::vector<adsbdec_b200_frame_t> &accepted);
+
+	// Offsets below this have been visited (or skipped) by the emulated scan.
+	uint64_t scan_end() const { return scan_end_; }
+	// Where the next deqframe call would start (= absolute index of ampbuff[0]).
+	uint64_t buffer_start() const { return base_; }
+
+private:
+	void run_calls(std::vector<adsbdec_b200_frame_t> &accepted);
+	void scan_to(uint64_t cutoff, std::vector<adsbdec_b200_frame_t> &accepted);
+
+	bool emulate_tail_;
+	uint64_t base_ = 0;       // absolute index of ampbuff[0] at the next deqframe call
+	uint64_t drift_ = 0;      // iterations saved by skips so far: sum(skip - 1)
+	uint64_t scan_end_ = 0;
+	uint64_t scanned_upto_ = 0;
+	uint64_t total_out_ = 0;
+	std::deque<adsbdec_b200_candidate_t> pending_;
+};
+
+}  // namespace adsb

@@ -1,0 +1,184 @@
+/*
+ * adsbdec_b200.h - C ABI of the B200-native Mode S demodulation path.
+ *
+ * This library replaces, for the `adsbdec -f FILE` path only, the reference's
+ * per-buffer calls into air.c / demod.c / valid.c.  Everything here is plain C:
+ * pointers, sizes, integer return codes (0 = ok, <0 = error, the reference's
+ * convention at air.c:117 and output.c:278-279).  No CUDA or torch types cross
+ * the boundary; device pointers travel as `const void *`.
+ *
+ * Reference interface each entry point stands in for (file:line into the
+ * reference tree, TLeconte/adsbdec):
+ *
+ *   adsbdec_b200_push          static void decodeiq(const unsigned short *r, const int len)   air.c:54
+ *                              (called by fileInput, air.c:239, with 1 Mi-sample buffers)
+ *                              + everything below it: deqframe (adsbdec.h:5, demod.c:84),
+ *                              getdf/getabyte (demod.c:31-81), validShort/validLong
+ *                              (demod.c:28-29, valid.c:39-82)
+ *   adsbdec_b200_finish        end of fileInput's read loop -> handlerExit(0)                  air.c:243-244
+ *   adsbdec_b200_sink_fn       void netout(const uint8_t *frame, const int len,
+ *                                          const uint64_t ts, const uint32_t pw)                output.c:159
+ *   adsbdec_b200_stats         stat_try / stat_ok read by print_stats()                         valid.c:30-31, 84-101
+ *   adsbdec_b200_config.accept_df18   the global `df` set by -a                                 demod.c:26, :59, main.c:76
+ *   adsbdec_b200_format_packet int formatpkt(blk_t *blk, char *pkt) (WITH_AIR build)            output.c:204-262
+ *   adsbdec_b200_decode_file   void *fileInput(void *arg)                                       air.c:219-246
+ *
+ * Semantics that are kept bit-for-bit: float32 envelope
+ * arithmetic incl. FMA contraction of the reference build, int-truncated
+ * preamble sums, DF11/17/18 gate, syndrome==0 acceptance, greedy skip after an
+ * accepted frame, the iteration-count timestamp, and the tail of the capture
+ * that the reference never scans.
+ *
+ * There is NO CPU fallback: every decode entry point fails with
+ * ADSB_B200_ENODEV when no CUDA device can be used.
+ */
+#ifndef ADSBDEC_B200_H
+#define ADSBDEC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADSB_B200_ABI_VERSION 1
+
+/* error codes (all negative) */
+#define ADSB_B200_OK        0
+#define ADSB_B200_EINVAL   -1   /* bad argument (NULL handle, n not a multiple of 4, ...) */
+#define ADSB_B200_ENODEV   -2   /* no usable CUDA device / kernels not built for it      */
+#define ADSB_B200_ECUDA    -3   /* a CUDA call failed; see adsbdec_b200_last_error()     */
+#define ADSB_B200_ENOMEM   -4
+#define ADSB_B200_ESTATE   -5   /* push after finish, ...                                */
+#define ADSB_B200_EIO      -6   /* decode_file: cannot open / read                       */
+#define ADSB_B200_ERANGE   -7   /* output capacity exhausted even after regrow           */
+
+typedef struct adsbdec_b200 adsbdec_b200_t;
+
+/* Frame sink: netout()'s signature (output.c:159) plus a user pointer.  Called on
+ * the thread that calls push()/finish()/decode_*(), in non-decreasing ts order.
+ * `frame` is only valid during the call (netout copies it, output.c:165). */
+typedef void (*adsbdec_b200_sink_fn)(const uint8_t *frame, int len, uint64_t ts,
+                                     uint32_t pw, void *user);
+
+/* One accepted frame, as handed to the sink, plus its absolute 10 MS/s offset. */
+typedef struct {
+	uint64_t ts;        /* deqframe's iteration counter (demod.c:99)              */
+	uint64_t n;         /* absolute output-sample offset of the preamble start    */
+	uint32_t pw;        /* (p1+p2)/4 (demod.c:127)                                */
+	int32_t len;        /* 7 or 14                                                */
+	uint8_t bytes[14];
+	uint8_t pad_[2];
+} adsbdec_b200_frame_t;
+
+typedef struct {
+	int32_t abi_version;             /* ADSB_B200_ABI_VERSION                                    */
+	int32_t device;                  /* CUDA device ordinal                                      */
+	int32_t accept_df18;             /* -a: also decode DF18 (demod.c:59)                        */
+	int32_t emulate_reference_tail;  /* 1: drop the tail the reference never scans (air.c:94-99) */
+	int32_t collect_stats;           /* 1: maintain Try/Ok counters (valid.c:46,53,68,75)        */
+	int32_t kernel;                  /* 0 = auto (fused sm_100a kernel), 1 = generic kernels only */
+	uint64_t batch_samples;          /* host-push staging batch, 0 = default (32 Mi samples)     */
+	uint64_t start_sample;           /* absolute index of the first pushed sample (0 for a file;
+	                                    a time-chunk of a longer capture passes its offset so the
+	                                    FIR rotation / fidx wrap (air.c:34,65) line up)           */
+	uint64_t reserved[4];
+} adsbdec_b200_config_t;
+
+/* Fills *cfg with defaults (device 0, reference-compatible behaviour). */
+void adsbdec_b200_default_config(adsbdec_b200_config_t *cfg);
+
+/* Creates a per-stream decoder on cfg->device.  Returns 0 and *out, or <0. */
+int adsbdec_b200_open(const adsbdec_b200_config_t *cfg, adsbdec_b200_t **out);
+void adsbdec_b200_close(adsbdec_b200_t *h);
+
+int adsbdec_b200_set_sink(adsbdec_b200_t *h, adsbdec_b200_sink_fn fn, void *user);
+
+/* decodeiq(r, len) replacement.  `samples` is caller-owned HOST memory and may be
+ * reused on return.  n must be a multiple of 4 (the reference consumes groups of
+ * four and over-reads otherwise, air.c:59-82; decode_file emulates that case). */
+int adsbdec_b200_push(adsbdec_b200_t *h, const uint16_t *samples, size_t n);
+
+/* Same, with the samples already in DEVICE memory of cfg->device.  The pointer
+ * must stay valid until the call returns. */
+int adsbdec_b200_push_device(adsbdec_b200_t *h, const void *dev_samples, size_t n);
+
+/* End of input: flushes staged samples, resolves and emits the remaining frames. */
+int adsbdec_b200_finish(adsbdec_b200_t *h);
+
+/* fileInput() replacement: 2 MiB reads, ragged-tail emulation, then finish().
+ * A file that cannot be opened yields no frames and returns ADSB_B200_EIO
+ * (the reference prints stats and exits 0, air.c:225-228; the CLI maps it). */
+int adsbdec_b200_decode_file(adsbdec_b200_t *h, const char *path);
+
+/* stat_try / stat_ok for DF 11, 17, 18, in print_stats order (valid.c:88-97). */
+int adsbdec_b200_stats(adsbdec_b200_t *h, uint32_t try_[3], uint32_t ok[3]);
+
+/* Frames accepted so far are also kept in the handle (in ts order). */
+size_t adsbdec_b200_num_frames(const adsbdec_b200_t *h);
+const adsbdec_b200_frame_t *adsbdec_b200_frames(const adsbdec_b200_t *h);
+/* Drop the kept frames (long-running streams). */
+void adsbdec_b200_clear_frames(adsbdec_b200_t *h);
+
+/* Device time (ms, CUDA events on the library's stream) spent in the demodulation
+ * kernels since open / since the last call, and how many kernels were launched. */
+int adsbdec_b200_kernel_time(adsbdec_b200_t *h, double *ms, uint64_t *launches, int reset);
+
+/* Per-kernel timing of the fused kernel alone (for the roofline line). */
+int adsbdec_b200_fused_time(adsbdec_b200_t *h, double *ms, uint64_t *launches,
+                            uint64_t *samples, int reset);
+
+/* formatpkt(): fmt 0 = avr "*HEX;\n", 1 = avrmlat "@TTTTTTTTTTTT HEX;\n" (12 MHz
+ * timestamp = ts*12/10, output.c:218), 2 = beast binary.  pkt must hold 256 bytes
+ * (output.c:267).  Returns the packet length. */
+int adsbdec_b200_format_packet(int fmt, const uint8_t *frame, int len, uint64_t ts,
+                               uint32_t pw, char *pkt);
+
+/* Debug / parity tap: envelope samples amp[first_out .. first_out+count) of a capture
+ * held in device or host memory, computed by the generic kernel (is_device = 0/1).
+ * start_sample as in the config.  Output is HOST float32. */
+int adsbdec_b200_envelope(int device, const void *samples, size_t n_samples, int is_device,
+                          uint64_t start_sample, float *amp_out, size_t count);
+
+/* ---- host-only helpers (no CUDA call; usable without a GPU) -------------- */
+
+/* Sequential semantics of demod.c:84-144 + air.c:94-99 applied to a sorted list of
+ * CRC-valid candidates (greedy skip, ts drift, tail cut-off).  Used by the decoder
+ * itself and exposed so that multi-GPU hosts can merge per-chunk candidate lists. */
+typedef struct adsbdec_b200_resolver adsbdec_b200_resolver_t;
+typedef struct {
+	uint64_t n;          /* absolute offset              */
+	uint32_t pw;
+	uint32_t len;        /* 7 or 14                       */
+	uint8_t bytes[16];   /* first `len` bytes significant */
+} adsbdec_b200_candidate_t;
+
+adsbdec_b200_resolver_t *adsbdec_b200_resolver_new(int emulate_reference_tail);
+void adsbdec_b200_resolver_free(adsbdec_b200_resolver_t *r);
+/* Candidates must arrive in non-decreasing n over the life of the resolver and be
+ * complete for all n < scanned_upto; total_out = envelope samples produced so far. */
+int adsbdec_b200_resolver_feed(adsbdec_b200_resolver_t *r, const adsbdec_b200_candidate_t *c,
+                               size_t count, uint64_t scanned_upto, uint64_t total_out,
+                               adsbdec_b200_sink_fn fn, void *user);
+int adsbdec_b200_resolver_finish(adsbdec_b200_resolver_t *r, adsbdec_b200_sink_fn fn, void *user);
+/* Number of spans accepted so far / copy them ([start, start+skip) pairs). */
+uint64_t adsbdec_b200_resolver_scan_end(const adsbdec_b200_resolver_t *r);
+
+/* Raw candidate access for multi-GPU time-chunking: decode the chunk and return every
+ * CRC-valid candidate whose preamble starts in [own_begin, own_end) (absolute offsets),
+ * WITHOUT applying the sequential rules.  Samples are device-resident, their first
+ * element has absolute index cfg.start_sample.  out must hold cap entries; returns the
+ * count (sorted by n), or <0. */
+int64_t adsbdec_b200_chunk_candidates(adsbdec_b200_t *h, const void *dev_samples, size_t n_samples,
+                                      uint64_t own_begin, uint64_t own_end,
+                                      adsbdec_b200_candidate_t *out, size_t cap,
+                                      uint32_t tries_out[3]);
+
+const char *adsbdec_b200_last_error(void);
+const char *adsbdec_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -267,6 +267,11 @@ oracle_ctx *oracle_new(int accept_df18, int fma_contract)
 	return c;
 }
 
+void oracle_set_origin(oracle_ctx *c, uint64_t origin)
+{
+	c->ring_pos = (uint32_t)origin;
+}
+
 void oracle_free(oracle_ctx *c)
 {
 	if (c) {

@@ -57,6 +57,7 @@ def lib():
         L.oracle_new.restype = C.c_void_p
         L.oracle_new.argtypes = [C.c_int, C.c_int]
         L.oracle_free.argtypes = [C.c_void_p]
+        L.oracle_set_origin.argtypes = [C.c_void_p, C.c_uint64]
         L.oracle_push.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.oracle_decode_file.argtypes = [C.c_void_p, C.c_char_p]
         L.oracle_decode_file.restype = C.c_int
@@ -98,13 +99,15 @@ def format_frame(f: Frame, fmt: int) -> bytes:
 
 
 def decode(samples: np.ndarray, *, accept_df18: bool = False, fma: bool = True,
-           want_amp: bool = False) -> Result:
+           want_amp: bool = False, origin: int = 0) -> Result:
     """Run the sequential restatement over a whole capture (file semantics)."""
     L = lib()
     samples = np.ascontiguousarray(samples, dtype="<u2")
     ctx = L.oracle_new(int(accept_df18), int(fma))
     amp = None
     try:
+        if origin:
+            L.oracle_set_origin(ctx, origin)
         if want_amp:
             amp = np.zeros(samples.size // 2 + 8, dtype=np.float32)
             L.oracle_record_amp(ctx, amp.ctypes.data, amp.size)
@@ -211,9 +214,10 @@ def run_ref_tcp(path, flags=("-b",), binary: Path | None = None, timeout: float 
     return RefRun(b"".join(chunks), r.stderr, r.returncode)
 
 
-def run_amp_probe(path, out_path) -> np.ndarray:
+def run_amp_probe(path, out_path, origin: int = 0) -> np.ndarray:
+    """Envelope stream of the UNMODIFIED air.c (optionally with fidx preset to origin)."""
     p = REF_DIR / "amp_probe"
-    subprocess.run([str(p), str(path), str(out_path)], check=True, timeout=600)
+    subprocess.run([str(p), str(path), str(out_path), str(origin)], check=True, timeout=600)
     return np.fromfile(out_path, dtype=np.float32)
 
 
