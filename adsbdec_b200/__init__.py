@@ -31,7 +31,8 @@ EXPORTS = [
     "adsbdec_b200_kernel_time", "adsbdec_b200_fused_time", "adsbdec_b200_format_packet",
     "adsbdec_b200_envelope", "adsbdec_b200_resolver_new", "adsbdec_b200_resolver_free",
     "adsbdec_b200_resolver_feed", "adsbdec_b200_resolver_finish", "adsbdec_b200_resolver_scan_end",
-    "adsbdec_b200_chunk_candidates", "adsbdec_b200_last_error", "adsbdec_b200_version",
+    "adsbdec_b200_chunk_candidates", "adsbdec_b200_debug_fused", "adsbdec_b200_last_error",
+    "adsbdec_b200_version",
 ]
 
 
@@ -123,8 +124,10 @@ def lib():
         L.adsbdec_b200_resolver_finish.argtypes = [vp, SINK_FN, vp]
         L.adsbdec_b200_resolver_scan_end.argtypes = [vp]
         L.adsbdec_b200_resolver_scan_end.restype = u64
-        L.adsbdec_b200_chunk_candidates.argtypes = [vp, vp, C.c_size_t, u64, u64, vp, C.c_size_t, u32p]
+        L.adsbdec_b200_chunk_candidates.argtypes = [vp, vp, C.c_size_t, u64, u64, u64, vp, C.c_size_t, u32p]
         L.adsbdec_b200_chunk_candidates.restype = C.c_int64
+        L.adsbdec_b200_debug_fused.argtypes = [vp, vp, C.c_size_t, u64, vp, vp, vp, vp, C.c_size_t,
+                                               C.POINTER(C.c_int64)]
         L.adsbdec_b200_last_error.restype = C.c_char_p
         L.adsbdec_b200_version.restype = C.c_char_p
         _lib = L
@@ -200,14 +203,30 @@ class Decoder:
             _check(rc)
         return rc
 
-    def chunk_candidates(self, dev_ptr: int, n_samples: int, own_begin: int, own_end: int,
+    def chunk_candidates(self, dev_ptr: int, n_samples: int, start_sample: int, own_begin: int, own_end: int,
                          cap: int = 1 << 20):
+        """Every CRC-valid candidate starting in [own_begin, own_end) (chunk-local offsets)."""
         out = np.zeros(cap, dtype=CAND_DTYPE)
         tries = (C.c_uint32 * 3)()
-        n = lib().adsbdec_b200_chunk_candidates(self._h, C.c_void_p(dev_ptr), n_samples, own_begin, own_end,
-                                                out.ctypes.data, cap, tries)
+        n = lib().adsbdec_b200_chunk_candidates(self._h, C.c_void_p(dev_ptr), n_samples, start_sample,
+                                                own_begin, own_end, out.ctypes.data, cap, tries)
         _check(int(n))
         return out[:n], tuple(tries)
+
+    def debug_fused(self, samples: np.ndarray, count: int, start_sample: int = 0):
+        """(j_begin, amp, p_bits, q_bits, b_bits) as the fused kernel computed them (parity tap)."""
+        a = np.ascontiguousarray(samples, dtype="<u2")
+        count -= count % 32
+        amp = np.zeros(count, dtype=np.float32)
+        pw = np.zeros(count // 32, dtype=np.uint32)
+        qw = np.zeros(count // 32, dtype=np.uint32)
+        bw = np.zeros(count // 32, dtype=np.uint32)
+        jb = C.c_int64()
+        _check(lib().adsbdec_b200_debug_fused(self._h, a.ctypes.data, a.size, start_sample, amp.ctypes.data,
+                                              pw.ctypes.data, qw.ctypes.data, bw.ctypes.data, count,
+                                              C.byref(jb)))
+        unpack = lambda w: np.unpackbits(w.astype(">u4").view(np.uint8)).astype(bool)
+        return jb.value, amp, unpack(pw), unpack(qw), unpack(bw)
 
     @property
     def frames_array(self) -> np.ndarray:

@@ -75,6 +75,7 @@ struct adsbdec_b200 {
 	cudaEvent_t ev_fa = nullptr, ev_fb = nullptr;
 
 	// stream position (local sample / offset indices, 0 = first sample ever pushed)
+	unsigned long long origin = 0;  // absolute index of local sample 0 (FIR phase / fidx wrap)
 	int64_t pushed = 0;      // samples received
 	int64_t own_next = 0;    // first offset the GPU has not scanned yet
 	bool finished = false;
@@ -117,6 +118,11 @@ struct adsbdec_b200 {
 	uint64_t launches = 0, fused_launches = 0, fused_samples = 0;
 
 	std::vector<adsbdec_b200_candidate_t> cand_tmp;
+
+	// parity taps of the fused kernel (adsbdec_b200_debug_fused)
+	float *dbg_amp = nullptr;
+	unsigned int *dbg_p = nullptr, *dbg_q = nullptr, *dbg_b = nullptr;
+	long long dbg_n = 0, dbg_jb = 0;
 };
 
 namespace {
@@ -166,7 +172,7 @@ int launch_generic(adsbdec_b200 *h, const uint16_t *buf, int64_t u0, int64_t n0,
 		CU(cudaMalloc(&h->d_amp, (size_t)(kAmpChunk + kLookahead) * sizeof(float)));
 	for (int64_t c0 = n0; c0 < n1; c0 += kAmpChunk) {
 		const int64_t cnt = std::min(kAmpChunk, n1 - c0);
-		CU(launch_envelope_generic(buf, u0, h->cfg.start_sample, c0, cnt + kLookahead, h->d_amp, h->st));
+		CU(launch_envelope_generic(buf, u0, h->origin, c0, cnt + kLookahead, h->d_amp, h->st));
 		CU(launch_scan_generic(h->d_amp, c0, c0, cnt, h->cfg.accept_df18, h->cfg.collect_stats,
 		                       h->d_cands, h->cand_cap, h->d_tries[h->try_cur], h->try_cap, h->d_ctr,
 		                       h->st));
@@ -179,7 +185,7 @@ int launch_generic(adsbdec_b200 *h, const uint16_t *buf, int64_t u0, int64_t n0,
 // windows of outputs [j0, j1)?  Those outputs go through the generic kernel.
 bool wrap_in_range(const adsbdec_b200 *h, int64_t j0, int64_t j1, int64_t *wrap_out)
 {
-	const unsigned long long org = h->cfg.start_sample;
+	const unsigned long long org = h->origin;
 	const unsigned long long a = (unsigned long long)std::max<int64_t>(0, 2 * j0 - 32) + org;
 	const unsigned long long b = (unsigned long long)(2 * j1 + 32) + org;
 	if ((a >> 32) == (b >> 32))
@@ -198,7 +204,7 @@ int launch_fused_range(adsbdec_b200 *h, const uint16_t *buf, int64_t u0, int64_t
 	// shift = (origin - epoch_base) mod 14.  A span must start on an output j with
 	// (2j + shift) % 14 == 0 (summation order becomes a compile-time constant per thread) and
 	// j % 4 == 0 (16-byte aligned bulk copies): j = r (mod 28).
-	const unsigned long long org = h->cfg.start_sample;
+	const unsigned long long org = h->origin;
 	const unsigned long long epoch_base = ((unsigned long long)(2 * n0) + org) & ~0xFFFFFFFFull;
 	const int shift = (int)(((org % 14ull) + 14ull - (epoch_base % 14ull)) % 14ull);
 	int r = -1;
@@ -254,6 +260,13 @@ int launch_fused_range(adsbdec_b200 *h, const uint16_t *buf, int64_t u0, int64_t
 	p.try_cap = h->try_cap;
 	p.ctr = h->d_ctr;
 	p.span_ticket = h->d_ticket;
+	p.dbg_amp = h->dbg_amp;
+	p.dbg_p = h->dbg_p;
+	p.dbg_q = h->dbg_q;
+	p.dbg_b = h->dbg_b;
+	p.dbg_n = h->dbg_n;
+	if (h->dbg_amp)
+		h->dbg_jb = h->h_fspans[0].j_begin;
 	CU(cudaEventRecord(h->ev_fa, h->st));
 	CU(launch_fused(p, std::min(h->fused_ctas, n_sp), h->st));
 	CU(cudaEventRecord(h->ev_fb, h->st));
@@ -509,6 +522,7 @@ int adsbdec_b200_open(const adsbdec_b200_config_t *cfg, adsbdec_b200_t **out)
 	if (!h)
 		return fail(ADSB_B200_ENOMEM, "out of memory");
 	h->cfg = *cfg;
+	h->origin = cfg->start_sample;
 	h->device = cfg->device;
 	h->batch = cfg->batch_samples ? (int64_t)cfg->batch_samples : kDefaultBatch;
 	h->batch = std::max<int64_t>(h->batch, 1 << 17);
@@ -834,21 +848,23 @@ int adsbdec_b200_envelope(int device, const void *samples, size_t n_samples, int
 }
 
 int64_t adsbdec_b200_chunk_candidates(adsbdec_b200_t *h, const void *dev_samples, size_t n_samples,
-                                      uint64_t own_begin, uint64_t own_end,
+                                      uint64_t start_sample, uint64_t own_begin, uint64_t own_end,
                                       adsbdec_b200_candidate_t *out, size_t cap, uint32_t tries_out[3])
 {
 	if (!h || !dev_samples || (!out && cap))
 		return fail(ADSB_B200_EINVAL, "null argument");
 	if (own_end < own_begin || (own_end + kLookahead) * 2 > n_samples)
 		return fail(ADSB_B200_EINVAL, "owned range needs 1200 envelope samples of look-ahead in the chunk");
-	if (((uintptr_t)dev_samples % 16) != 0)
-		return fail(ADSB_B200_EINVAL, "chunk must be 16-byte aligned");
+	if (((uintptr_t)dev_samples % 16) != 0 || start_sample % 4)
+		return fail(ADSB_B200_EINVAL, "chunk must be 16-byte aligned and start on a multiple of 4 samples");
 	CU(cudaSetDevice(h->device));
-	const unsigned long long saved = h->try_carried;
+	const unsigned long long saved = h->try_carried, saved_origin = h->origin;
 	h->try_carried = 0;
+	h->origin = start_sample;
 	int rc = scan_range(h, (const uint16_t *)dev_samples, 0, (int64_t)n_samples, (int64_t)own_begin,
 	                    (int64_t)own_end);
 	h->try_carried = saved;
+	h->origin = saved_origin;
 	if (rc) return rc;
 	if (h->cand_tmp.size() > cap)
 		return fail(ADSB_B200_ERANGE, "output capacity %zu < %zu candidates", cap, h->cand_tmp.size());
@@ -867,6 +883,62 @@ int64_t adsbdec_b200_chunk_candidates(adsbdec_b200_t *h, const void *dev_samples
 		}
 	}
 	return (int64_t)h->cand_tmp.size();
+}
+
+int adsbdec_b200_debug_fused(adsbdec_b200_t *h, const uint16_t *samples, size_t n_samples,
+                             uint64_t start_sample, float *amp_out, uint32_t *p_out, uint32_t *q_out,
+                             uint32_t *b_out, size_t count, int64_t *j_begin_out)
+{
+	if (!h || !samples || !amp_out || !p_out || !q_out || !b_out || count % 32)
+		return fail(ADSB_B200_EINVAL, "bad argument");
+	if (h->fused_ctas <= 0)
+		return fail(ADSB_B200_ENODEV, "fused kernel not configured");
+	CU(cudaSetDevice(h->device));
+	const int64_t n1 = (int64_t)(n_samples / 2) - kLookahead;
+	if (n1 <= 0)
+		return fail(ADSB_B200_EINVAL, "capture too short");
+	uint16_t *d_raw = nullptr;
+	CU(cudaMalloc(&d_raw, (n_samples + 64) * sizeof(uint16_t)));
+	CU(cudaMemcpy(d_raw, samples, n_samples * sizeof(uint16_t), cudaMemcpyHostToDevice));
+	CU(cudaMalloc(&h->dbg_amp, count * sizeof(float)));
+	CU(cudaMalloc(&h->dbg_p, count / 8));
+	CU(cudaMalloc(&h->dbg_q, count / 8));
+	CU(cudaMalloc(&h->dbg_b, count / 8));
+	CU(cudaMemset(h->dbg_amp, 0, count * sizeof(float)));
+	CU(cudaMemset(h->dbg_p, 0, count / 8));
+	CU(cudaMemset(h->dbg_q, 0, count / 8));
+	CU(cudaMemset(h->dbg_b, 0, count / 8));
+	h->dbg_n = (long long)count;
+	const unsigned long long saved_origin = h->origin;
+	const int saved_ctas = h->fused_ctas;
+	h->origin = start_sample;
+	h->fused_ctas = 1;  // one CTA, so span 0 covers the head of the capture in order
+	k_set_counters<<<1, 1, 0, h->st>>>(h->d_ctr, 0, h->try_carried, 0, 1);
+	int rc = launch_fused_range(h, d_raw, 0, (int64_t)n_samples, 0, n1);
+	h->origin = saved_origin;
+	h->fused_ctas = saved_ctas;
+	cudaError_t e = cudaStreamSynchronize(h->st);
+	if (rc == 0 && e == cudaSuccess) {
+		cudaMemcpy(amp_out, h->dbg_amp, count * sizeof(float), cudaMemcpyDeviceToHost);
+		cudaMemcpy(p_out, h->dbg_p, count / 8, cudaMemcpyDeviceToHost);
+		cudaMemcpy(q_out, h->dbg_q, count / 8, cudaMemcpyDeviceToHost);
+		cudaMemcpy(b_out, h->dbg_b, count / 8, cudaMemcpyDeviceToHost);
+		if (j_begin_out) *j_begin_out = h->dbg_jb;
+	}
+	cudaFree(h->dbg_amp);
+	cudaFree(h->dbg_p);
+	cudaFree(h->dbg_q);
+	cudaFree(h->dbg_b);
+	cudaFree(d_raw);
+	h->dbg_amp = nullptr;
+	h->dbg_p = h->dbg_q = h->dbg_b = nullptr;
+	h->dbg_n = 0;
+	k_set_counters<<<1, 1, 0, h->st>>>(h->d_ctr, 0, h->try_carried, 0, 1);
+	cudaStreamSynchronize(h->st);
+	if (rc) return rc;
+	if (e != cudaSuccess)
+		return fail(ADSB_B200_ECUDA, "debug_fused: %s", cudaGetErrorString(e));
+	return 0;
 }
 
 /* ---- host-only helpers ---------------------------------------------------- */

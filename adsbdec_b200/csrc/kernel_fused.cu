@@ -20,10 +20,12 @@
 //     two halves of packed fma.rn.f32x2 (the even/odd samples of a 32-bit word ARE the I/Q pair);
 //     u16 -> float by the 0x4B000000 magic-number trick (no I2F);
 //   * stage 2 (bits): per offset two decisions, both as sign bits collected by funnel shifts:
-//       P[n] = (int)(a[n]+a[n+10]) > 2*(int)(a[n+5]+a[n+15])   (floor via add.rm with 2^23)
-//       B[n] = a[n] > a[n+5]
+//       with f[n] = (int)(a[n]+a[n+10])  (floor via add.rm against 2^23):
+//       P[n] = f[n] > 2*f[n+5]      (pulse pair at n, n+10 against the gap pair at n+5, n+15)
+//       Q[n] = f[n+5] > 2*f[n]      (the mirrored test; the preamble is P[n] & Q[n+30])
+//       B[n] = a[n] > a[n+5]        (PPM bit decision)
 //     transposed inside 8-lane groups (8 runs of 28 = 7 words of 32) into bit arrays;
-//   * stage 3 (gate): word-parallel: preamble = P[n] & P[n+30]; DF gate = five bits of B at
+//   * stage 3 (gate): word-parallel: preamble = P[n] & Q[n+30]; DF gate = five bits of B at
 //     stride 10; survivors go to a shared-memory list;
 //   * stage 4 (slice+CRC): one warp per survivor; lane l pulls frame bits 4l..4l+3 out of B with
 //     one funnel shift, XORs their single-bit syndromes, warp REDUX.XOR gives the syndrome.
@@ -59,8 +61,9 @@ static_assert(NT % 8 == 0 && WPB <= NT, "geometry");
 struct Smem {
 	uint32_t raw[NSTAGE][STAGE_WORDS];  // 2 x 28704 B
 	float amp[RUNS * R];                // 34944 B
-	uint32_t pbits[WR];
-	uint32_t bbits[WR];
+	uint32_t pbits[WR];                 // P[n]: first pulse pair beats its gap
+	uint32_t qbits[WR];                 // Q[n]: pulse at n+5.. beats the gap at n..
+	uint32_t bbits[WR];                 // B[n]: PPM decision
 	uint32_t cand[CAND_CAP];
 	uint32_t syn[SYN_WORDS];            // single-bit syndromes x^(111-b) mod G
 	unsigned long long full[NSTAGE];    // mbarriers
@@ -279,8 +282,14 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const FusedParams p)
 					}
 					// air.c:76 as compiled by the reference flags: fma(I, I, round(Q*Q))
 					o[r_ & 3] = __fmaf_rn(acc.x, acc.x, __fmul_rn(acc.y, acc.y));
-					if ((r_ & 3) == 3)
+					if ((r_ & 3) == 3) {
 						dst[r_ >> 2] = make_float4(o[0], o[1], o[2], o[3]);
+						if (p.dbg_amp && span_idx == 0) {
+							const long long at = (long long)k * S + R * tid + (r_ - 3);
+							if (at + 4 <= p.dbg_n)
+								*reinterpret_cast<float4 *>(&p.dbg_amp[at]) = make_float4(o[0], o[1], o[2], o[3]);
+						}
+					}
 				}
 			}
 			__syncthreads();  // (1) envelope visible; raw stage s consumed
@@ -290,7 +299,7 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const FusedParams p)
 			// ================= stage 2: decision bits ========================
 			{
 				const int g2 = k * NT + tid - LAG2;  // run handled here (uniform sign per 8-lane group)
-				uint32_t P = 0, B = 0;
+				uint32_t P = 0, Q = 0, B = 0;
 				if (g2 >= 0) {
 					int q2 = q_fir - LAG2;
 					if (q2 < 0) q2 += RUNS;
@@ -322,9 +331,13 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const FusedParams p)
 					}
 #pragma unroll
 					for (int i = 0; i < R; i++) {
-						// demod.c:107 half-test: p > 2*s  <=>  2*s - p < 0  (exact small integers)
+						// demod.c:107, first half: p1 > 2*s1 with p1 = f[n], s1 = f[n+5]
+						//   <=> 2*s1 - p1 < 0 (exact small integers, so the sign bit is the answer)
 						const float e = __fmaf_rn(f[i + 5], 2.0f, -f[i]);
 						P = __funnelshift_l(__float_as_uint(e), P, 1);
+						// second half, as seen from m = n+30: p2 = f[m+5] > 2*s2, s2 = f[m]
+						const float e2 = __fmaf_rn(f[i], 2.0f, -f[i + 5]);
+						Q = __funnelshift_l(__float_as_uint(e2), Q, 1);
 						// demod.c:34: a[n] > a[n+5]  <=>  a[n+5] - a[n] < 0  (no FTZ: x-y==0 iff x==y)
 						const float d = __fsub_rn(a[i + 5], a[i]);
 						B = __funnelshift_l(__float_as_uint(d), B, 1);
@@ -333,13 +346,24 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const FusedParams p)
 				// 8 runs x 28 bits -> 7 words x 32 bits inside each 8-lane group (MSB = first offset)
 				const int j = lane & 7;
 				const uint32_t Pn = __shfl_down_sync(0xFFFFFFFFu, P, 1, 8);
+				const uint32_t Qn = __shfl_down_sync(0xFFFFFFFFu, Q, 1, 8);
 				const uint32_t Bn = __shfl_down_sync(0xFFFFFFFFu, B, 1, 8);
 				if (g2 >= 0 && j < 7) {
 					const uint32_t pw_ = (P << (4 + 4 * j)) | (Pn >> (24 - 4 * j));
+					const uint32_t qw_ = (Q << (4 + 4 * j)) | (Qn >> (24 - 4 * j));
 					const uint32_t bw_ = (B << (4 + 4 * j)) | (Bn >> (24 - 4 * j));
 					const int wi = (((g2 - j) >> 3) * 7 + j) & (WR - 1);
 					sm.pbits[wi] = pw_;
+					sm.qbits[wi] = qw_;
 					sm.bbits[wi] = bw_;
+					if (p.dbg_p && span_idx == 0) {
+						const long long at = (long long)((g2 - j) >> 3) * 7 + j;
+						if (at < p.dbg_n / 32) {
+							p.dbg_p[at] = pw_;
+							p.dbg_q[at] = qw_;
+							p.dbg_b[at] = bw_;
+						}
+					}
 				}
 			}
 			__syncthreads();  // (2) bit arrays visible
@@ -348,11 +372,12 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const FusedParams p)
 			if (tid < WPB) {
 				const int wd = k * WPB + tid - LAG3 / 32;
 				if (wd >= 0) {
-					const uint32_t p0 = sm.pbits[wd & (WR - 1)], p1 = sm.pbits[(wd + 1) & (WR - 1)];
+					const uint32_t p0 = sm.pbits[wd & (WR - 1)];
+					const uint32_t q0 = sm.qbits[wd & (WR - 1)], q1 = sm.qbits[(wd + 1) & (WR - 1)];
 					const uint32_t b2 = sm.bbits[(wd + 2) & (WR - 1)], b3 = sm.bbits[(wd + 3) & (WR - 1)],
 					               b4 = sm.bbits[(wd + 4) & (WR - 1)];
-					// demod.c:107: both half-tests, 30 samples apart
-					const uint32_t pre = p0 & __funnelshift_l(p1, p0, 30);
+					// demod.c:107: p1 > 2*s1 at n, p2 > 2*s2 at n+30
+					const uint32_t pre = p0 & __funnelshift_l(q1, q0, 30);
 					if (pre) {
 						// first five data bits sit at n+80, +90, +100, +110, +120 (demod.c:110, :46-81)
 						const uint32_t x7 = __funnelshift_l(b3, b2, 16);  // 80  = 64 + 16

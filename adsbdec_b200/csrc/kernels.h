@@ -49,6 +49,10 @@ struct FusedParams {
 	unsigned long long try_cap;
 	Counters *ctr;
 	int *span_ticket;      // dynamic span scheduler (zeroed before launch)
+	// parity taps (all null in production): envelope / bit arrays of span 0, indexed from its j_begin
+	float *dbg_amp;
+	unsigned int *dbg_p, *dbg_q, *dbg_b;
+	long long dbg_n;       // capacity of dbg_amp in samples (dbg_p/q/b hold dbg_n/32 words)
 };
 
 // Geometry the host needs to cut spans.

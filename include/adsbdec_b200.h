@@ -141,6 +141,18 @@ int adsbdec_b200_format_packet(int fmt, const uint8_t *frame, int len, uint64_t 
 int adsbdec_b200_envelope(int device, const void *samples, size_t n_samples, int is_device,
                           uint64_t start_sample, float *amp_out, size_t count);
 
+/* Debug / parity tap of the FUSED kernel: runs it over a host capture with one CTA and returns,
+ * for the first `count` (multiple of 32) offsets from *j_begin_out, the envelope it computed in
+ * shared memory and its three decision bit arrays (MSB of word 0 = offset j_begin), with
+ * f[n] = (int)(a[n]+a[n+10]):
+ *   p bit n = f[n] > 2*f[n+5]      (demod.c:102-107: p1 > 2*s1 at offset n)
+ *   q bit n = f[n+5] > 2*f[n]      (demod.c:102-107: p2 > 2*s2 at offset n-30)
+ *   b bit n = a[n] > a[n+5]        (demod.c:34)
+ * Bits are only complete for offsets the kernel's stage 2 reached (all but the last ~2000). */
+int adsbdec_b200_debug_fused(adsbdec_b200_t *h, const uint16_t *samples, size_t n_samples,
+                             uint64_t start_sample, float *amp_out, uint32_t *p_out, uint32_t *q_out,
+                             uint32_t *b_out, size_t count, int64_t *j_begin_out);
+
 /* ---- host-only helpers (no CUDA call; usable without a GPU) -------------- */
 
 /* Sequential semantics of demod.c:84-144 + air.c:94-99 applied to a sorted list of
@@ -165,13 +177,18 @@ int adsbdec_b200_resolver_finish(adsbdec_b200_resolver_t *r, adsbdec_b200_sink_f
 /* Number of spans accepted so far / copy them ([start, start+skip) pairs). */
 uint64_t adsbdec_b200_resolver_scan_end(const adsbdec_b200_resolver_t *r);
 
-/* Raw candidate access for multi-GPU time-chunking: decode the chunk and return every
- * CRC-valid candidate whose preamble starts in [own_begin, own_end) (absolute offsets),
- * WITHOUT applying the sequential rules.  Samples are device-resident, their first
- * element has absolute index cfg.start_sample.  out must hold cap entries; returns the
- * count (sorted by n), or <0. */
+/* Raw candidate access for multi-GPU time-chunking: scan one chunk of a longer
+ * capture and return every CRC-valid candidate whose preamble starts in [own_begin, own_end)
+ * (offsets LOCAL to the chunk: 0 = its first sample pair), WITHOUT applying the sequential
+ * rules - the host merges chunk lists by offset and runs the resolver once.  The chunk is
+ * device-resident and 16-byte aligned; start_sample (multiple of 4) is the absolute index of
+ * its first sample in the capture, so that the FIR rotation and the fidx wrap (air.c:34, :65)
+ * line up.  History before the chunk reads as zero, so own_begin must be >= 8 unless the chunk
+ * starts the capture; own_end + 1200 envelope samples must lie inside the chunk.  out must
+ * hold cap entries; returns the count (sorted by n), or <0.  tries_out: gate-passing offsets
+ * per DF class in the owned range (no sequential exclusion in chunk mode). */
 int64_t adsbdec_b200_chunk_candidates(adsbdec_b200_t *h, const void *dev_samples, size_t n_samples,
-                                      uint64_t own_begin, uint64_t own_end,
+                                      uint64_t start_sample, uint64_t own_begin, uint64_t own_end,
                                       adsbdec_b200_candidate_t *out, size_t cap,
                                       uint32_t tries_out[3]);
 

@@ -43,8 +43,9 @@ def all_offset_candidates(amp: np.ndarray, accept_df18: bool, n_end: int | None 
         return np.zeros(0, dtype=CAND_DTYPE), np.zeros((0, 2), dtype=np.int64)
     c = (a[:-10] + a[10:]).astype(np.float32)        # a[n] + a[n+10]
     ci = c.astype(np.int64)                          # (int) truncation of a non-negative float
-    half = ci[:-5] > 2 * ci[5:]                      # p > 2*s
-    pre = half[:n_end] & half[30:30 + n_end]
+    p_half = ci[:-5] > 2 * ci[5:]                    # p1 > 2*s1: pulses at n, n+10, gap at n+5, n+15
+    q_half = ci[5:] > 2 * ci[:-5]                    # p2 > 2*s2 seen from m=n+30: pulses at m+5, m+15
+    pre = p_half[:n_end] & q_half[30:30 + n_end]
     bit = a[:-5] > a[5:]                             # a[q] > a[q+5]
     b7, b6, b5, b4, b3 = (bit[80 + 10 * k:80 + 10 * k + n_end] for k in range(5))
     m17 = pre & b7 & ~b6 & ~b5 & ~b4 & b3
