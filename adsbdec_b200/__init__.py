@@ -25,7 +25,8 @@ SINK_FN = C.CFUNCTYPE(None, C.POINTER(C.c_uint8), C.c_int, C.c_uint64, C.c_uint3
 
 # every symbol include/adsbdec_b200.h declares (checked by the CPU test-suite)
 EXPORTS = [
-    "adsbdec_b200_default_config", "adsbdec_b200_open", "adsbdec_b200_close", "adsbdec_b200_set_sink",
+    "adsbdec_b200_default_config", "adsbdec_b200_open", "adsbdec_b200_close", "adsbdec_b200_reset",
+    "adsbdec_b200_set_sink",
     "adsbdec_b200_push", "adsbdec_b200_push_device", "adsbdec_b200_finish", "adsbdec_b200_decode_file",
     "adsbdec_b200_stats", "adsbdec_b200_num_frames", "adsbdec_b200_frames", "adsbdec_b200_clear_frames",
     "adsbdec_b200_kernel_time", "adsbdec_b200_fused_time", "adsbdec_b200_format_packet",
@@ -100,6 +101,7 @@ def lib():
         L.adsbdec_b200_open.argtypes = [C.POINTER(Config), C.POINTER(vp)]
         L.adsbdec_b200_close.argtypes = [vp]
         L.adsbdec_b200_close.restype = None
+        L.adsbdec_b200_reset.argtypes = [vp, u64]
         L.adsbdec_b200_set_sink.argtypes = [vp, SINK_FN, vp]
         L.adsbdec_b200_push.argtypes = [vp, vp, C.c_size_t]
         L.adsbdec_b200_push_device.argtypes = [vp, vp, C.c_size_t]
@@ -185,6 +187,10 @@ class Decoder:
         self._cb = SINK_FN(tramp)
         _check(lib().adsbdec_b200_set_sink(self._h, self._cb, None))
 
+    def reset(self, start_sample: int = 0) -> None:
+        """Back to an empty stream, buffers kept."""
+        _check(lib().adsbdec_b200_reset(self._h, start_sample))
+
     def push(self, samples: np.ndarray) -> None:
         a = np.ascontiguousarray(samples, dtype="<u2")
         _check(lib().adsbdec_b200_push(self._h, a.ctypes.data, a.size))
@@ -237,6 +243,10 @@ class Decoder:
         p = L.adsbdec_b200_frames(self._h)
         buf = (C.c_uint8 * (n * FRAME_DTYPE.itemsize)).from_address(p)
         return np.frombuffer(buf, dtype=FRAME_DTYPE).copy()
+
+    @property
+    def num_frames(self) -> int:
+        return int(lib().adsbdec_b200_num_frames(self._h))
 
     @property
     def frames(self) -> list[Frame]:

@@ -595,6 +595,37 @@ void adsbdec_b200_close(adsbdec_b200_t *h)
 	delete h;
 }
 
+int adsbdec_b200_reset(adsbdec_b200_t *h, uint64_t start_sample)
+{
+	if (!h)
+		return fail(ADSB_B200_EINVAL, "null handle");
+	if (start_sample % 4)
+		return fail(ADSB_B200_EINVAL, "start_sample must be a multiple of 4");
+	CU(cudaSetDevice(h->device));
+	CU(cudaStreamSynchronize(h->st));
+	h->origin = start_sample;
+	h->cfg.start_sample = start_sample;
+	h->pushed = 0;
+	h->own_next = 0;
+	h->finished = false;
+	h->cur = 0;
+	h->win_u0 = 0;
+	h->win_off = kCarryMax;
+	h->dev_fill = 0;
+	h->pin_fill = 0;
+	h->try_cur = 0;
+	h->try_carried = 0;
+	delete h->res;
+	h->res = new Resolver(h->cfg.emulate_reference_tail != 0);
+	h->frames.clear();
+	h->emitted = 0;
+	for (int i = 0; i < 3; i++)
+		h->stat_ok[i] = 0;
+	CU(cudaMemset(h->d_ctr, 0, sizeof(Counters)));
+	memset(h->h_ctr, 0, sizeof(Counters));
+	return 0;
+}
+
 int adsbdec_b200_set_sink(adsbdec_b200_t *h, adsbdec_b200_sink_fn fn, void *user)
 {
 	if (!h)

@@ -93,6 +93,10 @@ void adsbdec_b200_default_config(adsbdec_b200_config_t *cfg);
 int adsbdec_b200_open(const adsbdec_b200_config_t *cfg, adsbdec_b200_t **out);
 void adsbdec_b200_close(adsbdec_b200_t *h);
 
+/* Rewinds the handle to an empty stream (fidx = start_sample, ts = 0, counters 0) and keeps
+ * its buffers: what restarting the reference process on another file does. */
+int adsbdec_b200_reset(adsbdec_b200_t *h, uint64_t start_sample);
+
 int adsbdec_b200_set_sink(adsbdec_b200_t *h, adsbdec_b200_sink_fn fn, void *user);
 
 /* decodeiq(r, len) replacement.  `samples` is caller-owned HOST memory and may be
