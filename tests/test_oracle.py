@@ -1,0 +1,133 @@
+"""CPU: the oracle (oracle/oracle.c) against the golden vectors produced by the UNMODIFIED
+reference binaries (tests/golden/make_golden.py), and - when oracle/_ref is present and runs on
+this host - against the reference itself on fresh captures."""
+import hashlib
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import DF_MIX_ALL, capture_basic
+
+GOLDEN = sorted((Path(__file__).parent / "golden").glob("*.npz"))
+
+
+def load(p):
+    z = np.load(p)
+    d = {k: z[k] for k in z.files}
+    for k in ("avr", "avrmlat", "avrmlat_a", "beast_a"):
+        d[k] = d[k].tobytes()
+    d["amp_sha256"] = str(d["amp_sha256"])
+    return d
+
+
+def oracle_run(oracle, g, df18, **kw):
+    """File semantics: the reference reads ceil(n/4)*4 samples, the ragged tail being stale
+    buffer content = zeros for a file shorter than one 2 MiB read (air.c:233-239)."""
+    return oracle.decode(g["samples"], accept_df18=df18, **kw)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[p.stem for p in GOLDEN])
+def test_oracle_matches_reference_golden(oracle, path):
+    g = load(path)
+    r = oracle_run(oracle, g, False)
+    assert r.text(0) == g["avr"]
+    assert r.text(1) == g["avrmlat"]
+    assert [list(r.tried), list(r.ok)] == g["stats"].tolist()
+    ra = oracle_run(oracle, g, True)
+    assert ra.text(1) == g["avrmlat_a"]
+    assert ra.text(2) == g["beast_a"]
+    assert [list(ra.tried), list(ra.ok)] == g["stats_a"].tolist()
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[p.stem for p in GOLDEN])
+def test_oracle_envelope_matches_reference_golden(oracle, path):
+    g = load(path)
+    r = oracle_run(oracle, g, False, want_amp=True)
+    n = int(g["amp_len"])
+    assert r.amp.size >= n
+    assert np.array_equal(r.amp[:4096].view(np.uint32), g["amp_head"].view(np.uint32))
+    assert hashlib.sha256(r.amp[:n].tobytes()).hexdigest() == g["amp_sha256"]
+
+
+def test_golden_set_is_present():
+    assert {p.stem for p in GOLDEN} >= {"df17_20db", "mix_errors", "dense", "snr8", "ragged_tail"}
+
+
+def test_crc_table_and_known_answer(oracle):
+    """crc.h:1-34 is the byte table of generator 0xFFF409; the published DF17 frame has syndrome 0."""
+    tab = oracle.crc_table()
+    for b in (0, 1, 2, 0x80, 0xFF):
+        r = b << 16
+        for _ in range(8):
+            r = ((r << 1) ^ 0xFFF409) if r & 0x800000 else (r << 1)
+        assert tab[b] == r & 0xFFFFFF
+    assert tab[1] == 0xFFF409 and tab[255] == 0xFA0480      # crc.h first / last non-trivial entries
+    msg = bytes.fromhex("8D4840D6202CC371C32CE0576098")
+    crc = 0
+    for v in msg[:11]:
+        crc = ((crc << 8) ^ int(tab[v ^ ((crc >> 16) & 0xFF)])) & 0xFFFFFF
+    assert crc ^ int.from_bytes(msg[11:], "big") == 0
+
+
+def _ref_or_skip(oracle):
+    b = oracle.ref_binary()
+    if b is None:
+        pytest.skip("oracle/_ref not built or not runnable on this host")
+    return b
+
+
+def _run_ref_complete(oracle, path, flags, tcp=False):
+    for _ in range(50):         # EOF race of the reference, see make_golden.py
+        r = (oracle.run_ref_tcp if tcp else oracle.run_ref)(path, flags=flags)
+        t, k = r.stats()
+        if tcp or r.stdout.count(b"\n") == sum(k):
+            return r
+    raise AssertionError("reference kept dropping frames")
+
+
+def test_oracle_vs_live_reference(oracle, tmp_path):
+    _ref_or_skip(oracle)
+    cap = capture_basic(seed=5, seconds=0.3, n_frames=120, pad=1 << 21)
+    f = tmp_path / "c.bin"
+    cap.tofile(f)
+    for flags, df18, fmt in ((("-m",), False, 1), (("-a", "-m"), True, 1), ((), False, 0)):
+        ref = _run_ref_complete(oracle, f, flags)
+        r = oracle.decode(cap.samples, accept_df18=df18)
+        assert r.text(fmt) == ref.stdout
+        assert (r.tried, r.ok) == ref.stats()
+
+
+def test_oracle_vs_live_reference_no_padding_tail(oracle, tmp_path):
+    """air.c:94-99: whatever is left in ampbuff at EOF is never scanned."""
+    _ref_or_skip(oracle)
+    cap = capture_basic(seed=6, seconds=0.05, n_frames=40, pad=0)
+    for cut in (0, 4, 40000, 123456):
+        s = cap.samples[:cap.samples.size - cut]
+        f = tmp_path / f"t{cut}.bin"
+        s.astype("<u2").tofile(f)
+        ref = _run_ref_complete(oracle, f, ("-a", "-m"))
+        r = oracle.decode(s, accept_df18=True)
+        assert (r.tried, r.ok) == ref.stats()
+        assert r.text(1) == ref.stdout
+
+
+def test_oracle_envelope_vs_probe_across_fidx_wrap(oracle, tmp_path):
+    """air.c:34,65: uint32 fidx; white-box probe presets it (oracle/probe/amp_probe.c)."""
+    _ref_or_skip(oracle)
+    cap = capture_basic(seed=7, seconds=0.01, n_frames=4, pad=0)
+    f = tmp_path / "w.bin"
+    cap.tofile(f)
+    for origin in (0, 2**32 - 50000, 7 * 2**32 - 10):
+        amp = oracle.run_amp_probe(f, tmp_path / "a.f32", origin)
+        r = oracle.decode(cap.samples, want_amp=True, origin=origin)
+        assert np.array_equal(amp.view(np.uint32), r.amp[:amp.size].view(np.uint32))
+
+
+def test_fma_flavour_differs(oracle):
+    """FMA-contracted and uncontracted builds differ bitwise; parity follows the
+    reference's own flags (-O3 -march=native => contracted)."""
+    cap = capture_basic(seed=8, seconds=0.01, n_frames=4, pad=0)
+    a = oracle.decode(cap.samples, want_amp=True, fma=True).amp
+    b = oracle.decode(cap.samples, want_amp=True, fma=False).amp
+    assert 0.2 < np.mean(a.view(np.uint32) != b.view(np.uint32)) < 0.8
