@@ -5,6 +5,12 @@
 // (air.c:219-246, :54-101; demod.c:84-144; valid.c:39-82; output.c:159).  The host keeps the
 // stream position, carries the un-scanned tail between batches the way air.c:96-98 carries
 // ampbuff, and calls the sink in timestamp order on the caller's thread.
+//
+// Execution model: the stream is cut into batches; every batch becomes one scan JOB (kernels +
+// result copies, all asynchronous on the compute stream).  Two jobs can be in flight: while the
+// GPU scans batch k and the copy engine uploads batch k+1, the host sorts / resolves / emits the
+// results of batch k-1.  The Try/Ok statistics pass of a job runs on the GPU after the job has
+// been resolved (it needs the accepted spans), without any host round trip.
 #include <errno.h>
 #include <fcntl.h>
 #include <stdarg.h>
@@ -14,6 +20,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <new>
 #include <vector>
 
 #include "../../include/adsbdec_b200.h"
@@ -44,25 +51,46 @@ int fail(int code, const char *fmt, ...)
 			            __FILE__, __LINE__);                                                   \
 	} while (0)
 
+#define RC(call)          \
+	do {                  \
+		int rc_ = (call); \
+		if (rc_)          \
+			return rc_;   \
+	} while (0)
+
 constexpr int64_t kCarryBack = 128;        // raw samples kept in front of the next owned offset
 constexpr int64_t kCarryMax = 1 << 14;     // room in front of a batch for the carried tail
 constexpr int64_t kDefaultBatch = 32ll << 20;
 constexpr int64_t kAmpChunk = 8ll << 20;   // generic path: offsets per envelope scratch pass
-constexpr int64_t kMinFused = 1 << 16;     // windows smaller than this use the generic kernels
+constexpr int64_t kMinFused = 1 << 16;     // ranges smaller than this use the generic kernels
+constexpr int64_t kStageSlice = 4ll << 20; // pageable pushes are staged and uploaded in slices
+constexpr unsigned long long kSpecCands = 1ull << 15;  // candidates copied back speculatively
+constexpr unsigned long long kPendCap = 1ull << 18;
+constexpr int kSlots = 2;
 
-__global__ void k_set_counters(Counters *c, unsigned long long n_cand, unsigned long long n_try,
-                               unsigned long long n_try_next, int clear_flags)
+__global__ void k_reset_counters(Counters *c)
 {
-	c->n_cand = n_cand;
-	c->n_try = n_try;
-	c->n_try_next = n_try_next;
-	if (clear_flags) {
-		c->overflow = 0;
-		c->wide = 0;
-	}
+	c->n_cand = 0;
+	c->n_try = 0;
+	c->overflow = 0;
+	c->wide = 0;
 }
 
+__global__ void k_zero_u64(unsigned long long *p) { *p = 0; }
+
 inline int64_t align_down(int64_t v, int64_t a) { return v - (((v % a) + a) % a); }
+
+// One scan of offsets [n0, n1) over a device window, possibly still running.
+struct Job {
+	bool active = false;
+	const uint16_t *buf = nullptr;  // window: buf[0] is local sample u0, samples up to u1 present
+	int64_t u0 = 0, u1 = 0;
+	int64_t n0 = 0, n1 = 0;         // offsets scanned (n1 <= n0: nothing, only a resolver feed)
+	int64_t total_out = 0;          // envelope samples that exist once this window is in
+	unsigned long long origin = 0;
+	bool used_fused = false;
+	bool resolve = true;            // feed the stream resolver on completion
+};
 
 }  // namespace
 
@@ -70,47 +98,57 @@ struct adsbdec_b200 {
 	adsbdec_b200_config_t cfg;
 	int device = 0;
 	cudaStream_t st = nullptr;       // kernels + result copies
-	cudaStream_t st_copy = nullptr;  // H2D of sample batches
-	cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_copy[2] = {nullptr, nullptr};
-	cudaEvent_t ev_fa = nullptr, ev_fb = nullptr;
+	cudaStream_t st_copy = nullptr;  // uploads of sample batches
+	unsigned long long origin = 0;   // absolute index of local sample 0 (FIR phase / fidx wrap)
 
 	// stream position (local sample / offset indices, 0 = first sample ever pushed)
-	unsigned long long origin = 0;  // absolute index of local sample 0 (FIR phase / fidx wrap)
 	int64_t pushed = 0;      // samples received
-	int64_t own_next = 0;    // first offset the GPU has not scanned yet
+	int64_t own_next = 0;    // first offset not yet handed to a scan job
 	bool finished = false;
 
-	// current batch under construction: dev[cur] holds [carry | batch samples]
+	// batch windows: dev[i] holds [carried tail | batch samples]
 	int64_t batch = 0;       // capacity in samples
 	uint16_t *pin[2] = {nullptr, nullptr};
 	uint16_t *dev[2] = {nullptr, nullptr};
+	cudaEvent_t ev_dev_free[2] = {nullptr, nullptr};  // last reader of dev[i] (job + carry copy) done
+	cudaEvent_t ev_pin_free[2] = {nullptr, nullptr};  // last upload out of pin[i] done
+	cudaEvent_t ev_h2d = nullptr;
 	int cur = 0;
 	int64_t win_u0 = 0;      // local index of the first sample held in dev[cur] (carry start)
 	int64_t win_off = 0;     // element offset in dev[cur] where local sample win_u0 sits
-	int64_t dev_fill = 0;    // samples of the window already on the device (incl. carry)
-	int64_t pin_fill = 0;    // samples staged in pin[cur], not yet copied
+	int64_t dev_fill = 0;    // samples of the window whose upload has been issued (incl. carry)
+	int64_t pin_pos = 0;     // next free element of pin[cur] in this window
+	int64_t pin_fill = 0;    // samples staged at pin[cur][pin_pos - pin_fill ..), upload not issued
 
-	// outputs
-	CandRec *d_cands = nullptr, *h_cands = nullptr;
-	unsigned long long cand_cap = 0;
-	unsigned long long *d_tries[2] = {nullptr, nullptr};
-	unsigned long long try_cap = 0;
-	int try_cur = 0;
-	unsigned long long try_carried = 0;
-	Counters *d_ctr = nullptr, *h_ctr = nullptr;
+	// per-slot job state and result buffers
+	Job job[kSlots];
+	int next_slot = 0;
+	Counters *d_ctr[kSlots] = {nullptr, nullptr}, *h_ctr[kSlots] = {nullptr, nullptr};
+	CandRec *d_cands[kSlots] = {nullptr, nullptr}, *h_cands[kSlots] = {nullptr, nullptr};
+	unsigned long long cand_cap[kSlots] = {0, 0};
+	unsigned long long *d_tries[kSlots] = {nullptr, nullptr};
+	unsigned long long try_cap[kSlots] = {0, 0};
+	unsigned long long *d_spans[kSlots] = {nullptr, nullptr}, *h_spans[kSlots] = {nullptr, nullptr};
+	size_t span_cap[kSlots] = {0, 0};
+	FusedSpan *d_fspans[kSlots] = {nullptr, nullptr}, *h_fspans[kSlots] = {nullptr, nullptr};
+	int fspan_cap[kSlots] = {0, 0};
+	int *d_ticket[kSlots] = {nullptr, nullptr};
+	cudaEvent_t ev_done[kSlots] = {nullptr, nullptr};
+	cudaEvent_t ev_a[kSlots] = {nullptr, nullptr}, ev_b[kSlots] = {nullptr, nullptr};
+	cudaEvent_t ev_fa[kSlots] = {nullptr, nullptr}, ev_fb[kSlots] = {nullptr, nullptr};
+
+	// statistics
+	StreamStats *d_stats = nullptr, *h_stats = nullptr;
+	unsigned long long *d_pend[2] = {nullptr, nullptr};
+	int pend_in = 0;
+
 	float *d_amp = nullptr;
-	unsigned long long *d_spans = nullptr, *h_spans = nullptr;
-	size_t span_cap = 0;
-	FusedSpan *d_fspans = nullptr, *h_fspans = nullptr;
-	int *d_ticket = nullptr;
-	int fspan_cap = 0;
 	int fused_ctas = 0;      // grid size of the fused kernel (0 = unavailable)
 
 	Resolver *res = nullptr;
 	std::vector<adsbdec_b200_frame_t> frames;
 	size_t emitted = 0;
 	uint32_t stat_ok[3] = {0, 0, 0};
-	uint32_t raw_tries[3] = {0, 0, 0};
 	adsbdec_b200_sink_fn sink = nullptr;
 	void *sink_user = nullptr;
 
@@ -118,6 +156,7 @@ struct adsbdec_b200 {
 	uint64_t launches = 0, fused_launches = 0, fused_samples = 0;
 
 	std::vector<adsbdec_b200_candidate_t> cand_tmp;
+	std::vector<uint32_t> bucket;
 
 	// parity taps of the fused kernel (adsbdec_b200_debug_fused)
 	float *dbg_amp = nullptr;
@@ -127,55 +166,48 @@ struct adsbdec_b200 {
 
 namespace {
 
-int alloc_outputs(adsbdec_b200 *h, unsigned long long cand_cap, unsigned long long try_cap)
+int alloc_slot_outputs(adsbdec_b200 *h, int s, unsigned long long cand_cap, unsigned long long try_cap)
 {
-	if (h->d_cands) cudaFree(h->d_cands);
-	if (h->h_cands) cudaFreeHost(h->h_cands);
-	h->d_cands = nullptr;
-	h->h_cands = nullptr;
-	CU(cudaMalloc(&h->d_cands, cand_cap * sizeof(CandRec)));
-	CU(cudaMallocHost(&h->h_cands, cand_cap * sizeof(CandRec)));
-	h->cand_cap = cand_cap;
-	if (try_cap != h->try_cap) {
-		for (int i = 0; i < 2; i++) {
-			unsigned long long *nt = nullptr;
-			CU(cudaMalloc(&nt, try_cap * sizeof(unsigned long long)));
-			if (h->d_tries[i]) {
-				if (i == h->try_cur && h->try_carried)
-					CU(cudaMemcpy(nt, h->d_tries[i], h->try_carried * sizeof(unsigned long long),
-					              cudaMemcpyDeviceToDevice));
-				cudaFree(h->d_tries[i]);
-			}
-			h->d_tries[i] = nt;
-		}
-		h->try_cap = try_cap;
+	if (cand_cap != h->cand_cap[s]) {
+		if (h->d_cands[s]) cudaFree(h->d_cands[s]);
+		if (h->h_cands[s]) cudaFreeHost(h->h_cands[s]);
+		h->d_cands[s] = nullptr;
+		h->h_cands[s] = nullptr;
+		CU(cudaMalloc(&h->d_cands[s], cand_cap * sizeof(CandRec)));
+		CU(cudaMallocHost(&h->h_cands[s], cand_cap * sizeof(CandRec)));
+		h->cand_cap[s] = cand_cap;
+	}
+	if (try_cap != h->try_cap[s]) {
+		if (h->d_tries[s]) cudaFree(h->d_tries[s]);
+		h->d_tries[s] = nullptr;
+		CU(cudaMalloc(&h->d_tries[s], try_cap * sizeof(unsigned long long)));
+		h->try_cap[s] = try_cap;
 	}
 	return 0;
 }
 
-int ensure_batch_buffers(adsbdec_b200 *h)
+int ensure_batch_buffers(adsbdec_b200 *h, bool need_pinned)
 {
-	if (h->dev[0])
-		return 0;
 	for (int i = 0; i < 2; i++) {
-		CU(cudaMalloc(&h->dev[i], (size_t)(kCarryMax + h->batch + 64) * sizeof(uint16_t)));
-		CU(cudaMallocHost(&h->pin[i], (size_t)h->batch * sizeof(uint16_t)));
+		if (!h->dev[i])
+			CU(cudaMalloc(&h->dev[i], (size_t)(kCarryMax + h->batch + 64) * sizeof(uint16_t)));
+		if (need_pinned && !h->pin[i])
+			CU(cudaMallocHost(&h->pin[i], (size_t)h->batch * sizeof(uint16_t)));
 	}
 	return 0;
 }
 
-// Launches the scan of offsets [n0, n1) over a device window (buf[0] = local sample u0, samples up
-// to u1 present) with the generic kernels.  Counters must have been set by the caller.
-int launch_generic(adsbdec_b200 *h, const uint16_t *buf, int64_t u0, int64_t n0, int64_t n1)
+// ---- kernel launches of one job ----------------------------------------------------------
+
+int launch_generic(adsbdec_b200 *h, int s, const Job &j, int64_t n0, int64_t n1)
 {
 	if (!h->d_amp)
 		CU(cudaMalloc(&h->d_amp, (size_t)(kAmpChunk + kLookahead) * sizeof(float)));
 	for (int64_t c0 = n0; c0 < n1; c0 += kAmpChunk) {
 		const int64_t cnt = std::min(kAmpChunk, n1 - c0);
-		CU(launch_envelope_generic(buf, u0, h->origin, c0, cnt + kLookahead, h->d_amp, h->st));
-		CU(launch_scan_generic(h->d_amp, c0, c0, cnt, h->cfg.accept_df18, h->cfg.collect_stats,
-		                       h->d_cands, h->cand_cap, h->d_tries[h->try_cur], h->try_cap, h->d_ctr,
-		                       h->st));
+		CU(launch_envelope_generic(j.buf, j.u0, j.origin, c0, cnt + kLookahead, h->d_amp, h->st));
+		CU(launch_scan_generic(h->d_amp, c0, c0, cnt, h->cfg.accept_df18, h->cfg.collect_stats, h->d_cands[s],
+		                       h->cand_cap[s], h->d_tries[s], h->try_cap[s], h->d_ctr[s], h->st));
 		h->launches += 2;
 	}
 	return 0;
@@ -183,9 +215,8 @@ int launch_generic(adsbdec_b200 *h, const uint16_t *buf, int64_t u0, int64_t n0,
 
 // Does a 2^32 boundary of the reference's `fidx` (air.c:34) fall where it would disturb the FIR
 // windows of outputs [j0, j1)?  Those outputs go through the generic kernel.
-bool wrap_in_range(const adsbdec_b200 *h, int64_t j0, int64_t j1, int64_t *wrap_out)
+bool wrap_in_range(unsigned long long org, int64_t j0, int64_t j1, int64_t *wrap_out)
 {
-	const unsigned long long org = h->origin;
 	const unsigned long long a = (unsigned long long)std::max<int64_t>(0, 2 * j0 - 32) + org;
 	const unsigned long long b = (unsigned long long)(2 * j1 + 32) + org;
 	if ((a >> 32) == (b >> 32))
@@ -196,7 +227,7 @@ bool wrap_in_range(const adsbdec_b200 *h, int64_t j0, int64_t j1, int64_t *wrap_
 }
 
 // Cuts [n0, n1) into spans for the fused kernel and launches it.  Requires no fidx wrap in range.
-int launch_fused_range(adsbdec_b200 *h, const uint16_t *buf, int64_t u0, int64_t u1, int64_t n0, int64_t n1)
+int launch_fused_range(adsbdec_b200 *h, int s, const Job &j, int64_t n0, int64_t n1)
 {
 	const int S = fused_block_outputs();
 	const int lookback = fused_lookback();
@@ -204,7 +235,7 @@ int launch_fused_range(adsbdec_b200 *h, const uint16_t *buf, int64_t u0, int64_t
 	// shift = (origin - epoch_base) mod 14.  A span must start on an output j with
 	// (2j + shift) % 14 == 0 (summation order becomes a compile-time constant per thread) and
 	// j % 4 == 0 (16-byte aligned bulk copies): j = r (mod 28).
-	const unsigned long long org = h->origin;
+	const unsigned long long org = j.origin;
 	const unsigned long long epoch_base = ((unsigned long long)(2 * n0) + org) & ~0xFFFFFFFFull;
 	const int shift = (int)(((org % 14ull) + 14ull - (epoch_base % 14ull)) % 14ull);
 	int r = -1;
@@ -222,141 +253,102 @@ int launch_fused_range(adsbdec_b200 *h, const uint16_t *buf, int64_t u0, int64_t
 	per = std::min<int64_t>(per, 1ll << 29);
 	per = (per + S - 1) / S * S;
 	const int n_sp = (int)((total + per - 1) / per);
-	if (n_sp > h->fspan_cap) {
-		if (h->d_fspans) cudaFree(h->d_fspans);
-		if (h->h_fspans) cudaFreeHost(h->h_fspans);
-		h->fspan_cap = n_sp + 64;
-		CU(cudaMalloc(&h->d_fspans, h->fspan_cap * sizeof(FusedSpan)));
-		CU(cudaMallocHost(&h->h_fspans, h->fspan_cap * sizeof(FusedSpan)));
+	if (n_sp > h->fspan_cap[s]) {
+		if (h->d_fspans[s]) cudaFree(h->d_fspans[s]);
+		if (h->h_fspans[s]) cudaFreeHost(h->h_fspans[s]);
+		h->fspan_cap[s] = n_sp + 64;
+		CU(cudaMalloc(&h->d_fspans[s], h->fspan_cap[s] * sizeof(FusedSpan)));
+		CU(cudaMallocHost(&h->h_fspans[s], h->fspan_cap[s] * sizeof(FusedSpan)));
 	}
-	if (!h->d_ticket)
-		CU(cudaMalloc(&h->d_ticket, sizeof(int)));
-	if (u0 % 8 || ((uintptr_t)buf % 16))
+	if (!h->d_ticket[s])
+		CU(cudaMalloc(&h->d_ticket[s], sizeof(int)));
+	if (j.u0 % 8 || ((uintptr_t)j.buf % 16))
 		return fail(ADSB_B200_EINVAL, "internal: fused window not 16-byte aligned");
-	const int64_t w_lo = u0 / 2, w_hi = align_down(u1 / 2, 4);
+	const int64_t w_lo = j.u0 / 2, w_hi = align_down(j.u1 / 2, 4);
 	for (int i = 0; i < n_sp; i++) {
-		FusedSpan &sp = h->h_fspans[i];
+		FusedSpan &sp = h->h_fspans[s][i];
 		sp.own_begin = n0 + i * per;
 		sp.own_end = std::min<int64_t>(n1, sp.own_begin + per);
 		sp.j_begin = align_down(sp.own_begin - r, 28) + r;  // at or before own_begin, == r (mod 28)
-		if (sp.j_begin - 8 < w_lo && u0 != 0)
+		if (sp.j_begin - 8 < w_lo && j.u0 != 0)
 			return fail(ADSB_B200_EINVAL, "internal: window lacks FIR history");
-		sp.raw_w0 = (unsigned long long)(uintptr_t)buf - 2ull * (unsigned long long)u0;
+		sp.raw_w0 = (unsigned long long)(uintptr_t)j.buf - 2ull * (unsigned long long)j.u0;
 		sp.w_lo = w_lo;
 		sp.w_hi = w_hi;
 		sp.n_blocks = (int)((sp.own_end + lookback - sp.j_begin + S - 1) / S);
 		sp.pad_ = 0;
 	}
-	CU(cudaMemcpyAsync(h->d_fspans, h->h_fspans, n_sp * sizeof(FusedSpan), cudaMemcpyHostToDevice, h->st));
-	CU(cudaMemsetAsync(h->d_ticket, 0, sizeof(int), h->st));
+	CU(cudaMemcpyAsync(h->d_fspans[s], h->h_fspans[s], n_sp * sizeof(FusedSpan), cudaMemcpyHostToDevice, h->st));
+	CU(cudaMemsetAsync(h->d_ticket[s], 0, sizeof(int), h->st));
 	FusedParams p;
-	p.spans = h->d_fspans;
+	p.spans = h->d_fspans[s];
 	p.n_spans = n_sp;
 	p.accept_df18 = h->cfg.accept_df18;
 	p.want_tries = h->cfg.collect_stats;
-	p.cands = h->d_cands;
-	p.cand_cap = h->cand_cap;
-	p.tries = h->d_tries[h->try_cur];
-	p.try_cap = h->try_cap;
-	p.ctr = h->d_ctr;
-	p.span_ticket = h->d_ticket;
+	p.cands = h->d_cands[s];
+	p.cand_cap = h->cand_cap[s];
+	p.tries = h->d_tries[s];
+	p.try_cap = h->try_cap[s];
+	p.ctr = h->d_ctr[s];
+	p.span_ticket = h->d_ticket[s];
 	p.dbg_amp = h->dbg_amp;
 	p.dbg_p = h->dbg_p;
 	p.dbg_q = h->dbg_q;
 	p.dbg_b = h->dbg_b;
 	p.dbg_n = h->dbg_n;
 	if (h->dbg_amp)
-		h->dbg_jb = h->h_fspans[0].j_begin;
-	CU(cudaEventRecord(h->ev_fa, h->st));
+		h->dbg_jb = h->h_fspans[s][0].j_begin;
+	CU(cudaEventRecord(h->ev_fa[s], h->st));
 	CU(launch_fused(p, std::min(h->fused_ctas, n_sp), h->st));
-	CU(cudaEventRecord(h->ev_fb, h->st));
+	CU(cudaEventRecord(h->ev_fb[s], h->st));
 	h->launches += 1;
 	h->fused_launches += 1;
 	h->fused_samples += (uint64_t)(2 * total);
 	return 0;
 }
 
-// Scans offsets [n0, n1) of a device window into the candidate / try lists and brings the
-// candidates back, sorted by n, in h->cand_tmp.  Retries with larger lists on overflow and with
-// the generic kernels when the fused kernel reports out-of-range samples.
-int scan_range(adsbdec_b200 *h, const uint16_t *buf, int64_t u0, int64_t u1, int64_t n0, int64_t n1)
+// Enqueues the kernels and result copies of job slot s (asynchronous).
+int enqueue_job(adsbdec_b200 *h, int s, bool force_generic)
 {
-	h->cand_tmp.clear();
-	if (n1 <= n0)
-		return 0;
-	bool force_generic = h->cfg.kernel == 1 || h->fused_ctas <= 0;
-	for (int attempt = 0; attempt < 8; attempt++) {
-		k_set_counters<<<1, 1, 0, h->st>>>(h->d_ctr, 0, h->try_carried, 0, 1);
-		CU(cudaGetLastError());
-		CU(cudaEventRecord(h->ev_a, h->st));
-		bool used_fused = false;
-		// pieces: [n0, n1) split around fidx wraps; each piece fused if large enough
-		int64_t a = n0;
-		while (a < n1) {
-			int64_t b = n1, w = 0;
-			bool has_wrap = wrap_in_range(h, a, n1 + kLookahead, &w);
-			if (has_wrap) {
-				// generic over the neighbourhood of the wrap, fused (if any) before it
-				int64_t g0 = std::max(a, w - kLookahead - 64), g1 = std::min(n1, w + 64);
-				if (g0 > a) {
-					b = g0;
-				} else {
-					int rc = launch_generic(h, buf, u0, a, g1);
-					if (rc) return rc;
-					a = g1;
-					continue;
-				}
-			}
-			if (!force_generic && b - a >= kMinFused) {
-				int rc = launch_fused_range(h, buf, u0, u1, a, b);
-				if (rc) return rc;
-				used_fused = true;
-			} else {
-				int rc = launch_generic(h, buf, u0, a, b);
-				if (rc) return rc;
-			}
-			a = b;
-		}
-		CU(cudaEventRecord(h->ev_b, h->st));
-		CU(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, h->st));
-		CU(cudaStreamSynchronize(h->st));
-		float ms = 0;
-		cudaEventElapsedTime(&ms, h->ev_a, h->ev_b);
-		h->kernel_ms += ms;
-		if (used_fused) {
-			cudaEventElapsedTime(&ms, h->ev_fa, h->ev_fb);
-			h->fused_ms += ms;
-		}
-		if (used_fused && h->h_ctr->wide) {
-			force_generic = true;  // samples beyond 12 bits: exact int path only
-			continue;
-		}
-		if (h->h_ctr->overflow) {
-			unsigned long long cc = h->cand_cap, tc = h->try_cap;
-			if (h->h_ctr->overflow & 1) cc *= 4;
-			if (h->h_ctr->overflow & 2) tc *= 4;
-			int rc = alloc_outputs(h, cc, tc);
-			if (rc) return rc;
-			continue;
-		}
-		const size_t nc = (size_t)h->h_ctr->n_cand;
-		if (nc) {
-			CU(cudaMemcpyAsync(h->h_cands, h->d_cands, nc * sizeof(CandRec), cudaMemcpyDeviceToHost, h->st));
-			CU(cudaStreamSynchronize(h->st));
-			std::sort(h->h_cands, h->h_cands + nc,
-			          [](const CandRec &x, const CandRec &y) { return x.n < y.n; });
-			h->cand_tmp.resize(nc);
-			for (size_t i = 0; i < nc; i++) {
-				adsbdec_b200_candidate_t &c = h->cand_tmp[i];
-				c.n = h->h_cands[i].n;
-				c.pw = h->h_cands[i].pw;
-				c.len = h->h_cands[i].len;
-				memcpy(c.bytes, h->h_cands[i].bytes, 16);
-			}
-		}
+	Job &j = h->job[s];
+	j.used_fused = false;
+	if (j.n1 <= j.n0) {
+		CU(cudaEventRecord(h->ev_done[s], h->st));
 		return 0;
 	}
-	return fail(ADSB_B200_ERANGE, "candidate lists keep overflowing");
+	force_generic = force_generic || h->cfg.kernel == 1 || h->fused_ctas <= 0;
+	k_reset_counters<<<1, 1, 0, h->st>>>(h->d_ctr[s]);
+	CU(cudaGetLastError());
+	CU(cudaEventRecord(h->ev_a[s], h->st));
+	// pieces: [n0, n1) split around fidx wraps; each piece fused if large enough
+	int64_t a = j.n0;
+	while (a < j.n1) {
+		int64_t b = j.n1, w = 0;
+		if (wrap_in_range(j.origin, a, j.n1 + kLookahead, &w)) {
+			// generic kernels over the neighbourhood of the wrap, fused (if any) before it
+			const int64_t g0 = std::max(a, w - kLookahead - 64), g1 = std::min(j.n1, w + 64);
+			if (g0 > a) {
+				b = g0;
+			} else {
+				RC(launch_generic(h, s, j, a, g1));
+				a = g1;
+				continue;
+			}
+		}
+		if (!force_generic && b - a >= kMinFused) {
+			RC(launch_fused_range(h, s, j, a, b));
+			j.used_fused = true;
+		} else {
+			RC(launch_generic(h, s, j, a, b));
+		}
+		a = b;
+	}
+	CU(cudaEventRecord(h->ev_b[s], h->st));
+	CU(cudaMemcpyAsync(h->h_ctr[s], h->d_ctr[s], sizeof(Counters), cudaMemcpyDeviceToHost, h->st));
+	CU(cudaMemcpyAsync(h->h_cands[s], h->d_cands[s], std::min(kSpecCands, h->cand_cap[s]) * sizeof(CandRec),
+	                   cudaMemcpyDeviceToHost, h->st));
+	CU(cudaEventRecord(h->ev_done[s], h->st));
+	return 0;
 }
 
 void emit_new_frames(adsbdec_b200 *h)
@@ -370,107 +362,222 @@ void emit_new_frames(adsbdec_b200 *h)
 	}
 }
 
-// Stats pass over the try list: counts visited tries below the resolver's scan end, carries the rest.
-int stats_pass(adsbdec_b200 *h, size_t first_new_frame)
+// Stats pass for the tries of slot s (and the pending list): counts visited tries below the
+// resolver's scan end, moves the rest to the other pending list.  All on the GPU.
+int stats_pass(adsbdec_b200 *h, int s, size_t first_new_frame, bool with_slot_list)
 {
 	if (!h->cfg.collect_stats)
 		return 0;
-	const unsigned long long n_try = h->h_ctr->n_try;
-	size_t f0 = first_new_frame > 0 ? first_new_frame - 1 : 0;
-	size_t ns = h->frames.size() - f0;
-	if (ns > h->span_cap) {
-		if (h->d_spans) cudaFree(h->d_spans);
-		if (h->h_spans) cudaFreeHost(h->h_spans);
-		h->span_cap = ns * 2 + 1024;
-		CU(cudaMalloc(&h->d_spans, h->span_cap * 2 * sizeof(unsigned long long)));
-		CU(cudaMallocHost(&h->h_spans, h->span_cap * 2 * sizeof(unsigned long long)));
+	const size_t f0 = first_new_frame > 0 ? first_new_frame - 1 : 0;  // the previous span may still cover tries
+	const size_t ns = h->frames.size() - f0;
+	if (ns > h->span_cap[s]) {
+		CU(cudaStreamSynchronize(h->st));
+		if (h->d_spans[s]) cudaFree(h->d_spans[s]);
+		if (h->h_spans[s]) cudaFreeHost(h->h_spans[s]);
+		h->span_cap[s] = ns * 2 + 1024;
+		CU(cudaMalloc(&h->d_spans[s], h->span_cap[s] * 2 * sizeof(unsigned long long)));
+		CU(cudaMallocHost(&h->h_spans[s], h->span_cap[s] * 2 * sizeof(unsigned long long)));
 	}
 	for (size_t i = 0; i < ns; i++) {
 		const adsbdec_b200_frame_t &f = h->frames[f0 + i];
-		h->h_spans[2 * i] = f.n;
-		h->h_spans[2 * i + 1] = f.n + (f.len == 7 ? kSkipShort : kSkipLong);
+		h->h_spans[s][2 * i] = f.n;
+		h->h_spans[s][2 * i + 1] = f.n + (f.len == 7 ? kSkipShort : kSkipLong);
 	}
 	if (ns)
-		CU(cudaMemcpyAsync(h->d_spans, h->h_spans, ns * 2 * sizeof(unsigned long long),
+		CU(cudaMemcpyAsync(h->d_spans[s], h->h_spans[s], ns * 2 * sizeof(unsigned long long),
 		                   cudaMemcpyHostToDevice, h->st));
-	k_set_counters<<<1, 1, 0, h->st>>>(h->d_ctr, 0, n_try, 0, 0);
-	CU(launch_count_tries(h->d_tries[h->try_cur], n_try, h->d_spans, (int)ns, h->res->scan_end(),
-	                      h->d_tries[1 - h->try_cur], h->try_cap, h->d_ctr, h->st));
-	h->launches += 1;
-	CU(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, h->st));
-	CU(cudaStreamSynchronize(h->st));
-	if (h->h_ctr->overflow)
-		return fail(ADSB_B200_ERANGE, "try list overflow in stats pass");
-	h->try_carried = h->h_ctr->n_try_next;
-	h->try_cur = 1 - h->try_cur;
+	const int pin = h->pend_in, pout = 1 - h->pend_in;
+	const unsigned long long scan_end = h->res->scan_end();
+	if (with_slot_list) {
+		CU(launch_count_tries(h->d_tries[s], &h->d_ctr[s]->n_try, h->try_cap[s], h->d_spans[s], (int)ns, scan_end,
+		                      h->d_pend[pout], &h->d_stats->n_pend[pout], kPendCap, h->d_stats, h->st));
+		h->launches += 1;
+	}
+	CU(launch_count_tries(h->d_pend[pin], &h->d_stats->n_pend[pin], kPendCap, h->d_spans[s], (int)ns, scan_end,
+	                      h->d_pend[pout], &h->d_stats->n_pend[pout], kPendCap, h->d_stats, h->st));
+	k_zero_u64<<<1, 1, 0, h->st>>>(&h->d_stats->n_pend[pin]);
+	CU(cudaGetLastError());
+	h->launches += 2;
+	h->pend_in = pout;
 	return 0;
 }
 
-// Processes a device window holding local samples [u0, u1): scans every offset that now has its
-// full look-ahead, resolves, emits.
-int process_window(adsbdec_b200 *h, const uint16_t *buf, int64_t u0, int64_t u1)
+// The kernels append candidates in whatever order CTAs finish.  Bucket them by offset (counting
+// sort over 4096-offset buckets: one pass to count, one to scatter), then order the handful of
+// entries inside each bucket - O(n) instead of a comparison sort of 32-byte records.
+void sort_candidates(adsbdec_b200 *h, const CandRec *c, size_t nc, int64_t n0, int64_t n1)
 {
-	const int64_t total_out = u1 / 2;
-	const int64_t n1 = total_out - kLookahead;
-	if (n1 > h->own_next) {
-		int rc = scan_range(h, buf, u0, u1, h->own_next, n1);
-		if (rc) return rc;
-		h->own_next = n1;
-	} else {
-		h->cand_tmp.clear();
-		h->h_ctr->n_try = h->try_carried;
+	static_assert(sizeof(CandRec) == sizeof(adsbdec_b200_candidate_t), "record layouts must agree");
+	const int shift = 12;
+	const size_t nb = (size_t)((n1 - n0) >> shift) + 2;
+	h->bucket.assign(nb + 1, 0);
+	for (size_t i = 0; i < nc; i++)
+		h->bucket[(size_t)(((int64_t)c[i].n - n0) >> shift) + 1]++;
+	for (size_t b = 0; b < nb; b++)
+		h->bucket[b + 1] += h->bucket[b];
+	h->cand_tmp.resize(nc);
+	adsbdec_b200_candidate_t *out = h->cand_tmp.data();
+	for (size_t i = 0; i < nc; i++) {
+		const size_t b = (size_t)(((int64_t)c[i].n - n0) >> shift);
+		memcpy(&out[h->bucket[b]++], &c[i], sizeof(CandRec));
 	}
+	// bucket[b] is now the END of bucket b; insertion sort inside each (a few entries)
+	size_t lo = 0;
+	for (size_t b = 0; b < nb; b++) {
+		const size_t hi = h->bucket[b];
+		for (size_t i = lo + 1; i < hi; i++) {
+			const adsbdec_b200_candidate_t v = out[i];
+			size_t k = i;
+			while (k > lo && out[k - 1].n > v.n) {
+				out[k] = out[k - 1];
+				k--;
+			}
+			out[k] = v;
+		}
+		lo = hi;
+	}
+}
+
+// Waits for job slot s, handles overflow / out-of-range fall-backs, resolves and emits.
+int complete_job(adsbdec_b200 *h, int s)
+{
+	Job &j = h->job[s];
+	if (!j.active)
+		return 0;
+	h->cand_tmp.clear();
+	const bool scanned = j.n1 > j.n0;
+	if (scanned) {
+		bool force_generic = false;
+		for (int attempt = 0;; attempt++) {
+			CU(cudaEventSynchronize(h->ev_done[s]));
+			float ms = 0;
+			cudaEventElapsedTime(&ms, h->ev_a[s], h->ev_b[s]);
+			h->kernel_ms += ms;
+			if (j.used_fused) {
+				cudaEventElapsedTime(&ms, h->ev_fa[s], h->ev_fb[s]);
+				h->fused_ms += ms;
+			}
+			const Counters &c = *h->h_ctr[s];
+			if (attempt >= 8)
+				return fail(ADSB_B200_ERANGE, "candidate lists keep overflowing");
+			if (j.used_fused && (c.wide || (c.overflow & 4u))) {
+				// samples beyond 12 bits (or an absurd survivor density): exact generic kernels
+				force_generic = true;
+			} else if (c.overflow & 3u) {
+				CU(cudaStreamSynchronize(h->st));
+				RC(alloc_slot_outputs(h, s, (c.overflow & 1u) ? h->cand_cap[s] * 4 : h->cand_cap[s],
+				                      (c.overflow & 2u) ? h->try_cap[s] * 4 : h->try_cap[s]));
+			} else {
+				break;
+			}
+			RC(enqueue_job(h, s, force_generic));
+		}
+		const size_t nc = (size_t)h->h_ctr[s]->n_cand;
+		if (nc > kSpecCands) {
+			CU(cudaMemcpyAsync(h->h_cands[s] + kSpecCands, h->d_cands[s] + kSpecCands,
+			                   (nc - kSpecCands) * sizeof(CandRec), cudaMemcpyDeviceToHost, h->st));
+			CU(cudaStreamSynchronize(h->st));
+		}
+		if (nc)
+			sort_candidates(h, h->h_cands[s], nc, j.n0, j.n1);
+	} else {
+		CU(cudaEventSynchronize(h->ev_done[s]));
+	}
+	j.active = false;
+	if (!j.resolve)
+		return 0;
 	const size_t f0 = h->frames.size();
-	h->res->feed(h->cand_tmp.data(), h->cand_tmp.size(), (uint64_t)h->own_next, (uint64_t)total_out,
+	h->res->feed(h->cand_tmp.data(), h->cand_tmp.size(), (uint64_t)std::max<int64_t>(j.n1, 0), (uint64_t)j.total_out,
 	             h->frames);
-	int rc = stats_pass(h, f0);
-	if (rc) return rc;
+	RC(stats_pass(h, s, f0, scanned));
 	emit_new_frames(h);
 	return 0;
 }
 
-// Copies whatever is staged in pinned memory to the device window.
+int complete_all(adsbdec_b200 *h)
+{
+	// oldest first
+	const int a = h->next_slot, b = 1 - h->next_slot;
+	RC(complete_job(h, a));
+	RC(complete_job(h, b));
+	return 0;
+}
+
+// Submits a scan of every offset that has its full look-ahead once the window [u0, u1) is in.
+int submit_window(adsbdec_b200 *h, const uint16_t *buf, int64_t u0, int64_t u1)
+{
+	const int s = h->next_slot;
+	RC(complete_job(h, s));  // the slot's previous job (two submissions ago)
+	Job &j = h->job[s];
+	j.buf = buf;
+	j.u0 = u0;
+	j.u1 = u1;
+	j.total_out = u1 / 2;
+	j.n0 = h->own_next;
+	j.n1 = std::max<int64_t>(h->own_next, j.total_out - kLookahead);
+	j.origin = h->origin;
+	j.resolve = true;
+	j.active = true;
+	h->own_next = j.n1;
+	RC(enqueue_job(h, s, false));
+	h->next_slot = 1 - s;
+	return 0;
+}
+
+// Issues the upload of whatever is staged in pinned memory into the device window.
 int drain_pinned(adsbdec_b200 *h)
 {
 	if (h->pin_fill == 0)
 		return 0;
-	CU(cudaMemcpyAsync(h->dev[h->cur] + h->win_off + h->dev_fill, h->pin[h->cur],
-	                   (size_t)h->pin_fill * sizeof(uint16_t), cudaMemcpyHostToDevice, h->st));
-	CU(cudaStreamSynchronize(h->st));
+	CU(cudaMemcpyAsync(h->dev[h->cur] + h->win_off + h->dev_fill, h->pin[h->cur] + (h->pin_pos - h->pin_fill),
+	                   (size_t)h->pin_fill * sizeof(uint16_t), cudaMemcpyHostToDevice, h->st_copy));
+	CU(cudaEventRecord(h->ev_pin_free[h->cur], h->st_copy));
 	h->dev_fill += h->pin_fill;
 	h->pin_fill = 0;
 	return 0;
 }
 
-// Ends the current batch: process the window, then start the next one with the carried tail.
-int flush_batch(adsbdec_b200 *h)
+// Opens the next window in the other device buffer, starting with the tail the next scan still
+// needs (air.c:96-98 keeps the unscanned envelope; we keep the raw samples it is computed from).
+// The copy is issued on the compute stream, behind the job that was just submitted.
+int carry_to_next(adsbdec_b200 *h, const uint16_t *buf, int64_t u0, int64_t u1)
 {
-	int rc = drain_pinned(h);
-	if (rc) return rc;
-	const int64_t u0 = h->win_u0, u1 = h->win_u0 + h->dev_fill;
-	const uint16_t *buf = h->dev[h->cur] + h->win_off;
-	rc = process_window(h, buf, u0, u1);
-	if (rc) return rc;
-	// carry: everything from kCarryBack samples before the next owned offset (air.c:96-98 keeps
-	// the unscanned envelope; we keep the raw samples it is computed from)
 	int64_t c0 = std::max<int64_t>(u0, align_down(2 * h->own_next - kCarryBack, 8));
-	if (c0 < 0) c0 = 0;
-	c0 = std::max<int64_t>(c0, u0 - (u0 % 8));
+	c0 = std::max<int64_t>(c0, 0);
 	const int64_t clen = u1 - c0;
 	if (clen > kCarryMax)
 		return fail(ADSB_B200_EINVAL, "internal: carry too large (%lld)", (long long)clen);
 	const int nxt = 1 - h->cur;
-	// place the carry so that local sample c0 (a multiple of 8) lands on a 16-byte boundary
+	// local sample c0 (a multiple of 8) must land on a 16-byte boundary
 	const int64_t off = kCarryMax - align_down(clen + 7, 8);
 	if (clen > 0)
 		CU(cudaMemcpyAsync(h->dev[nxt] + off, buf + (c0 - u0), (size_t)clen * sizeof(uint16_t),
 		                   cudaMemcpyDeviceToDevice, h->st));
-	CU(cudaStreamSynchronize(h->st));
 	h->cur = nxt;
 	h->win_u0 = c0;
 	h->win_off = off;
 	h->dev_fill = clen;
+	h->pin_pos = 0;
 	h->pin_fill = 0;
+	return 0;
+}
+
+// Ends the current batch window: scan it (asynchronously) and open the next one.
+int flush_batch(adsbdec_b200 *h)
+{
+	RC(drain_pinned(h));
+	const int old = h->cur;
+	const int64_t u0 = h->win_u0, u1 = h->win_u0 + h->dev_fill;
+	const uint16_t *buf = h->dev[old] + h->win_off;
+	// the kernels must see the uploads
+	CU(cudaEventRecord(h->ev_h2d, h->st_copy));
+	CU(cudaStreamWaitEvent(h->st, h->ev_h2d, 0));
+	RC(submit_window(h, buf, u0, u1));
+	RC(carry_to_next(h, buf, u0, u1));
+	// dev[old] may be overwritten once this job and the carry copy out of it are done
+	CU(cudaEventRecord(h->ev_dev_free[old], h->st));
+	// uploads into the new window wait for the last readers of that buffer (recorded one flush ago)
+	CU(cudaStreamWaitEvent(h->st_copy, h->ev_dev_free[h->cur], 0));
 	return 0;
 }
 
@@ -479,6 +586,16 @@ int64_t batch_room(const adsbdec_b200 *h)
 	// samples that still fit in the current batch (the carry lives in the kCarryMax head room)
 	const int64_t used = h->win_off + h->dev_fill + h->pin_fill - kCarryMax;
 	return h->batch - std::max<int64_t>(0, used);
+}
+
+bool is_pinned_host(const void *p)
+{
+	cudaPointerAttributes at;
+	if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+		cudaGetLastError();
+		return false;
+	}
+	return at.type == cudaMemoryTypeHost;
 }
 
 }  // namespace
@@ -531,21 +648,33 @@ int adsbdec_b200_open(const adsbdec_b200_config_t *cfg, adsbdec_b200_t **out)
 	h->win_off = kCarryMax;
 	int rc = 0;
 	do {
-		if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess ||
-		    cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
-		    cudaEventCreate(&h->ev_a) != cudaSuccess || cudaEventCreate(&h->ev_b) != cudaSuccess ||
-		    cudaEventCreate(&h->ev_fa) != cudaSuccess || cudaEventCreate(&h->ev_fb) != cudaSuccess ||
-		    cudaMalloc(&h->d_ctr, sizeof(Counters)) != cudaSuccess ||
-		    cudaMallocHost(&h->h_ctr, sizeof(Counters)) != cudaSuccess) {
+		bool ok = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) == cudaSuccess &&
+		          cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking) == cudaSuccess &&
+		          cudaEventCreateWithFlags(&h->ev_h2d, cudaEventDisableTiming) == cudaSuccess &&
+		          cudaMalloc(&h->d_stats, sizeof(StreamStats)) == cudaSuccess &&
+		          cudaMallocHost(&h->h_stats, sizeof(StreamStats)) == cudaSuccess &&
+		          cudaMemset(h->d_stats, 0, sizeof(StreamStats)) == cudaSuccess;
+		for (int i = 0; ok && i < 2; i++) {
+			ok = cudaEventCreateWithFlags(&h->ev_dev_free[i], cudaEventDisableTiming) == cudaSuccess &&
+			     cudaEventCreateWithFlags(&h->ev_pin_free[i], cudaEventDisableTiming) == cudaSuccess &&
+			     cudaMalloc(&h->d_pend[i], kPendCap * sizeof(unsigned long long)) == cudaSuccess;
+		}
+		for (int s = 0; ok && s < kSlots; s++) {
+			ok = cudaEventCreate(&h->ev_a[s]) == cudaSuccess && cudaEventCreate(&h->ev_b[s]) == cudaSuccess &&
+			     cudaEventCreate(&h->ev_fa[s]) == cudaSuccess && cudaEventCreate(&h->ev_fb[s]) == cudaSuccess &&
+			     cudaEventCreateWithFlags(&h->ev_done[s], cudaEventDisableTiming) == cudaSuccess &&
+			     cudaMalloc(&h->d_ctr[s], sizeof(Counters)) == cudaSuccess &&
+			     cudaMallocHost(&h->h_ctr[s], sizeof(Counters)) == cudaSuccess &&
+			     cudaMemset(h->d_ctr[s], 0, sizeof(Counters)) == cudaSuccess;
+			if (ok)
+				memset(h->h_ctr[s], 0, sizeof(Counters));
+		}
+		if (!ok) {
 			rc = fail(ADSB_B200_ECUDA, "stream/event/counter setup: %s", cudaGetErrorString(cudaGetLastError()));
 			break;
 		}
-		memset(h->h_ctr, 0, sizeof(Counters));
-		if (cudaMemset(h->d_ctr, 0, sizeof(Counters)) != cudaSuccess) {
-			rc = fail(ADSB_B200_ECUDA, "memset");
-			break;
-		}
-		rc = alloc_outputs(h, 1ull << 18, 1ull << 20);
+		for (int s = 0; s < kSlots && !rc; s++)
+			rc = alloc_slot_outputs(h, s, 1ull << 18, 1ull << 20);
 		if (rc) break;
 		if (cfg->kernel != 1) {
 			int per_sm = fused_prepare(cfg->device);
@@ -569,26 +698,36 @@ void adsbdec_b200_close(adsbdec_b200_t *h)
 	if (!h)
 		return;
 	cudaSetDevice(h->device);
+	if (h->st_copy) cudaStreamSynchronize(h->st_copy);
 	if (h->st) cudaStreamSynchronize(h->st);
 	for (int i = 0; i < 2; i++) {
 		if (h->dev[i]) cudaFree(h->dev[i]);
 		if (h->pin[i]) cudaFreeHost(h->pin[i]);
-		if (h->d_tries[i]) cudaFree(h->d_tries[i]);
+		if (h->d_pend[i]) cudaFree(h->d_pend[i]);
+		if (h->ev_dev_free[i]) cudaEventDestroy(h->ev_dev_free[i]);
+		if (h->ev_pin_free[i]) cudaEventDestroy(h->ev_pin_free[i]);
 	}
-	if (h->d_cands) cudaFree(h->d_cands);
-	if (h->h_cands) cudaFreeHost(h->h_cands);
-	if (h->d_ctr) cudaFree(h->d_ctr);
-	if (h->h_ctr) cudaFreeHost(h->h_ctr);
+	for (int s = 0; s < kSlots; s++) {
+		if (h->d_tries[s]) cudaFree(h->d_tries[s]);
+		if (h->d_cands[s]) cudaFree(h->d_cands[s]);
+		if (h->h_cands[s]) cudaFreeHost(h->h_cands[s]);
+		if (h->d_ctr[s]) cudaFree(h->d_ctr[s]);
+		if (h->h_ctr[s]) cudaFreeHost(h->h_ctr[s]);
+		if (h->d_spans[s]) cudaFree(h->d_spans[s]);
+		if (h->h_spans[s]) cudaFreeHost(h->h_spans[s]);
+		if (h->d_fspans[s]) cudaFree(h->d_fspans[s]);
+		if (h->h_fspans[s]) cudaFreeHost(h->h_fspans[s]);
+		if (h->d_ticket[s]) cudaFree(h->d_ticket[s]);
+		if (h->ev_a[s]) cudaEventDestroy(h->ev_a[s]);
+		if (h->ev_b[s]) cudaEventDestroy(h->ev_b[s]);
+		if (h->ev_fa[s]) cudaEventDestroy(h->ev_fa[s]);
+		if (h->ev_fb[s]) cudaEventDestroy(h->ev_fb[s]);
+		if (h->ev_done[s]) cudaEventDestroy(h->ev_done[s]);
+	}
+	if (h->d_stats) cudaFree(h->d_stats);
+	if (h->h_stats) cudaFreeHost(h->h_stats);
 	if (h->d_amp) cudaFree(h->d_amp);
-	if (h->d_spans) cudaFree(h->d_spans);
-	if (h->h_spans) cudaFreeHost(h->h_spans);
-	if (h->d_fspans) cudaFree(h->d_fspans);
-	if (h->h_fspans) cudaFreeHost(h->h_fspans);
-	if (h->d_ticket) cudaFree(h->d_ticket);
-	if (h->ev_a) cudaEventDestroy(h->ev_a);
-	if (h->ev_b) cudaEventDestroy(h->ev_b);
-	if (h->ev_fa) cudaEventDestroy(h->ev_fa);
-	if (h->ev_fb) cudaEventDestroy(h->ev_fb);
+	if (h->ev_h2d) cudaEventDestroy(h->ev_h2d);
 	if (h->st) cudaStreamDestroy(h->st);
 	if (h->st_copy) cudaStreamDestroy(h->st_copy);
 	delete h->res;
@@ -602,6 +741,7 @@ int adsbdec_b200_reset(adsbdec_b200_t *h, uint64_t start_sample)
 	if (start_sample % 4)
 		return fail(ADSB_B200_EINVAL, "start_sample must be a multiple of 4");
 	CU(cudaSetDevice(h->device));
+	CU(cudaStreamSynchronize(h->st_copy));
 	CU(cudaStreamSynchronize(h->st));
 	h->origin = start_sample;
 	h->cfg.start_sample = start_sample;
@@ -612,17 +752,19 @@ int adsbdec_b200_reset(adsbdec_b200_t *h, uint64_t start_sample)
 	h->win_u0 = 0;
 	h->win_off = kCarryMax;
 	h->dev_fill = 0;
+	h->pin_pos = 0;
 	h->pin_fill = 0;
-	h->try_cur = 0;
-	h->try_carried = 0;
+	h->next_slot = 0;
+	h->pend_in = 0;
+	for (int s = 0; s < kSlots; s++)
+		h->job[s].active = false;
 	delete h->res;
 	h->res = new Resolver(h->cfg.emulate_reference_tail != 0);
 	h->frames.clear();
 	h->emitted = 0;
 	for (int i = 0; i < 3; i++)
 		h->stat_ok[i] = 0;
-	CU(cudaMemset(h->d_ctr, 0, sizeof(Counters)));
-	memset(h->h_ctr, 0, sizeof(Counters));
+	CU(cudaMemset(h->d_stats, 0, sizeof(StreamStats)));
 	return 0;
 }
 
@@ -643,23 +785,42 @@ int adsbdec_b200_push(adsbdec_b200_t *h, const uint16_t *samples, size_t n)
 		return fail(ADSB_B200_EINVAL, "push length must be a multiple of 4 samples (air.c:59-82)");
 	if (h->finished)
 		return fail(ADSB_B200_ESTATE, "push after finish");
+	if (n == 0)
+		return 0;
 	CU(cudaSetDevice(h->device));
-	int rc = ensure_batch_buffers(h);
-	if (rc) return rc;
+	// Page-locked caller memory is uploaded straight from where it lies; pageable memory goes
+	// through our own pinned staging buffers, in slices so that the upload of one slice overlaps
+	// the memcpy of the next.
+	const bool direct = is_pinned_host(samples);
+	RC(ensure_batch_buffers(h, !direct));
 	size_t done = 0;
 	while (done < n) {
-		int64_t room = batch_room(h);
+		const int64_t room = batch_room(h);
 		if (room <= 0) {
-			rc = flush_batch(h);
-			if (rc) return rc;
+			RC(flush_batch(h));
 			continue;
 		}
-		const size_t take = std::min<size_t>((size_t)room, n - done);
-		memcpy(h->pin[h->cur] + h->pin_fill, samples + done, take * sizeof(uint16_t));
-		h->pin_fill += (int64_t)take;
+		size_t take = std::min<size_t>((size_t)room, n - done);
+		if (direct) {
+			RC(drain_pinned(h));
+			CU(cudaMemcpyAsync(h->dev[h->cur] + h->win_off + h->dev_fill, samples + done, take * sizeof(uint16_t),
+			                   cudaMemcpyHostToDevice, h->st_copy));
+			h->dev_fill += (int64_t)take;
+		} else {
+			take = std::min<size_t>(take, (size_t)kStageSlice);
+			if (h->pin_pos == 0)
+				CU(cudaEventSynchronize(h->ev_pin_free[h->cur]));  // uploads of two windows ago
+			memcpy(h->pin[h->cur] + h->pin_pos, samples + done, take * sizeof(uint16_t));
+			h->pin_pos += (int64_t)take;
+			h->pin_fill += (int64_t)take;
+			if (h->pin_fill >= kStageSlice)
+				RC(drain_pinned(h));
+		}
 		h->pushed += (int64_t)take;
 		done += take;
 	}
+	if (direct)
+		CU(cudaStreamSynchronize(h->st_copy));  // the caller may reuse its buffer on return
 	return 0;
 }
 
@@ -671,66 +832,58 @@ int adsbdec_b200_push_device(adsbdec_b200_t *h, const void *dev_samples, size_t 
 		return fail(ADSB_B200_EINVAL, "push length must be a multiple of 4 samples (air.c:59-82)");
 	if (h->finished)
 		return fail(ADSB_B200_ESTATE, "push after finish");
+	if (n == 0)
+		return 0;
 	CU(cudaSetDevice(h->device));
-	int rc = ensure_batch_buffers(h);
-	if (rc) return rc;
+	RC(ensure_batch_buffers(h, false));
 	const uint16_t *src = (const uint16_t *)dev_samples;
 	const int64_t seam = 2 * kLookahead + 2 * kCarryBack;  // samples of the piece the seam window needs
 	const bool direct = (int64_t)n >= (int64_t)kMinFused * 4 && ((uintptr_t)src % 16) == 0 &&
-	                    (h->pushed % 8) == 0;
+	                    (h->pushed % 8) == 0 && (n % 8) == 0;
 	if (!direct) {
 		// small or unaligned piece: append to the batch window on the device
 		size_t done = 0;
 		while (done < n) {
-			int64_t room = batch_room(h);
+			const int64_t room = batch_room(h);
 			if (room <= 0) {
-				rc = flush_batch(h);
-				if (rc) return rc;
+				RC(flush_batch(h));
 				continue;
 			}
-			rc = drain_pinned(h);
-			if (rc) return rc;
+			RC(drain_pinned(h));
 			const size_t take = std::min<size_t>((size_t)room, n - done);
-			CU(cudaMemcpyAsync(h->dev[h->cur] + h->win_off + h->dev_fill, src + done,
-			                   take * sizeof(uint16_t), cudaMemcpyDeviceToDevice, h->st));
+			CU(cudaMemcpyAsync(h->dev[h->cur] + h->win_off + h->dev_fill, src + done, take * sizeof(uint16_t),
+			                   cudaMemcpyDeviceToDevice, h->st_copy));
 			h->dev_fill += (int64_t)take;
 			h->pushed += (int64_t)take;
 			done += take;
 		}
-		CU(cudaStreamSynchronize(h->st));
+		CU(cudaStreamSynchronize(h->st_copy));  // the caller may free its buffer on return
 		return 0;
 	}
-	// Large aligned piece: (1) seam window = [carry | first `seam` samples of the piece] in our own
-	// buffer, (2) the body straight from the caller's memory.
-	rc = drain_pinned(h);
-	if (rc) return rc;
-	const int64_t piece_u0 = h->pushed;
+	// Large aligned piece: (1) a seam window [carried tail | first `seam` samples of the piece] in
+	// our own buffer, (2) the body straight from the caller's memory, in batch-sized scan jobs.
+	RC(drain_pinned(h));
+	if (h->dev_fill > 0 && batch_room(h) < seam)
+		RC(flush_batch(h));
+	const int64_t piece_u0 = h->pushed, piece_u1 = h->pushed + (int64_t)n;
 	if (h->dev_fill > 0) {
 		CU(cudaMemcpyAsync(h->dev[h->cur] + h->win_off + h->dev_fill, src, (size_t)seam * sizeof(uint16_t),
-		                   cudaMemcpyDeviceToDevice, h->st));
-		const int64_t u0 = h->win_u0, u1 = h->win_u0 + h->dev_fill + seam;
-		rc = process_window(h, h->dev[h->cur] + h->win_off, u0, u1);
-		if (rc) return rc;
+		                   cudaMemcpyDeviceToDevice, h->st_copy));
+		CU(cudaEventRecord(h->ev_h2d, h->st_copy));
+		CU(cudaStreamWaitEvent(h->st, h->ev_h2d, 0));
+		RC(submit_window(h, h->dev[h->cur] + h->win_off, h->win_u0, h->win_u0 + h->dev_fill + seam));
 	}
-	h->pushed += (int64_t)n;
-	rc = process_window(h, src, piece_u0, piece_u0 + (int64_t)n);
-	if (rc) return rc;
-	// carry the tail of the piece into the next window
-	const int64_t u1 = piece_u0 + (int64_t)n;
-	int64_t c0 = std::max<int64_t>(piece_u0, align_down(2 * h->own_next - kCarryBack, 8));
-	const int64_t clen = u1 - c0;
-	if (clen > kCarryMax)
-		return fail(ADSB_B200_EINVAL, "internal: carry too large (%lld)", (long long)clen);
-	const int nxt = 1 - h->cur;
-	const int64_t off = kCarryMax - align_down(clen + 7, 8);
-	CU(cudaMemcpyAsync(h->dev[nxt] + off, src + (c0 - piece_u0), (size_t)clen * sizeof(uint16_t),
-	                   cudaMemcpyDeviceToDevice, h->st));
+	h->pushed = piece_u1;
+	for (int64_t end = piece_u0; end < piece_u1;) {
+		end = std::min(piece_u1, end + h->batch);
+		// window: from the FIR history of the next owned offset to `end`, inside the caller's memory
+		const int64_t w0 = std::max<int64_t>(piece_u0, align_down(2 * h->own_next - kCarryBack, 8));
+		RC(submit_window(h, src + (w0 - piece_u0), w0, end));
+	}
+	RC(complete_all(h));  // the caller's memory is no longer needed after this ...
+	h->dev_fill = 0;
+	RC(carry_to_next(h, src, piece_u0, piece_u1));  // ... except for the tail we keep
 	CU(cudaStreamSynchronize(h->st));
-	h->cur = nxt;
-	h->win_u0 = c0;
-	h->win_off = off;
-	h->dev_fill = clen;
-	h->pin_fill = 0;
 	return 0;
 }
 
@@ -741,18 +894,14 @@ int adsbdec_b200_finish(adsbdec_b200_t *h)
 	if (h->finished)
 		return 0;
 	CU(cudaSetDevice(h->device));
-	if (h->dev[0] && (h->pin_fill > 0 || h->dev_fill > 0)) {
-		int rc = flush_batch(h);
-		if (rc) return rc;
-	}
+	if (h->dev[0] && (h->pin_fill > 0 || h->dev_fill > 0))
+		RC(flush_batch(h));
+	RC(complete_all(h));
 	const size_t f0 = h->frames.size();
 	h->res->finish(h->frames);
-	h->h_ctr->n_try = h->try_carried;
-	if (h->d_tries[0]) {
-		int rc = stats_pass(h, f0);
-		if (rc) return rc;
-	}
+	RC(stats_pass(h, 0, f0, false));
 	emit_new_frames(h);
+	CU(cudaStreamSynchronize(h->st));
 	h->finished = true;
 	return 0;
 }
@@ -795,9 +944,13 @@ int adsbdec_b200_stats(adsbdec_b200_t *h, uint32_t try_[3], uint32_t ok[3])
 	if (!h)
 		return fail(ADSB_B200_EINVAL, "null handle");
 	CU(cudaSetDevice(h->device));
-	CU(cudaMemcpy(h->h_ctr, h->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost));
+	RC(complete_all(h));
+	CU(cudaMemcpyAsync(h->h_stats, h->d_stats, sizeof(StreamStats), cudaMemcpyDeviceToHost, h->st));
+	CU(cudaStreamSynchronize(h->st));
+	if (h->h_stats->pend_overflow)
+		return fail(ADSB_B200_ERANGE, "pending-try list overflow");
 	for (int i = 0; i < 3; i++) {
-		if (try_) try_[i] = h->h_ctr->stat_try[i];
+		if (try_) try_[i] = h->h_stats->stat_try[i];
 		if (ok) ok[i] = h->stat_ok[i];
 	}
 	return 0;
@@ -862,7 +1015,7 @@ int adsbdec_b200_envelope(int device, const void *samples, size_t n_samples, int
 	float *d_amp = nullptr;
 	const uint16_t *raw = (const uint16_t *)samples;
 	if (!is_device) {
-		CU(cudaMalloc(&d_raw, n_samples * sizeof(uint16_t)));
+		CU(cudaMalloc(&d_raw, std::max<size_t>(n_samples, 1) * sizeof(uint16_t)));
 		CU(cudaMemcpy(d_raw, samples, n_samples * sizeof(uint16_t), cudaMemcpyHostToDevice));
 		raw = d_raw;
 	}
@@ -889,14 +1042,20 @@ int64_t adsbdec_b200_chunk_candidates(adsbdec_b200_t *h, const void *dev_samples
 	if (((uintptr_t)dev_samples % 16) != 0 || start_sample % 4)
 		return fail(ADSB_B200_EINVAL, "chunk must be 16-byte aligned and start on a multiple of 4 samples");
 	CU(cudaSetDevice(h->device));
-	const unsigned long long saved = h->try_carried, saved_origin = h->origin;
-	h->try_carried = 0;
-	h->origin = start_sample;
-	int rc = scan_range(h, (const uint16_t *)dev_samples, 0, (int64_t)n_samples, (int64_t)own_begin,
-	                    (int64_t)own_end);
-	h->try_carried = saved;
-	h->origin = saved_origin;
-	if (rc) return rc;
+	RC(complete_all(h));
+	const int s = h->next_slot;
+	Job &j = h->job[s];
+	j.buf = (const uint16_t *)dev_samples;
+	j.u0 = 0;
+	j.u1 = (int64_t)n_samples;
+	j.total_out = (int64_t)n_samples / 2;
+	j.n0 = (int64_t)own_begin;
+	j.n1 = (int64_t)own_end;
+	j.origin = start_sample;
+	j.resolve = false;
+	j.active = true;
+	RC(enqueue_job(h, s, false));
+	RC(complete_job(h, s));
 	if (h->cand_tmp.size() > cap)
 		return fail(ADSB_B200_ERANGE, "output capacity %zu < %zu candidates", cap, h->cand_tmp.size());
 	if (!h->cand_tmp.empty())
@@ -904,11 +1063,10 @@ int64_t adsbdec_b200_chunk_candidates(adsbdec_b200_t *h, const void *dev_samples
 	if (tries_out) {
 		// raw gate-pass counts in the owned range (no sequential exclusion in chunk mode)
 		tries_out[0] = tries_out[1] = tries_out[2] = 0;
-		const unsigned long long nt = h->h_ctr->n_try;
+		const unsigned long long nt = own_end > own_begin && h->cfg.collect_stats ? h->h_ctr[s]->n_try : 0;
 		if (nt) {
 			std::vector<unsigned long long> t(nt);
-			CU(cudaMemcpy(t.data(), h->d_tries[h->try_cur], nt * sizeof(unsigned long long),
-			              cudaMemcpyDeviceToHost));
+			CU(cudaMemcpy(t.data(), h->d_tries[s], nt * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
 			for (unsigned long long e : t)
 				tries_out[e >> kTryClsShift]++;
 		}
@@ -925,6 +1083,7 @@ int adsbdec_b200_debug_fused(adsbdec_b200_t *h, const uint16_t *samples, size_t 
 	if (h->fused_ctas <= 0)
 		return fail(ADSB_B200_ENODEV, "fused kernel not configured");
 	CU(cudaSetDevice(h->device));
+	RC(complete_all(h));
 	const int64_t n1 = (int64_t)(n_samples / 2) - kLookahead;
 	if (n1 <= 0)
 		return fail(ADSB_B200_EINVAL, "capture too short");
@@ -940,13 +1099,16 @@ int adsbdec_b200_debug_fused(adsbdec_b200_t *h, const uint16_t *samples, size_t 
 	CU(cudaMemset(h->dbg_q, 0, count / 8));
 	CU(cudaMemset(h->dbg_b, 0, count / 8));
 	h->dbg_n = (long long)count;
-	const unsigned long long saved_origin = h->origin;
 	const int saved_ctas = h->fused_ctas;
-	h->origin = start_sample;
 	h->fused_ctas = 1;  // one CTA, so span 0 covers the head of the capture in order
-	k_set_counters<<<1, 1, 0, h->st>>>(h->d_ctr, 0, h->try_carried, 0, 1);
-	int rc = launch_fused_range(h, d_raw, 0, (int64_t)n_samples, 0, n1);
-	h->origin = saved_origin;
+	const int s = h->next_slot;
+	Job j;
+	j.buf = d_raw;
+	j.u0 = 0;
+	j.u1 = (int64_t)n_samples;
+	j.origin = start_sample;
+	k_reset_counters<<<1, 1, 0, h->st>>>(h->d_ctr[s]);
+	int rc = launch_fused_range(h, s, j, 0, n1);
 	h->fused_ctas = saved_ctas;
 	cudaError_t e = cudaStreamSynchronize(h->st);
 	if (rc == 0 && e == cudaSuccess) {
@@ -964,8 +1126,6 @@ int adsbdec_b200_debug_fused(adsbdec_b200_t *h, const uint16_t *samples, size_t 
 	h->dbg_amp = nullptr;
 	h->dbg_p = h->dbg_q = h->dbg_b = nullptr;
 	h->dbg_n = 0;
-	k_set_counters<<<1, 1, 0, h->st>>>(h->d_ctr, 0, h->try_carried, 0, 1);
-	cudaStreamSynchronize(h->st);
 	if (rc) return rc;
 	if (e != cudaSuccess)
 		return fail(ADSB_B200_ECUDA, "debug_fused: %s", cudaGetErrorString(e));
@@ -1018,6 +1178,6 @@ int adsbdec_b200_resolver_finish(adsbdec_b200_resolver_t *r, adsbdec_b200_sink_f
 uint64_t adsbdec_b200_resolver_scan_end(const adsbdec_b200_resolver_t *r) { return r ? r->r.scan_end() : 0; }
 
 const char *adsbdec_b200_last_error(void) { return t_err; }
-const char *adsbdec_b200_version(void) { return "adsbdec_b200 0.1 (sm_100a)"; }
+const char *adsbdec_b200_version(void) { return "adsbdec_b200 0.2 (sm_100a)"; }
 
 }  // extern "C"

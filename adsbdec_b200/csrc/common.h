@@ -30,17 +30,24 @@ static_assert(sizeof(CandRec) == 32, "CandRec layout");
 constexpr int kTryClsShift = 62;
 constexpr uint64_t kTryMask = (1ull << kTryClsShift) - 1;
 
-// Device-side counters of one decoder (one 64-byte block, zeroed per batch where noted).
+// Device-side counters of one scan job (one 64-byte block, reset per job).
 struct Counters {
-	unsigned long long n_cand;      // entries in the candidate list
-	unsigned long long n_try;       // entries in the current try list
-	unsigned long long n_try_next;  // entries carried to the next try list by the stats pass
-	unsigned int stat_try[3];       // visited tries per class (accumulates over the stream)
-	unsigned int overflow;          // bit0: candidate list full, bit1: try list full
+	unsigned long long n_cand;      // entries in the job's candidate list
+	unsigned long long n_try;       // entries in the job's try list
+	unsigned int overflow;          // bit0: candidate list full, bit1: try list full, bit2: CTA survivor list full
 	unsigned int wide;              // a sample outside 0..4095 was seen by the fused kernel
-	unsigned int pad_[5];
+	unsigned int pad_[10];
 };
 static_assert(sizeof(Counters) == 64, "Counters layout");
+
+// Device-side per-stream statistics (valid.c:30-31 as seen by the sequential scan).
+struct StreamStats {
+	unsigned int stat_try[3];       // visited tries per class (accumulates over the stream)
+	unsigned int pend_overflow;
+	unsigned long long n_pend[2];   // entries in the two pending-try lists (tries beyond the scan end)
+	unsigned int pad_[8];
+};
+static_assert(sizeof(StreamStats) == 64, "StreamStats layout");
 
 // Mode S CRC-24 generator (crc.h:1-34 is its byte-wise table).
 constexpr uint32_t kCrcPoly = 0xFFF409u;

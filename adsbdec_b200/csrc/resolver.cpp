@@ -14,9 +14,8 @@ void Resolver::scan_to(uint64_t cutoff, std::vector<adsbdec_b200_frame_t> &accep
 	// One deqframe(ampbuff, len) call whose loop bound len-DECOFFSET is `cutoff` in absolute
 	// offsets (demod.c:89).  idx starts at ampbuff[0] = base_.
 	uint64_t pos = base_;
-	while (!pending_.empty() && pending_.front().n < cutoff) {
-		const adsbdec_b200_candidate_t c = pending_.front();
-		pending_.pop_front();
+	while (head_ < pending_.size() && pending_[head_].n < cutoff) {
+		const adsbdec_b200_candidate_t &c = pending_[head_++];
 		if (c.n < pos)
 			continue;  // inside the frame just accepted: never evaluated (demod.c:128, :134)
 		const uint64_t skip = c.len == 7 ? kSkipShort : kSkipLong;
@@ -54,8 +53,14 @@ void Resolver::run_calls(std::vector<adsbdec_b200_frame_t> &accepted)
 void Resolver::feed(const adsbdec_b200_candidate_t *c, size_t count, uint64_t scanned_upto,
                     uint64_t total_out, std::vector<adsbdec_b200_frame_t> &accepted)
 {
-	for (size_t i = 0; i < count; i++)
-		pending_.push_back(c[i]);
+	if (head_ == pending_.size()) {
+		pending_.clear();
+		head_ = 0;
+	} else if (head_ > (1u << 16)) {
+		pending_.erase(pending_.begin(), pending_.begin() + (ptrdiff_t)head_);
+		head_ = 0;
+	}
+	pending_.insert(pending_.end(), c, c + count);
 	scanned_upto_ = std::max(scanned_upto_, scanned_upto);
 	total_out_ = std::max(total_out_, total_out);
 	run_calls(accepted);
@@ -72,7 +77,8 @@ void Resolver::finish(std::vector<adsbdec_b200_frame_t> &accepted)
 		if (cutoff > scan_end_)
 			scan_to(cutoff, accepted);
 	}
-	pending_.clear();  // the reference drops whatever is left in ampbuff at EOF (air.c:243-244)
+	pending_.clear();
+	head_ = 0;  // the reference drops whatever is left in ampbuff at EOF (air.c:243-244)
 }
 
 }  // namespace adsb

@@ -11,7 +11,6 @@
 #pragma once
 #include <stdint.h>
 
-#include <deque>
 #include <vector>
 
 #include "../../include/adsbdec_b200.h"
@@ -42,7 +41,8 @@ private:
 	uint64_t scan_end_ = 0;
 	uint64_t scanned_upto_ = 0;
 	uint64_t total_out_ = 0;
-	std::deque<adsbdec_b200_candidate_t> pending_;
+	std::vector<adsbdec_b200_candidate_t> pending_;  // sorted by n; [head_, size) not yet consumed
+	size_t head_ = 0;
 };
 
 }  // namespace adsb
