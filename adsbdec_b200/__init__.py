@@ -29,7 +29,7 @@ EXPORTS = [
     "adsbdec_b200_set_sink",
     "adsbdec_b200_push", "adsbdec_b200_push_device", "adsbdec_b200_finish", "adsbdec_b200_decode_file",
     "adsbdec_b200_stats", "adsbdec_b200_num_frames", "adsbdec_b200_frames", "adsbdec_b200_clear_frames",
-    "adsbdec_b200_kernel_time", "adsbdec_b200_fused_time", "adsbdec_b200_format_packet",
+    "adsbdec_b200_kernel_time", "adsbdec_b200_host_time", "adsbdec_b200_fused_time", "adsbdec_b200_format_packet",
     "adsbdec_b200_envelope", "adsbdec_b200_resolver_new", "adsbdec_b200_resolver_free",
     "adsbdec_b200_resolver_feed", "adsbdec_b200_resolver_finish", "adsbdec_b200_resolver_scan_end",
     "adsbdec_b200_chunk_candidates", "adsbdec_b200_debug_fused", "adsbdec_b200_last_error",
@@ -115,6 +115,7 @@ def lib():
         L.adsbdec_b200_clear_frames.argtypes = [vp]
         L.adsbdec_b200_clear_frames.restype = None
         L.adsbdec_b200_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64), C.c_int]
+        L.adsbdec_b200_host_time.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
         L.adsbdec_b200_fused_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64), C.POINTER(u64), C.c_int]
         L.adsbdec_b200_format_packet.argtypes = [C.c_int, C.c_char_p, C.c_int, u64, C.c_uint32, C.c_char_p]
         L.adsbdec_b200_envelope.argtypes = [C.c_int, vp, C.c_size_t, C.c_int, u64, vp, C.c_size_t]
@@ -263,6 +264,12 @@ class Decoder:
         n = C.c_uint64()
         _check(lib().adsbdec_b200_kernel_time(self._h, C.byref(ms), C.byref(n), int(reset)))
         return ms.value, n.value
+
+    def host_time(self, reset: bool = False):
+        """Host wall ms by phase: wait_job, sort, resolve, stats_issue, sink, -, wait_upload, jobs."""
+        a = (C.c_double * 8)()
+        _check(lib().adsbdec_b200_host_time(self._h, a, int(reset)))
+        return dict(zip(("wait_job", "sort", "resolve", "stats_issue", "sink", "rsv", "wait_upload", "jobs"), a))
 
     def fused_time(self, reset: bool = False):
         ms = C.c_double()

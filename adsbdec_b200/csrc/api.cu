@@ -19,7 +19,12 @@
 #include <string.h>
 #include <unistd.h>
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
 #include <algorithm>
+#include <chrono>
 #include <new>
 #include <vector>
 
@@ -61,6 +66,7 @@ int fail(int code, const char *fmt, ...)
 constexpr int64_t kCarryBack = 128;        // raw samples kept in front of the next owned offset
 constexpr int64_t kCarryMax = 1 << 14;     // room in front of a batch for the carried tail
 constexpr int64_t kDefaultBatch = 32ll << 20;
+constexpr int64_t kDeviceJob = 256ll << 20;  // samples per scan job when the data is already in HBM
 constexpr int64_t kAmpChunk = 8ll << 20;   // generic path: offsets per envelope scratch pass
 constexpr int64_t kMinFused = 1 << 16;     // ranges smaller than this use the generic kernels
 constexpr int64_t kStageSlice = 4ll << 20; // pageable pushes are staged and uploaded in slices
@@ -77,6 +83,42 @@ __global__ void k_reset_counters(Counters *c)
 }
 
 __global__ void k_zero_u64(unsigned long long *p) { *p = 0; }
+
+// Small host->device transfers are done by kernels that read page-locked host memory directly:
+// a cudaMemcpyAsync would queue behind the sample uploads on the copy engine and stall the job.
+__global__ void k_fetch_u64(unsigned long long *dst, const unsigned long long *host_src, size_t n)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+		dst[i] = host_src[i];
+}
+
+// Builds the span table of one fused launch on the device.
+__global__ void k_make_spans(FusedSpan *sp, int *ticket, int n_sp, long long n0, long long n1, long long per,
+                             int r, unsigned long long raw_w0, long long w_lo, long long w_hi, int S, int lookback)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i == 0)
+		*ticket = 0;
+	if (i >= n_sp)
+		return;
+	FusedSpan s;
+	s.own_begin = n0 + (long long)i * per;
+	s.own_end = min(n1, s.own_begin + per);
+	long long q = s.own_begin - r;
+	q -= ((q % 28) + 28) % 28;
+	s.j_begin = q + r;  // at or before own_begin, == r (mod 28)
+	s.raw_w0 = raw_w0;
+	s.w_lo = w_lo;
+	s.w_hi = w_hi;
+	s.n_blocks = (int)((s.own_end + lookback - s.j_begin + S - 1) / S);
+	s.pad_ = 0;
+	sp[i] = s;
+}
+
+inline double now_ms()
+{
+	return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 inline int64_t align_down(int64_t v, int64_t a) { return v - (((v % a) + a) % a); }
 
@@ -130,7 +172,7 @@ struct adsbdec_b200 {
 	unsigned long long try_cap[kSlots] = {0, 0};
 	unsigned long long *d_spans[kSlots] = {nullptr, nullptr}, *h_spans[kSlots] = {nullptr, nullptr};
 	size_t span_cap[kSlots] = {0, 0};
-	FusedSpan *d_fspans[kSlots] = {nullptr, nullptr}, *h_fspans[kSlots] = {nullptr, nullptr};
+	FusedSpan *d_fspans[kSlots] = {nullptr, nullptr};
 	int fspan_cap[kSlots] = {0, 0};
 	int *d_ticket[kSlots] = {nullptr, nullptr};
 	cudaEvent_t ev_done[kSlots] = {nullptr, nullptr};
@@ -157,6 +199,10 @@ struct adsbdec_b200 {
 
 	std::vector<adsbdec_b200_candidate_t> cand_tmp;
 	std::vector<uint32_t> bucket;
+	std::vector<size_t> bucket_end;
+	// host-side wall time by phase (ms): 0 wait for job, 1 sort/repack, 2 resolve, 3 stats pass issue,
+	// 4 sink/emit, 5 upload issue + staging memcpy, 6 wait for uploads, 7 jobs completed
+	double host_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
 	// parity taps of the fused kernel (adsbdec_b200_debug_fused)
 	float *dbg_amp = nullptr;
@@ -247,39 +293,35 @@ int launch_fused_range(adsbdec_b200 *h, int s, const Job &j, int64_t n0, int64_t
 	if (r < 0)
 		return fail(ADSB_B200_EINVAL, "internal: no FIR phase for shift %d", shift);
 	const int64_t total = n1 - n0;
-	const int want = h->fused_ctas * 4;
-	int64_t per = (total + want - 1) / want;
-	per = std::max<int64_t>(per, 8 * (int64_t)S);
-	per = std::min<int64_t>(per, 1ll << 29);
-	per = (per + S - 1) / S * S;
+	// Span length: a whole number of sub-blocks INCLUDING the look-back tail, so that the last
+	// sub-block of a span is not mostly wasted: per = k*S - (lookback + alignment slack).
+	// Big ranges get 4 spans per CTA (the dynamic scheduler evens out the tail); small ones
+	// exactly one span per CTA or fewer - never "a few more spans than CTAs".
+	const int64_t tail = lookback + 64;
+	const int want = total >= (int64_t)h->fused_ctas * 4 * 16 * S ? h->fused_ctas * 4 : h->fused_ctas;
+	int64_t nbk = ((total + want - 1) / want + tail + S - 1) / S;
+	nbk = std::max<int64_t>(nbk, 2);
+	nbk = std::min<int64_t>(nbk, (1ll << 29) / S);
+	const int64_t per = nbk * S - tail;
 	const int n_sp = (int)((total + per - 1) / per);
 	if (n_sp > h->fspan_cap[s]) {
+		CU(cudaStreamSynchronize(h->st));
 		if (h->d_fspans[s]) cudaFree(h->d_fspans[s]);
-		if (h->h_fspans[s]) cudaFreeHost(h->h_fspans[s]);
 		h->fspan_cap[s] = n_sp + 64;
 		CU(cudaMalloc(&h->d_fspans[s], h->fspan_cap[s] * sizeof(FusedSpan)));
-		CU(cudaMallocHost(&h->h_fspans[s], h->fspan_cap[s] * sizeof(FusedSpan)));
 	}
 	if (!h->d_ticket[s])
 		CU(cudaMalloc(&h->d_ticket[s], sizeof(int)));
 	if (j.u0 % 8 || ((uintptr_t)j.buf % 16))
 		return fail(ADSB_B200_EINVAL, "internal: fused window not 16-byte aligned");
 	const int64_t w_lo = j.u0 / 2, w_hi = align_down(j.u1 / 2, 4);
-	for (int i = 0; i < n_sp; i++) {
-		FusedSpan &sp = h->h_fspans[s][i];
-		sp.own_begin = n0 + i * per;
-		sp.own_end = std::min<int64_t>(n1, sp.own_begin + per);
-		sp.j_begin = align_down(sp.own_begin - r, 28) + r;  // at or before own_begin, == r (mod 28)
-		if (sp.j_begin - 8 < w_lo && j.u0 != 0)
-			return fail(ADSB_B200_EINVAL, "internal: window lacks FIR history");
-		sp.raw_w0 = (unsigned long long)(uintptr_t)j.buf - 2ull * (unsigned long long)j.u0;
-		sp.w_lo = w_lo;
-		sp.w_hi = w_hi;
-		sp.n_blocks = (int)((sp.own_end + lookback - sp.j_begin + S - 1) / S);
-		sp.pad_ = 0;
-	}
-	CU(cudaMemcpyAsync(h->d_fspans[s], h->h_fspans[s], n_sp * sizeof(FusedSpan), cudaMemcpyHostToDevice, h->st));
-	CU(cudaMemsetAsync(h->d_ticket[s], 0, sizeof(int), h->st));
+	const int64_t jb0 = align_down(n0 - r, 28) + r;
+	if (jb0 - 8 < w_lo && j.u0 != 0)
+		return fail(ADSB_B200_EINVAL, "internal: window lacks FIR history");
+	k_make_spans<<<(n_sp + 127) / 128, 128, 0, h->st>>>(
+	    h->d_fspans[s], h->d_ticket[s], n_sp, n0, n1, per, r,
+	    (unsigned long long)(uintptr_t)j.buf - 2ull * (unsigned long long)j.u0, w_lo, w_hi, S, lookback);
+	CU(cudaGetLastError());
 	FusedParams p;
 	p.spans = h->d_fspans[s];
 	p.n_spans = n_sp;
@@ -297,7 +339,7 @@ int launch_fused_range(adsbdec_b200 *h, int s, const Job &j, int64_t n0, int64_t
 	p.dbg_b = h->dbg_b;
 	p.dbg_n = h->dbg_n;
 	if (h->dbg_amp)
-		h->dbg_jb = h->h_fspans[s][0].j_begin;
+		h->dbg_jb = jb0;
 	CU(cudaEventRecord(h->ev_fa[s], h->st));
 	CU(launch_fused(p, std::min(h->fused_ctas, n_sp), h->st));
 	CU(cudaEventRecord(h->ev_fb[s], h->st));
@@ -383,9 +425,11 @@ int stats_pass(adsbdec_b200 *h, int s, size_t first_new_frame, bool with_slot_li
 		h->h_spans[s][2 * i] = f.n;
 		h->h_spans[s][2 * i + 1] = f.n + (f.len == 7 ? kSkipShort : kSkipLong);
 	}
-	if (ns)
-		CU(cudaMemcpyAsync(h->d_spans[s], h->h_spans[s], ns * 2 * sizeof(unsigned long long),
-		                   cudaMemcpyHostToDevice, h->st));
+	if (ns) {
+		k_fetch_u64<<<(unsigned)std::min<size_t>(64, (2 * ns + 255) / 256), 256, 0, h->st>>>(h->d_spans[s],
+		                                                                                    h->h_spans[s], 2 * ns);
+		CU(cudaGetLastError());
+	}
 	const int pin = h->pend_in, pout = 1 - h->pend_in;
 	const unsigned long long scan_end = h->res->scan_end();
 	if (with_slot_list) {
@@ -402,39 +446,95 @@ int stats_pass(adsbdec_b200 *h, int s, size_t first_new_frame, bool with_slot_li
 	return 0;
 }
 
+// Fused-kernel records carry the frame as four 28-bit words; repack into bytes.
+inline void repack_candidate(adsbdec_b200_candidate_t &o, const CandRec &c)
+{
+	memcpy(&o, &c, sizeof(CandRec));
+	if (!(o.len & kCandNibbleWords))
+		return;
+	o.len &= ~kCandNibbleWords;
+	uint32_t w[4];
+	memcpy(w, c.bytes, 16);
+	unsigned __int128 f;
+	int nbits;
+	if (o.len == 14) {
+		f = ((unsigned __int128)w[0] << 84) | ((unsigned __int128)w[1] << 56) | ((unsigned __int128)w[2] << 28) | w[3];
+		nbits = 112;
+	} else {
+		f = ((unsigned __int128)w[0] << 28) | w[1];
+		nbits = 56;
+	}
+	memset(o.bytes, 0, 16);
+	for (uint32_t k = 0; k < o.len; k++)
+		o.bytes[k] = (uint8_t)(f >> (nbits - 8 - 8 * (int)k));
+}
+
 // The kernels append candidates in whatever order CTAs finish.  Bucket them by offset (counting
-// sort over 4096-offset buckets: one pass to count, one to scatter), then order the handful of
-// entries inside each bucket - O(n) instead of a comparison sort of 32-byte records.
+// sort over 4096-offset buckets: histogram, prefix, scatter), then order the handful of entries
+// inside each bucket - O(n) instead of a comparison sort of 32-byte records.  Large lists are
+// split over a few host threads (OpenMP): per-thread histograms, one prefix, parallel scatter.
 void sort_candidates(adsbdec_b200 *h, const CandRec *c, size_t nc, int64_t n0, int64_t n1)
 {
 	static_assert(sizeof(CandRec) == sizeof(adsbdec_b200_candidate_t), "record layouts must agree");
 	const int shift = 12;
 	const size_t nb = (size_t)((n1 - n0) >> shift) + 2;
-	h->bucket.assign(nb + 1, 0);
-	for (size_t i = 0; i < nc; i++)
-		h->bucket[(size_t)(((int64_t)c[i].n - n0) >> shift) + 1]++;
-	for (size_t b = 0; b < nb; b++)
-		h->bucket[b + 1] += h->bucket[b];
+	int T = 1;
+#ifdef _OPENMP
+	if (nc >= (1u << 15))
+		T = std::max(1, std::min(8, omp_get_max_threads()));
+#endif
+	h->bucket.assign((size_t)T * nb + 1, 0);
+	uint32_t *hist = h->bucket.data();
 	h->cand_tmp.resize(nc);
 	adsbdec_b200_candidate_t *out = h->cand_tmp.data();
-	for (size_t i = 0; i < nc; i++) {
-		const size_t b = (size_t)(((int64_t)c[i].n - n0) >> shift);
-		memcpy(&out[h->bucket[b]++], &c[i], sizeof(CandRec));
-	}
-	// bucket[b] is now the END of bucket b; insertion sort inside each (a few entries)
-	size_t lo = 0;
-	for (size_t b = 0; b < nb; b++) {
-		const size_t hi = h->bucket[b];
-		for (size_t i = lo + 1; i < hi; i++) {
-			const adsbdec_b200_candidate_t v = out[i];
-			size_t k = i;
-			while (k > lo && out[k - 1].n > v.n) {
-				out[k] = out[k - 1];
-				k--;
+	std::vector<size_t> &bend = h->bucket_end;
+	bend.resize(nb);
+#pragma omp parallel num_threads(T)
+	{
+#ifdef _OPENMP
+		const int t = omp_get_thread_num();
+#else
+		const int t = 0;
+#endif
+		const size_t lo = nc * (size_t)t / T, hi = nc * (size_t)(t + 1) / T;
+		uint32_t *my = hist + (size_t)t * nb;
+		for (size_t i = lo; i < hi; i++)
+			my[(size_t)(((int64_t)c[i].n - n0) >> shift)]++;
+#pragma omp barrier
+#pragma omp single
+		{
+			// exclusive prefix in (bucket, thread) order: thread t's slice of bucket b
+			uint32_t run = 0;
+			for (size_t b = 0; b < nb; b++) {
+				for (int k = 0; k < T; k++) {
+					const uint32_t v = hist[(size_t)k * nb + b];
+					hist[(size_t)k * nb + b] = run;
+					run += v;
+				}
+				bend[b] = run;
 			}
-			out[k] = v;
 		}
-		lo = hi;
+		for (size_t i = lo; i < hi; i++) {
+			const size_t b = (size_t)(((int64_t)c[i].n - n0) >> shift);
+			repack_candidate(out[my[b]++], c[i]);
+		}
+#pragma omp barrier
+		// insertion sort inside each bucket (a few entries), buckets split over the threads
+		const size_t blo = nb * (size_t)t / T, bhi = nb * (size_t)(t + 1) / T;
+		size_t s0 = blo ? bend[blo - 1] : 0;
+		for (size_t b = blo; b < bhi; b++) {
+			const size_t e0 = bend[b];
+			for (size_t i = s0 + 1; i < e0; i++) {
+				const adsbdec_b200_candidate_t v = out[i];
+				size_t k = i;
+				while (k > s0 && out[k - 1].n > v.n) {
+					out[k] = out[k - 1];
+					k--;
+				}
+				out[k] = v;
+			}
+			s0 = e0;
+		}
 	}
 }
 
@@ -449,7 +549,9 @@ int complete_job(adsbdec_b200 *h, int s)
 	if (scanned) {
 		bool force_generic = false;
 		for (int attempt = 0;; attempt++) {
+			const double t0 = now_ms();
 			CU(cudaEventSynchronize(h->ev_done[s]));
+			h->host_ms[0] += now_ms() - t0;
 			float ms = 0;
 			cudaEventElapsedTime(&ms, h->ev_a[s], h->ev_b[s]);
 			h->kernel_ms += ms;
@@ -478,8 +580,10 @@ int complete_job(adsbdec_b200 *h, int s)
 			                   (nc - kSpecCands) * sizeof(CandRec), cudaMemcpyDeviceToHost, h->st));
 			CU(cudaStreamSynchronize(h->st));
 		}
+		const double t1 = now_ms();
 		if (nc)
 			sort_candidates(h, h->h_cands[s], nc, j.n0, j.n1);
+		h->host_ms[1] += now_ms() - t1;
 	} else {
 		CU(cudaEventSynchronize(h->ev_done[s]));
 	}
@@ -487,10 +591,17 @@ int complete_job(adsbdec_b200 *h, int s)
 	if (!j.resolve)
 		return 0;
 	const size_t f0 = h->frames.size();
+	const double t2 = now_ms();
 	h->res->feed(h->cand_tmp.data(), h->cand_tmp.size(), (uint64_t)std::max<int64_t>(j.n1, 0), (uint64_t)j.total_out,
 	             h->frames);
+	const double t3 = now_ms();
 	RC(stats_pass(h, s, f0, scanned));
+	const double t4 = now_ms();
 	emit_new_frames(h);
+	h->host_ms[2] += t3 - t2;
+	h->host_ms[3] += t4 - t3;
+	h->host_ms[4] += now_ms() - t4;
+	h->host_ms[7] += 1;
 	return 0;
 }
 
@@ -716,7 +827,6 @@ void adsbdec_b200_close(adsbdec_b200_t *h)
 		if (h->d_spans[s]) cudaFree(h->d_spans[s]);
 		if (h->h_spans[s]) cudaFreeHost(h->h_spans[s]);
 		if (h->d_fspans[s]) cudaFree(h->d_fspans[s]);
-		if (h->h_fspans[s]) cudaFreeHost(h->h_fspans[s]);
 		if (h->d_ticket[s]) cudaFree(h->d_ticket[s]);
 		if (h->ev_a[s]) cudaEventDestroy(h->ev_a[s]);
 		if (h->ev_b[s]) cudaEventDestroy(h->ev_b[s]);
@@ -819,8 +929,11 @@ int adsbdec_b200_push(adsbdec_b200_t *h, const uint16_t *samples, size_t n)
 		h->pushed += (int64_t)take;
 		done += take;
 	}
-	if (direct)
+	if (direct) {
+		const double t0 = now_ms();
 		CU(cudaStreamSynchronize(h->st_copy));  // the caller may reuse its buffer on return
+		h->host_ms[6] += now_ms() - t0;
+	}
 	return 0;
 }
 
@@ -875,7 +988,7 @@ int adsbdec_b200_push_device(adsbdec_b200_t *h, const void *dev_samples, size_t 
 	}
 	h->pushed = piece_u1;
 	for (int64_t end = piece_u0; end < piece_u1;) {
-		end = std::min(piece_u1, end + h->batch);
+		end = std::min(piece_u1, end + std::max(h->batch, kDeviceJob));
 		// window: from the FIR history of the next owned offset to `end`, inside the caller's memory
 		const int64_t w0 = std::max<int64_t>(piece_u0, align_down(2 * h->own_next - kCarryBack, 8));
 		RC(submit_window(h, src + (w0 - piece_u0), w0, end));
@@ -981,6 +1094,18 @@ int adsbdec_b200_kernel_time(adsbdec_b200_t *h, double *ms, uint64_t *launches, 
 	if (reset) {
 		h->kernel_ms = 0;
 		h->launches = 0;
+	}
+	return 0;
+}
+
+int adsbdec_b200_host_time(adsbdec_b200_t *h, double ms[8], int reset)
+{
+	if (!h || !ms)
+		return fail(ADSB_B200_EINVAL, "null argument");
+	for (int i = 0; i < 8; i++) {
+		ms[i] = h->host_ms[i];
+		if (reset)
+			h->host_ms[i] = 0;
 	}
 	return 0;
 }

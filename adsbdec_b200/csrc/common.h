@@ -25,6 +25,9 @@ struct alignas(16) CandRec {
 	uint8_t bytes[16]; // first len bytes
 };
 static_assert(sizeof(CandRec) == 32, "CandRec layout");
+// Flag in CandRec::len: `bytes` holds four 28-bit words (frame bits 28k..28k+27, MSB first in bits
+// 27..0 of word k) instead of the frame bytes; the host repacks them.
+constexpr uint32_t kCandNibbleWords = 0x100u;
 
 // A "try" (offset that reached validShort/validLong, valid.c:46,68): class in the top 2 bits.
 constexpr int kTryClsShift = 62;

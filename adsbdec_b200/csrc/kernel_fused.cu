@@ -27,8 +27,9 @@
 //     transposed inside 8-lane groups (8 runs of 28 = 7 words of 32) into bit arrays;
 //   * stage 3 (gate): word-parallel: preamble = P[n] & Q[n+30]; DF gate = five bits of B at
 //     stride 10; survivors go to a shared-memory list;
-//   * stage 4 (slice+CRC): one warp per survivor; lane l pulls frame bits 4l..4l+3 out of B with
-//     one funnel shift, XORs their single-bit syndromes, warp REDUX.XOR gives the syndrome.
+//   * stage 4 (slice+CRC): four lanes per survivor; a lane pulls its 7 nibbles of the frame out of
+//     B (one funnel shift + one multiply each), looks their syndromes up in a 28x16 table and the
+//     four lanes XOR-reduce; syndrome 0 -> the frame bits and pw go to the candidate list.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -51,7 +52,6 @@ constexpr int RUNS = NT + 56;       // envelope ring, in runs of 28 floats
 constexpr int WR = 512;             // bit-array ring, in 32-bit words
 constexpr int WPB = S / 32;         // bit words per sub-block (224)
 constexpr int CAND_CAP = 1024;      // survivors of the DF gate per sub-block
-constexpr int SYN_WORDS = 112;
 
 static_assert(LAG3 % 32 == 0 && LAG3 >= kLookahead + LAG2 * R + 32 + 8, "stage-3 lag");
 static_assert(RUNS * R >= S + LAG3 + R, "envelope ring too small");
@@ -63,9 +63,9 @@ struct Smem {
 	float amp[RUNS * R];                // 34944 B
 	uint32_t pbits[WR];                 // P[n]: first pulse pair beats its gap
 	uint32_t qbits[WR];                 // Q[n]: pulse at n+5.. beats the gap at n..
-	uint32_t bbits[WR];                 // B[n]: PPM decision
+	uint32_t bbits[WR + 4];             // B[n]: PPM decision; bbits[WR] mirrors bbits[0]
 	uint32_t cand[CAND_CAP];
-	uint32_t syn[SYN_WORDS];            // single-bit syndromes x^(111-b) mod G
+	uint32_t lut[28 * 16];              // lut[g][v]: syndrome of nibble g of a 112-bit frame holding v
 	unsigned long long full[NSTAGE];    // mbarriers
 	unsigned long long try_base;
 	int ncand;
@@ -155,12 +155,22 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const FusedParams p)
 	const int warp = tid >> 5;
 
 	// ---- one-time setup --------------------------------------------------
-	if (tid < SYN_WORDS) {
-		// x^(111-tid) mod G, by shifting x^0 up (crc.h's table is the byte-wise form of this)
-		uint32_t r = 1;
-		for (int i = 0; i < 111 - tid; i++)
-			r = (r & 0x800000u) ? ((r << 1) ^ kCrcPoly) & 0xFFFFFFu : (r << 1);
-		sm.syn[tid] = r;
+	for (int e = tid; e < 28 * 16; e += NT) {
+		// Frame bit b contributes x^(111-b) mod G to the syndrome (crc.h's table is the byte-wise
+		// form of the same polynomial division; the last 24 bits are XORed in unreduced,
+		// crc.h:40-42).  Entry [g][v]: nibble g (bits 4g..4g+3, MSB first) holding value v.
+		// A 56-bit frame is the tail of the table: its nibble g is row g+14.
+		const int g = e >> 4, v = e & 15;
+		uint32_t acc = 0;
+		for (int kb = 0; kb < 4; kb++) {
+			if (!((v >> (3 - kb)) & 1))
+				continue;
+			uint32_t r = 1;
+			for (int i = 0; i < 111 - (4 * g + kb); i++)
+				r = (r & 0x800000u) ? ((r << 1) ^ kCrcPoly) & 0xFFFFFFu : (r << 1);
+			acc ^= r;
+		}
+		sm.lut[e] = acc;
 	}
 	if (tid == 0) {
 		for (int s = 0; s < NSTAGE; s++)
@@ -193,6 +203,7 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const FusedParams p)
 		const long long jb = sp.j_begin;
 		const int nb = sp.n_blocks;
 		const char *raw0 = reinterpret_cast<const char *>(sp.raw_w0);  // address of abs word 0
+		const uint32_t own_lo = (uint32_t)(sp.own_begin - jb), own_hi = (uint32_t)(sp.own_end - jb);
 
 		auto issue = [&](int kb, int s) {
 			// elected thread: one bulk copy for the valid part of sub-block kb
@@ -356,6 +367,8 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const FusedParams p)
 					sm.pbits[wi] = pw_;
 					sm.qbits[wi] = qw_;
 					sm.bbits[wi] = bw_;
+					if (wi == 0)
+						sm.bbits[WR] = bw_;  // mirror: stage 4 reads word pairs without wrapping
 					if (p.dbg_p && span_idx == 0) {
 						const long long at = (long long)((g2 - j) >> 3) * 7 + j;
 						if (at < p.dbg_n / 32) {
@@ -374,11 +387,20 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const FusedParams p)
 				if (wd >= 0) {
 					const uint32_t p0 = sm.pbits[wd & (WR - 1)];
 					const uint32_t q0 = sm.qbits[wd & (WR - 1)], q1 = sm.qbits[(wd + 1) & (WR - 1)];
-					const uint32_t b2 = sm.bbits[(wd + 2) & (WR - 1)], b3 = sm.bbits[(wd + 3) & (WR - 1)],
-					               b4 = sm.bbits[(wd + 4) & (WR - 1)];
 					// demod.c:107: p1 > 2*s1 at n, p2 > 2*s2 at n+30
-					const uint32_t pre = p0 & __funnelshift_l(q1, q0, 30);
+					uint32_t pre = p0 & __funnelshift_l(q1, q0, 30);
+					// ownership: only offsets in [own_lo, own_hi) (relative to j_begin) are emitted here
+					const uint32_t o0 = (uint32_t)wd * 32u;
+					if (o0 < own_lo || o0 + 32u > own_hi) {
+						const uint32_t lo = own_lo > o0 ? own_lo - o0 : 0u;              // first owned bit index
+						const uint32_t hi = own_hi > o0 ? min(own_hi - o0, 32u) : 0u;    // one past the last
+						const uint32_t m_lo = lo >= 32u ? 0u : 0xFFFFFFFFu >> lo;
+						const uint32_t m_hi = hi >= 32u ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> hi);
+						pre &= m_lo & m_hi;
+					}
 					if (pre) {
+						const uint32_t b2 = sm.bbits[(wd + 2) & (WR - 1)], b3 = sm.bbits[(wd + 3) & (WR - 1)],
+						               b4 = sm.bbits[(wd + 4) & (WR - 1)];
 						// first five data bits sit at n+80, +90, +100, +110, +120 (demod.c:110, :46-81)
 						const uint32_t x7 = __funnelshift_l(b3, b2, 16);  // 80  = 64 + 16
 						const uint32_t x6 = __funnelshift_l(b3, b2, 26);  // 90  = 64 + 26
@@ -389,25 +411,24 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const FusedParams p)
 						const uint32_t m18 = p.accept_df18 ? (pre & x7 & ~x6 & ~x5 & x4 & ~x3) : 0u;  // 10010
 						const uint32_t m11 = pre & ~x7 & x6 & ~x5 & x4 & x3;                // 01011
 						uint32_t any = m17 | m18 | m11;
-						while (any) {
-							const int i = __clz(any);
-							const uint32_t bit = 0x80000000u >> i;
-							any &= ~bit;
-							const uint32_t n_rel = (uint32_t)wd * 32u + (uint32_t)i;
-							const long long n = jb + (long long)n_rel;
-							if (n >= sp.own_begin && n < sp.own_end) {
+						if (any) {
+							int slot = atomicAdd(&sm.ncand, __popc(any));
+							do {
+								const int i = __clz(any);
+								const uint32_t bit = 0x80000000u >> i;
+								any &= ~bit;
 								const uint32_t cls = (m17 & bit) ? kClsDF17 : (m11 & bit) ? kClsDF11 : kClsDF18;
-								const int slot = atomicAdd(&sm.ncand, 1);
 								if (slot < CAND_CAP)
-									sm.cand[slot] = n_rel | (cls << 30);
-							}
+									sm.cand[slot] = (o0 + (uint32_t)i) | (cls << 30);
+								slot++;
+							} while (any);
 						}
 					}
 				}
 			}
 			__syncthreads();  // (3) survivor list complete
 
-			// ================= stage 4: slice + CRC, one warp per survivor ===
+			// ================= stage 4: slice + CRC, four lanes per survivor ==
 			int ncand = sm.ncand;
 			if (ncand > CAND_CAP) {
 				if (tid == 0)
@@ -416,63 +437,65 @@ __global__ void __launch_bounds__(NT, 2) k_fused(const FusedParams p)
 			}
 			if (p.want_tries && tid == 0 && ncand > 0)
 				sm.try_base = atomicAdd(&p.ctr->n_try, (unsigned long long)ncand);
-			for (int ci = warp; ci < ncand; ci += NT / 32) {
-				const uint32_t ent = sm.cand[ci];
-				const uint32_t n_rel = ent & 0x3FFFFFFFu;
-				const uint32_t cls = ent >> 30;
-				const bool is_long = cls != kClsDF11;
-				const int nnib = is_long ? 28 : 14;
-				uint32_t acc = 0, x = 0;
-				if (lane < nnib) {
-					// frame bit b sits at n + 80 + 10 b; this lane takes b = 4*lane .. 4*lane+3
-					const uint32_t pb = n_rel + 80u + 40u * (uint32_t)lane;
-					const uint32_t wi = pb >> 5;
-					const uint32_t w0 = sm.bbits[wi & (WR - 1)], w1 = sm.bbits[(wi + 1) & (WR - 1)];
-					x = __funnelshift_l(w1, w0, pb & 31u);  // bits 31, 21, 11, 1
-					const uint4 sy = *reinterpret_cast<const uint4 *>(&sm.syn[4 * lane + (is_long ? 0 : 56)]);
-					acc = ((uint32_t)bfe_s1(x, 31) & sy.x) ^ ((uint32_t)bfe_s1(x, 21) & sy.y) ^
-					      ((uint32_t)bfe_s1(x, 11) & sy.z) ^ ((uint32_t)bfe_s1(x, 1) & sy.w);
-				}
-				// valid.c:48-52 / :70-74: CRC over all but the last 3 bytes, XOR the last 3, == 0
-				const uint32_t syndrome = __reduce_xor_sync(0xFFFFFFFFu, acc);
-				if (syndrome == 0) {
-					// nibble of this lane, MSB first, then 8 nibbles -> one big-endian word per 8 lanes
-					const uint32_t y = x & 0x80200802u;
-					const uint32_t nib = lane < nnib ? (y * 0x08040201u) >> 28 : 0u;
-					const uint32_t grp = 0xFFu << (lane & 24);
-					const uint32_t word = __reduce_or_sync(grp, nib << (4 * (7 - (lane & 7))));
-					const uint32_t w0 = __shfl_sync(0xFFFFFFFFu, word, 0), w1 = __shfl_sync(0xFFFFFFFFu, word, 8),
-					               w2 = __shfl_sync(0xFFFFFFFFu, word, 16), w3 = __shfl_sync(0xFFFFFFFFu, word, 24);
-					if (lane == 0) {
-						// demod.c:102-105, :127: pw from the int-truncated preamble sums
-						auto amp_at = [&](uint32_t o) -> float {
-							const uint32_t run = o / R;
-							return sm.amp[(run % RUNS) * R + (o - run * R)];
-						};
-						const int p1 = __float2int_rz(__fadd_rn(amp_at(n_rel), amp_at(n_rel + 10)));
-						const int p2 = __float2int_rz(__fadd_rn(amp_at(n_rel + 35), amp_at(n_rel + 45)));
-						const unsigned long long slot = atomicAdd(&p.ctr->n_cand, 1ull);
-						if (slot < p.cand_cap) {
-							uint4 head, body;
-							const unsigned long long n = (unsigned long long)(jb + (long long)n_rel);
-							head.x = (uint32_t)n;
-							head.y = (uint32_t)(n >> 32);
-							head.z = (uint32_t)((p1 + p2) / 4);
-							head.w = is_long ? 14u : 7u;
-							body.x = __byte_perm(w0, 0, 0x0123);  // big-endian word -> byte order in memory
-							body.y = __byte_perm(w1, 0, 0x0123);
-							body.z = __byte_perm(w2, 0, 0x0123);
-							body.w = __byte_perm(w3, 0, 0x0123);
-							if (!is_long) {
-								body.y &= 0x00FFFFFFu;
-								body.z = 0;
+			{
+				const int sub = lane & 3;  // quarter of the frame this lane slices: nibbles 7*sub .. 7*sub+6
+				for (int c0 = warp * 8; c0 < ncand; c0 += (NT / 32) * 8) {
+					const int ci = c0 + (lane >> 2);
+					const bool have = ci < ncand;
+					const uint32_t ent = have ? sm.cand[ci] : 0u;
+					const uint32_t n_rel = ent & 0x3FFFFFFFu;
+					const bool is_long = (ent >> 30) != kClsDF11;
+					// short frames are the last 56 bits of the syndrome table and only use sub 0, 1
+					const bool active = have && (is_long || sub < 2);
+					// frame bit b sits at n + 80 + 10 b; nibble g starts at bit 4g
+					const uint32_t pb0 = n_rel + 80u + 280u * (uint32_t)sub;
+					const uint32_t lut0 = (uint32_t)(7 * sub + (is_long ? 0 : 14)) * 64u;  // byte offset of row g
+					uint32_t acc = 0, bits28 = 0;
+					if (active) {
+#pragma unroll
+						for (int s_ = 0; s_ < 7; s_++) {
+							const uint32_t pb = pb0 + 40u * s_;
+							const uint32_t wa = (pb >> 3) & ((WR - 1) << 2);  // byte offset of the word in the ring
+							const uint32_t w0 = *reinterpret_cast<const uint32_t *>(
+							    reinterpret_cast<const char *>(sm.bbits) + wa);
+							const uint32_t w1 = *reinterpret_cast<const uint32_t *>(
+							    reinterpret_cast<const char *>(sm.bbits) + wa + 4);  // bbits[WR] mirrors bbits[0]
+							const uint32_t x = __funnelshift_l(w1, w0, pb & 31u);  // bits 31, 21, 11, 1
+							const uint32_t nib = ((x & 0x80200802u) * 0x08040201u) >> 28;
+							acc ^= *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(sm.lut) +
+							                                            lut0 + 64u * s_ + 4u * nib);
+							bits28 = bits28 * 16u + nib;
+						}
+					}
+					// valid.c:48-52 / :70-74: CRC over all but the last 3 bytes, XOR the last 3, == 0
+					acc ^= __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
+					acc ^= __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
+					const bool ok = have && acc == 0;
+					if (__any_sync(0xFFFFFFFFu, ok)) {
+						// demod.c:102-105, :127: pw from the int-truncated preamble sums; the four lanes
+						// fetch a[n], a[n+10], a[n+35], a[n+45]
+						const uint32_t o = n_rel + (sub == 0 ? 0u : sub == 1 ? 10u : sub == 2 ? 35u : 45u);
+						const float av = sm.amp[o % (uint32_t)(RUNS * R)];
+						const float pair = __fadd_rn(av, __shfl_xor_sync(0xFFFFFFFFu, av, 1));
+						const int pi = __float2int_rz(pair);
+						const int psum = pi + __shfl_xor_sync(0xFFFFFFFFu, pi, 2);
+						unsigned long long slot = 0;
+						if (ok && sub == 0)
+							slot = atomicAdd(&p.ctr->n_cand, 1ull);
+						slot = __shfl_sync(0xFFFFFFFFu, slot, lane & ~3);
+						if (ok) {
+							if (slot < p.cand_cap) {
+								uint32_t *out = reinterpret_cast<uint32_t *>(&p.cands[slot]);
+								if (sub == 0) {
+									const unsigned long long n = (unsigned long long)(jb + (long long)n_rel);
+									*reinterpret_cast<uint4 *>(out) =
+									    make_uint4((uint32_t)n, (uint32_t)(n >> 32), (uint32_t)(psum / 4),
+									               (is_long ? 14u : 7u) | kCandNibbleWords);
+								}
+								out[4 + sub] = bits28;
+							} else if (sub == 0) {
+								atomicOr(&p.ctr->overflow, 1u);
 							}
-							body.w &= 0x0000FFFFu;
-							uint4 *out = reinterpret_cast<uint4 *>(&p.cands[slot]);
-							out[0] = head;
-							out[1] = body;
-						} else {
-							atomicOr(&p.ctr->overflow, 1u);
 						}
 					}
 				}
