@@ -385,6 +385,10 @@ int enqueue_job(adsbdec_b200 *h, int s, bool force_generic)
 		}
 		a = b;
 	}
+	if (j.used_fused) {
+		CU(launch_fill_pw(j.buf, j.u0, j.origin, h->d_cands[s], &h->d_ctr[s]->n_cand, h->cand_cap[s], h->st));
+		h->launches += 1;
+	}
 	CU(cudaEventRecord(h->ev_b[s], h->st));
 	CU(cudaMemcpyAsync(h->h_ctr[s], h->d_ctr[s], sizeof(Counters), cudaMemcpyDeviceToHost, h->st));
 	CU(cudaMemcpyAsync(h->h_cands[s], h->d_cands[s], std::min(kSpecCands, h->cand_cap[s]) * sizeof(CandRec),

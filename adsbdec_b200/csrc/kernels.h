@@ -12,6 +12,9 @@ namespace adsb {
 cudaError_t launch_envelope_generic(const uint16_t *raw, long long u_raw0, unsigned long long origin,
                                     long long j0, long long n, float *amp, cudaStream_t st);
 
+cudaError_t launch_fill_pw(const uint16_t *raw, long long u_raw0, unsigned long long origin, CandRec *cands,
+                           const unsigned long long *n_cand_ptr, unsigned long long cap, cudaStream_t st);
+
 cudaError_t launch_scan_generic(const float *amp, long long j_amp0, long long n0, long long count,
                                 int accept_df18, int want_tries, CandRec *cands,
                                 unsigned long long cand_cap, unsigned long long *tries,

@@ -26,24 +26,31 @@ static __constant__ CrcTable c_crc = make_crc_table();
 //   u_limit  : local samples [0, u_limit) exist; u < 0 reads as "ring still zero" (air.c:33)
 //   j0, n    : compute amp[j0 .. j0+n)
 //   amp      : output, amp[0] = envelope sample j0
-__global__ void k_envelope_generic(const uint16_t *__restrict__ raw, long long u_raw0,
-                                   unsigned long long phase_origin, long long j0, long long n,
-                                   float *__restrict__ amp)
+__device__ float envelope_at(const uint16_t *__restrict__ raw, long long u_raw0,
+                             unsigned long long phase_origin, long long j)
 {
-	long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-	if (i >= n)
-		return;
-	const long long j = j0 + i;
 	const long long T = 2 * j + 1;  // newest input sample of this output
 	// ring_pos after pushing sample T is T+1 (air.c:65: fidx++ after each store)
 	const uint32_t pos = (uint32_t)((unsigned long long)(T + 1) + phase_origin);
 	const uint32_t rot = kTaps - pos % kTaps;  // air.c:68: o = DSFLTLEN - fidx%DSFLTLEN
 	float si = 0.0f, sq = 0.0f;
+	// No 2^32 wrap of fidx among the last 32 samples: slot k simply holds the sample that is
+	// (slot(T) - k) mod 14 back.  Otherwise search (the ring is briefly "scrambled").
+	const uint32_t posT = pos - 1u;  // (uint32)(T + origin)
+	const bool plain = posT >= 32u;
+	const uint32_t slotT = posT % kTaps;
 #pragma unroll 1
 	for (int k = 0; k < kTaps; k++) {
 		// slot k holds the newest sample u <= T with (uint32)(u+origin)%14 == k; away from a
 		// 2^32 wrap that is within the last 14 samples, across one it can be up to 17 back.
 		float v = 0.0f;
+		if (plain) {
+			const long long u = T - (long long)((slotT + kTaps - (uint32_t)k) % kTaps);
+			if (u >= 0) {
+				const float x = (float)raw[u - u_raw0] - 2048.0f;  // air.c:64
+				v = (u & 2) ? -x : x;                              // air.c:79-82
+			}
+		} else
 		for (int back = 0; back < 32; back++) {
 			long long u = T - back;
 			if (u < 0)
@@ -60,7 +67,45 @@ __global__ void k_envelope_generic(const uint16_t *__restrict__ raw, long long u
 		else
 			si = __fmaf_rn(tap, v, si);  // air.c:70
 	}
-	amp[i] = __fmaf_rn(si, si, __fmul_rn(sq, sq));  // air.c:76: vmulss q,q ; vfmadd i,i
+	return __fmaf_rn(si, si, __fmul_rn(sq, sq));  // air.c:76: vmulss q,q ; vfmadd i,i
+}
+
+__global__ void k_envelope_generic(const uint16_t *__restrict__ raw, long long u_raw0,
+                                   unsigned long long phase_origin, long long j0, long long n,
+                                   float *__restrict__ amp)
+{
+	long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	amp[i] = envelope_at(raw, u_raw0, phase_origin, j0 + i);
+}
+
+// pw = (p1+p2)/4 (demod.c:102-105, :127) for the candidates the fused kernel found: it hands over
+// the frame bits only, the four envelope samples are recomputed here from the raw window.
+__global__ void k_fill_pw(const uint16_t *__restrict__ raw, long long u_raw0, unsigned long long phase_origin,
+                          CandRec *cands, const unsigned long long *n_cand_ptr, unsigned long long cap)
+{
+	unsigned long long n_cand = *n_cand_ptr;
+	if (n_cand > cap)
+		n_cand = cap;
+	// four lanes per candidate: a[n], a[n+10], a[n+35], a[n+45]
+	const int sub = threadIdx.x & 3;
+	const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x / 4;
+	const unsigned long long rounds = (n_cand + stride - 1) / stride;
+	unsigned long long i = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) / 4;
+	for (unsigned long long r = 0; r < rounds; r++, i += stride) {
+		const bool todo = i < n_cand && (cands[i].len & kCandNibbleWords);  // else a complete generic record
+		float a = 0.0f;
+		if (todo) {
+			const long long n = (long long)cands[i].n;
+			a = envelope_at(raw, u_raw0, phase_origin, n + (sub == 0 ? 0 : sub == 1 ? 10 : sub == 2 ? 35 : 45));
+		}
+		const float pair = __fadd_rn(a, __shfl_xor_sync(0xFFFFFFFFu, a, 1));
+		const int pi = __float2int_rz(pair);
+		const int sum = pi + __shfl_xor_sync(0xFFFFFFFFu, pi, 2);
+		if (todo && sub == 0)
+			cands[i].pw = (uint32_t)(sum / 4);
+	}
 }
 
 __device__ __forceinline__ bool ppm(const float *a, int at)
@@ -195,6 +240,13 @@ cudaError_t launch_envelope_generic(const uint16_t *raw, long long u_raw0, unsig
 		return cudaSuccess;
 	const int bs = 256;
 	k_envelope_generic<<<(unsigned)((n + bs - 1) / bs), bs, 0, st>>>(raw, u_raw0, origin, j0, n, amp);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_fill_pw(const uint16_t *raw, long long u_raw0, unsigned long long origin, CandRec *cands,
+                           const unsigned long long *n_cand_ptr, unsigned long long cap, cudaStream_t st)
+{
+	k_fill_pw<<<592, 256, 0, st>>>(raw, u_raw0, origin, cands, n_cand_ptr, cap);
 	return cudaGetLastError();
 }
 
