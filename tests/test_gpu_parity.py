@@ -178,3 +178,200 @@ def test_sink_order_and_content(adsb, oracle):
     d.finish()
     assert got == [(f.ts, f.pw, f.data) for f in ref.frames]
     assert [g[0] for g in got] == sorted(g[0] for g in got)
+
+
+# ---- golden vectors of the reference binary, file path, command line -------------------------
+
+import subprocess
+from pathlib import Path
+
+GOLDEN = sorted((Path(__file__).parent / "golden").glob("*.npz"))
+
+
+def _load_golden(p):
+    z = np.load(p)
+    d = {k: z[k] for k in z.files}
+    for k in ("avr", "avrmlat", "avrmlat_a", "beast_a"):
+        d[k] = d[k].tobytes()
+    return d
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[p.stem for p in GOLDEN])
+@pytest.mark.parametrize("kernel", [0, 1], ids=["fused", "generic"])
+def test_golden_reference_outputs_via_file(adsb, tmp_path, path, kernel):
+    """decode_file() (fileInput, air.c:219-246) on the exact bytes the reference read, against
+    what the reference binary printed (tests/golden/make_golden.py)."""
+    g = _load_golden(path)
+    f = tmp_path / "cap.bin"
+    g["samples"].astype("<u2").tofile(f)
+    d = adsb.Decoder(kernel=kernel)
+    assert d.decode_file(f) == 0
+    assert d.text(0) == g["avr"] and d.text(1) == g["avrmlat"]
+    assert [list(x) for x in d.stats()] == g["stats"].tolist()
+    da = adsb.Decoder(kernel=kernel, accept_df18=True)
+    assert da.decode_file(f) == 0
+    assert da.text(1) == g["avrmlat_a"] and da.text(2) == g["beast_a"]
+    assert [list(x) for x in da.stats()] == g["stats_a"].tolist()
+
+
+def _parse_stats(stderr: str):
+    t = k = None
+    for line in stderr.splitlines():
+        if line.startswith("Try :"):
+            t = [int(x) for x in line.split(":")[1].split()]
+        elif line.startswith("Ok :"):
+            k = [int(x) for x in line.split(":")[1].split()]
+    return [t, k]
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[p.stem for p in GOLDEN])
+def test_cli_matches_golden(adsb, tmp_path, path):
+    """The adsbdec-compatible command line: same flags, same stdout bytes, same stats block."""
+    g = _load_golden(path)
+    f = tmp_path / "cap.bin"
+    g["samples"].astype("<u2").tofile(f)
+    cli = str(adsb.CLI_PATH)
+    r = subprocess.run([cli, "-f", str(f)], capture_output=True)
+    assert r.returncode == 0 and r.stdout == g["avr"]
+    assert _parse_stats(r.stderr.decode()) == g["stats"].tolist()
+    r = subprocess.run([cli, "-m", "-f", str(f)], capture_output=True)
+    assert r.stdout == g["avrmlat"]
+    r = subprocess.run([cli, "-b", "-a", "-m", "-f", str(f)], capture_output=True)   # last of -m/-b wins (main.c:79-84)
+    assert r.stdout == g["avrmlat_a"]
+    assert _parse_stats(r.stderr.decode()) == g["stats_a"].tolist()
+    r = subprocess.run([cli, "-a", "-b", "-f", str(f)], capture_output=True)         # full beast packets on stdout
+    assert r.stdout == g["beast_a"]
+
+
+def test_cli_beast_over_tcp_and_missing_file(adsb, tmp_path):
+    import socket
+    import threading
+    g = _load_golden(GOLDEN[0])
+    f = tmp_path / "cap.bin"
+    g["samples"].astype("<u2").tofile(f)
+    srv = socket.socket()
+    srv.bind(("127.0.0.1", 0))
+    srv.listen(1)
+    port = srv.getsockname()[1]
+    got = []
+
+    def sink():
+        c, _ = srv.accept()
+        with c:
+            while True:
+                b = c.recv(65536)
+                if not b:
+                    break
+                got.append(b)
+    th = threading.Thread(target=sink, daemon=True)
+    th.start()
+    r = subprocess.run([str(adsb.CLI_PATH), "-a", "-b", "-s", f"127.0.0.1:{port}", "-f", str(f)], capture_output=True)
+    th.join(10)
+    assert r.returncode == 0 and b"".join(got) == g["beast_a"]
+    # air.c:225-228: a file that cannot be opened -> no frames, stats, exit 0
+    r = subprocess.run([str(adsb.CLI_PATH), "-f", str(tmp_path / "nope.bin")], capture_output=True)
+    assert r.returncode == 0 and r.stdout == b"" and b"Try :" in r.stderr
+
+
+def test_cli_vs_live_reference_binary(adsb, oracle, tmp_path):
+    """When oracle/_ref travelled to this box and runs here: byte-identical stdout on a 1 s capture."""
+    binary = oracle.ref_binary()
+    if binary is None:
+        pytest.skip("oracle/_ref not present / not runnable on this host")
+    cap = synth_capture(1.0, 400, snr_db=18, seed=123, df_mix=DF_MIX_ALL, pad=1 << 21)
+    f = tmp_path / "c1.bin"
+    cap.tofile(f)
+    for flags in (["-m"], ["-a", "-m"], []):
+        for _ in range(30):     # reference EOF race (SURVEY F9): retry until nothing was dropped
+            ref = oracle.run_ref(f, flags=tuple(flags), binary=binary)
+            t, k = ref.stats()
+            if ref.stdout.count(b"\n") == sum(k):
+                break
+        r = subprocess.run([str(adsb.CLI_PATH), *flags, "-f", str(f)], capture_output=True)
+        assert r.stdout == ref.stdout
+        assert _parse_stats(r.stderr.decode()) == [list(t), list(k)]
+
+
+# ---- device-resident input, time-chunking, full-size properties ------------------------------
+
+def test_push_device_matches_host_push(adsb, oracle):
+    import torch
+    cap = capture_basic(seed=140, seconds=0.6, n_frames=300)
+    ref = oracle.decode(cap.samples, accept_df18=True)
+    t = torch.from_numpy(cap.samples.astype(np.int16)).cuda()
+    d = adsb.Decoder(accept_df18=True)
+    d.push_device(t.data_ptr(), t.numel())
+    d.finish()
+    assert frames_key(d.frames) == frames_key(ref.frames) and d.stats() == (ref.tried, ref.ok)
+    # in pieces: aligned big ones take the direct path, small / ragged ones the staging window
+    d2 = adsb.Decoder(accept_df18=True, batch_samples=1 << 20)
+    pos = 0
+    for n in (400_000, 8, 2_000_000, 4, 1_048_576, 12):
+        d2.push_device(t.data_ptr() + 2 * pos, n)
+        pos += n
+    d2.push(cap.samples[pos:pos + 1000])
+    pos += 1000
+    d2.push_device(t.data_ptr() + 2 * pos, t.numel() - pos)
+    d2.finish()
+    assert frames_key(d2.frames) == frames_key(ref.frames) and d2.stats() == (ref.tried, ref.ok)
+
+
+@pytest.mark.parametrize("n_chunks", [2, 5])
+def test_chunk_candidates_merge_equals_whole(adsb, oracle, n_chunks):
+    """time chunks with halo scanned independently (any GPU), merged by offset, resolved once."""
+    import torch
+    from adsbdec_b200.chunking import merge_candidates, plan_chunks, resolve_merged
+    cap = capture_basic(seed=141, seconds=0.5, n_frames=400)
+    ref = oracle.decode(cap.samples, accept_df18=True)
+    t = torch.from_numpy(cap.samples.astype(np.int16)).cuda()
+    d = adsb.Decoder(accept_df18=True)
+    parts = []
+    for ch in plan_chunks(cap.samples.size, n_chunks):
+        seg = t[ch.sample_begin:ch.sample_end].clone()       # a chunk as it would sit on another GPU
+        lo, hi = ch.local_own
+        c, _tries = d.chunk_candidates(seg.data_ptr(), seg.numel(), ch.sample_begin, lo, hi)
+        parts.append((ch, c))
+    out = resolve_merged(merge_candidates(parts), cap.samples.size)
+    assert [(f.ts, f.pw, f.data) for f in out] == [(f.ts, f.pw, f.data) for f in ref.frames]
+
+
+def test_full_size_60s_tiling_property(adsb, oracle):
+    """BASELINE configs[1] size (1.2 G samples, 2.4 GB in HBM).  The capture is one 2 s dense tile
+    repeated 30 times; the tile length is a multiple of 28 samples (FIR rotation period 14, mixer
+    period 4) and ends in silence, so every tile must decode to the oracle's frames of ONE tile,
+    shifted: same bytes and pw, offsets + k*tile, timestamps following the drift rule."""
+    import torch
+    tile_cap = synth_capture(2.0, 6000, snr_db=16, seed=150, df_mix=DF_MIX_ALL, pad=0)
+    s = tile_cap.samples
+    s = s[:s.size - s.size % 28].copy()
+    s[-6000:] = 2048
+    ref = oracle.decode(np.concatenate([s, np.full(1 << 17, 2048, dtype="<u2")]), accept_df18=True)
+    assert len(ref.frames) > 1500
+    reps = 30
+    tile = torch.from_numpy(s.astype(np.int16)).cuda()
+    big = torch.cat([tile.repeat(reps), torch.full((1 << 17,), 2048, dtype=torch.int16, device="cuda")])
+    assert big.numel() >= 1_199_000_000
+    d = adsb.Decoder(accept_df18=True)
+    d.push_device(big.data_ptr(), big.numel())
+    d.finish()
+    fa = d.frames_array
+    nt = len(ref.frames)
+    assert len(fa) == reps * nt
+    tile_out = s.size // 2
+    ref_n = np.array([f.n for f in ref.frames], dtype=np.uint64)
+    ref_b = np.array([np.frombuffer(f.data.ljust(14, b"\0"), dtype=np.uint8) for f in ref.frames])
+    ref_pw = np.array([f.pw for f in ref.frames], dtype=np.uint32)
+    skip = np.array([640 if len(f.data) == 7 else 1200 for f in ref.frames], dtype=np.uint64)
+    drift_tile = int((skip - 1).sum())
+    drift_before = np.concatenate([[0], np.cumsum(skip - 1)[:-1]]).astype(np.uint64)
+    for k in (0, 1, 7, reps - 1):
+        blk = fa[k * nt:(k + 1) * nt]
+        assert np.array_equal(blk["n"], ref_n + np.uint64(k * tile_out))
+        assert np.array_equal(blk["bytes"], ref_b) and np.array_equal(blk["pw"], ref_pw)
+        ts = ref_n + np.uint64(k * tile_out + 1) - drift_before - np.uint64(k * drift_tile)
+        assert np.array_equal(blk["ts"], ts)
+    # and the whole list: periodic bytes, strictly increasing timestamps
+    assert np.array_equal(fa["bytes"].reshape(reps, nt, 14), np.broadcast_to(ref_b, (reps, nt, 14)))
+    assert np.all(np.diff(fa["ts"].astype(np.int64)) > 0)
+    tr, ok = d.stats()
+    assert ok == tuple(reps * x for x in ref.ok) and tr == tuple(reps * x for x in ref.tried)
