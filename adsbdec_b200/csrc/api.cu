@@ -19,10 +19,6 @@
 #include <string.h>
 #include <unistd.h>
 
-#ifdef _OPENMP
-#include <omp.h>
-#endif
-
 #include <algorithm>
 #include <chrono>
 #include <new>
@@ -83,14 +79,6 @@ __global__ void k_reset_counters(Counters *c)
 }
 
 __global__ void k_zero_u64(unsigned long long *p) { *p = 0; }
-
-// Small host->device transfers are done by kernels that read page-locked host memory directly:
-// a cudaMemcpyAsync would queue behind the sample uploads on the copy engine and stall the job.
-__global__ void k_fetch_u64(unsigned long long *dst, const unsigned long long *host_src, size_t n)
-{
-	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-		dst[i] = host_src[i];
-}
 
 // Builds the span table of one fused launch on the device.
 __global__ void k_make_spans(FusedSpan *sp, int *ticket, int n_sp, long long n0, long long n1, long long per,
@@ -170,8 +158,13 @@ struct adsbdec_b200 {
 	unsigned long long cand_cap[kSlots] = {0, 0};
 	unsigned long long *d_tries[kSlots] = {nullptr, nullptr};
 	unsigned long long try_cap[kSlots] = {0, 0};
-	unsigned long long *d_spans[kSlots] = {nullptr, nullptr}, *h_spans[kSlots] = {nullptr, nullptr};
-	size_t span_cap[kSlots] = {0, 0};
+	// on-GPU ordering + greedy resolve (kernels_resolve.cu)
+	ResolveBuffers rb[kSlots] = {};
+	int nb_cap[kSlots] = {0, 0};
+	SlotResolve *d_slot[kSlots] = {nullptr, nullptr}, *h_slot[kSlots] = {nullptr, nullptr};
+	CandRec *d_acc[kSlots] = {nullptr, nullptr};  // accepted candidates of the job, in order
+	ResolveState *d_state = nullptr;
+	int last_slot = 0;
 	FusedSpan *d_fspans[kSlots] = {nullptr, nullptr};
 	int fspan_cap[kSlots] = {0, 0};
 	int *d_ticket[kSlots] = {nullptr, nullptr};
@@ -198,9 +191,7 @@ struct adsbdec_b200 {
 	uint64_t launches = 0, fused_launches = 0, fused_samples = 0;
 
 	std::vector<adsbdec_b200_candidate_t> cand_tmp;
-	std::vector<uint32_t> bucket;
-	std::vector<size_t> bucket_end;
-	// host-side wall time by phase (ms): 0 wait for job, 1 sort/repack, 2 resolve, 3 stats pass issue,
+	// host-side wall time by phase (ms): 0 wait for job, 1 (unused), 2 resolve, 3 stats pass issue,
 	// 4 sink/emit, 5 upload issue + staging memcpy, 6 wait for uploads, 7 jobs completed
 	double host_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
@@ -217,10 +208,16 @@ int alloc_slot_outputs(adsbdec_b200 *h, int s, unsigned long long cand_cap, unsi
 	if (cand_cap != h->cand_cap[s]) {
 		if (h->d_cands[s]) cudaFree(h->d_cands[s]);
 		if (h->h_cands[s]) cudaFreeHost(h->h_cands[s]);
-		h->d_cands[s] = nullptr;
-		h->h_cands[s] = nullptr;
+		if (h->d_acc[s]) cudaFree(h->d_acc[s]);
+		if (h->rb[s].sorted) cudaFree(h->rb[s].sorted);
+		if (h->rb[s].accept) cudaFree(h->rb[s].accept);
+		h->d_cands[s] = h->h_cands[s] = h->d_acc[s] = h->rb[s].sorted = nullptr;
+		h->rb[s].accept = nullptr;
 		CU(cudaMalloc(&h->d_cands[s], cand_cap * sizeof(CandRec)));
-		CU(cudaMallocHost(&h->h_cands[s], cand_cap * sizeof(CandRec)));
+		CU(cudaMalloc(&h->d_acc[s], cand_cap * sizeof(CandRec)));
+		CU(cudaMalloc(&h->rb[s].sorted, cand_cap * sizeof(CandRec)));
+		CU(cudaMalloc(&h->rb[s].accept, cand_cap));
+		CU(cudaMallocHost(&h->h_cands[s], cand_cap * sizeof(CandRec)));  // accepted / sorted candidates land here
 		h->cand_cap[s] = cand_cap;
 	}
 	if (try_cap != h->try_cap[s]) {
@@ -229,6 +226,23 @@ int alloc_slot_outputs(adsbdec_b200 *h, int s, unsigned long long cand_cap, unsi
 		CU(cudaMalloc(&h->d_tries[s], try_cap * sizeof(unsigned long long)));
 		h->try_cap[s] = try_cap;
 	}
+	return 0;
+}
+
+int ensure_buckets(adsbdec_b200 *h, int s, int nb)
+{
+	if (nb + 1 <= h->nb_cap[s])
+		return 0;
+	CU(cudaStreamSynchronize(h->st));
+	ResolveBuffers &rb = h->rb[s];
+	unsigned int **arr[5] = {&rb.cnt, &rb.cur, &rb.off, &rb.bacc, &rb.bacc_x};
+	const int cap = nb + 1 + 4096;
+	for (unsigned int **a : arr) {
+		if (*a) cudaFree(*a);
+		*a = nullptr;
+		CU(cudaMalloc(a, (size_t)cap * sizeof(unsigned int)));
+	}
+	h->nb_cap[s] = cap;
 	return 0;
 }
 
@@ -389,9 +403,25 @@ int enqueue_job(adsbdec_b200 *h, int s, bool force_generic)
 		CU(launch_fill_pw(j.buf, j.u0, j.origin, h->d_cands[s], &h->d_ctr[s]->n_cand, h->cand_cap[s], h->st));
 		h->launches += 1;
 	}
+	// order the candidates on the GPU; for a stream job also apply the greedy skip there, so that
+	// only accepted frames come back
+	RC(ensure_buckets(h, s, resolve_bucket_count(j.n0, j.n1)));
+	const CandRec *result;
+	if (j.resolve) {
+		CU(launch_resolve(h->rb[s], h->d_cands[s], h->d_ctr[s], h->cand_cap[s], j.n0, j.n1, h->d_state, h->d_slot[s],
+		                  h->d_acc[s], h->cand_cap[s], h->st));
+		h->launches += 10;
+		result = h->d_acc[s];
+	} else {
+		CU(launch_sort(h->rb[s], h->d_cands[s], h->d_ctr[s], h->cand_cap[s], j.n0, j.n1, h->st));
+		h->launches += 4;
+		result = h->rb[s].sorted;
+	}
 	CU(cudaEventRecord(h->ev_b[s], h->st));
 	CU(cudaMemcpyAsync(h->h_ctr[s], h->d_ctr[s], sizeof(Counters), cudaMemcpyDeviceToHost, h->st));
-	CU(cudaMemcpyAsync(h->h_cands[s], h->d_cands[s], std::min(kSpecCands, h->cand_cap[s]) * sizeof(CandRec),
+	if (j.resolve)
+		CU(cudaMemcpyAsync(h->h_slot[s], h->d_slot[s], sizeof(SlotResolve), cudaMemcpyDeviceToHost, h->st));
+	CU(cudaMemcpyAsync(h->h_cands[s], result, std::min(kSpecCands, h->cand_cap[s]) * sizeof(CandRec),
 	                   cudaMemcpyDeviceToHost, h->st));
 	CU(cudaEventRecord(h->ev_done[s], h->st));
 	return 0;
@@ -408,41 +438,24 @@ void emit_new_frames(adsbdec_b200 *h)
 	}
 }
 
-// Stats pass for the tries of slot s (and the pending list): counts visited tries below the
-// resolver's scan end, moves the rest to the other pending list.  All on the GPU.
-int stats_pass(adsbdec_b200 *h, int s, size_t first_new_frame, bool with_slot_list)
+// Stats pass for the tries of slot s (and the pending list), entirely on the GPU: a try counts if
+// it lies below the resolver's scan end and outside the accepted frames of the job (which are
+// still in d_acc[s]); tries beyond the scan end go to the other pending list.
+int stats_pass(adsbdec_b200 *h, int s, bool with_slot_list)
 {
 	if (!h->cfg.collect_stats)
 		return 0;
-	const size_t f0 = first_new_frame > 0 ? first_new_frame - 1 : 0;  // the previous span may still cover tries
-	const size_t ns = h->frames.size() - f0;
-	if (ns > h->span_cap[s]) {
-		CU(cudaStreamSynchronize(h->st));
-		if (h->d_spans[s]) cudaFree(h->d_spans[s]);
-		if (h->h_spans[s]) cudaFreeHost(h->h_spans[s]);
-		h->span_cap[s] = ns * 2 + 1024;
-		CU(cudaMalloc(&h->d_spans[s], h->span_cap[s] * 2 * sizeof(unsigned long long)));
-		CU(cudaMallocHost(&h->h_spans[s], h->span_cap[s] * 2 * sizeof(unsigned long long)));
-	}
-	for (size_t i = 0; i < ns; i++) {
-		const adsbdec_b200_frame_t &f = h->frames[f0 + i];
-		h->h_spans[s][2 * i] = f.n;
-		h->h_spans[s][2 * i + 1] = f.n + (f.len == 7 ? kSkipShort : kSkipLong);
-	}
-	if (ns) {
-		k_fetch_u64<<<(unsigned)std::min<size_t>(64, (2 * ns + 255) / 256), 256, 0, h->st>>>(h->d_spans[s],
-		                                                                                    h->h_spans[s], 2 * ns);
-		CU(cudaGetLastError());
-	}
 	const int pin = h->pend_in, pout = 1 - h->pend_in;
 	const unsigned long long scan_end = h->res->scan_end();
 	if (with_slot_list) {
-		CU(launch_count_tries(h->d_tries[s], &h->d_ctr[s]->n_try, h->try_cap[s], h->d_spans[s], (int)ns, scan_end,
-		                      h->d_pend[pout], &h->d_stats->n_pend[pout], kPendCap, h->d_stats, h->st));
+		CU(launch_count_tries_frames(h->d_tries[s], &h->d_ctr[s]->n_try, h->try_cap[s], h->d_acc[s], h->d_slot[s],
+		                             h->cand_cap[s], scan_end, h->d_pend[pout], &h->d_stats->n_pend[pout], kPendCap,
+		                             h->d_stats, h->st));
 		h->launches += 1;
 	}
-	CU(launch_count_tries(h->d_pend[pin], &h->d_stats->n_pend[pin], kPendCap, h->d_spans[s], (int)ns, scan_end,
-	                      h->d_pend[pout], &h->d_stats->n_pend[pout], kPendCap, h->d_stats, h->st));
+	CU(launch_count_tries_frames(h->d_pend[pin], &h->d_stats->n_pend[pin], kPendCap, h->d_acc[s], h->d_slot[s],
+	                             h->cand_cap[s], scan_end, h->d_pend[pout], &h->d_stats->n_pend[pout], kPendCap,
+	                             h->d_stats, h->st));
 	k_zero_u64<<<1, 1, 0, h->st>>>(&h->d_stats->n_pend[pin]);
 	CU(cudaGetLastError());
 	h->launches += 2;
@@ -450,99 +463,7 @@ int stats_pass(adsbdec_b200 *h, int s, size_t first_new_frame, bool with_slot_li
 	return 0;
 }
 
-// Fused-kernel records carry the frame as four 28-bit words; repack into bytes.
-inline void repack_candidate(adsbdec_b200_candidate_t &o, const CandRec &c)
-{
-	memcpy(&o, &c, sizeof(CandRec));
-	if (!(o.len & kCandNibbleWords))
-		return;
-	o.len &= ~kCandNibbleWords;
-	uint32_t w[4];
-	memcpy(w, c.bytes, 16);
-	unsigned __int128 f;
-	int nbits;
-	if (o.len == 14) {
-		f = ((unsigned __int128)w[0] << 84) | ((unsigned __int128)w[1] << 56) | ((unsigned __int128)w[2] << 28) | w[3];
-		nbits = 112;
-	} else {
-		f = ((unsigned __int128)w[0] << 28) | w[1];
-		nbits = 56;
-	}
-	memset(o.bytes, 0, 16);
-	for (uint32_t k = 0; k < o.len; k++)
-		o.bytes[k] = (uint8_t)(f >> (nbits - 8 - 8 * (int)k));
-}
-
-// The kernels append candidates in whatever order CTAs finish.  Bucket them by offset (counting
-// sort over 4096-offset buckets: histogram, prefix, scatter), then order the handful of entries
-// inside each bucket - O(n) instead of a comparison sort of 32-byte records.  Large lists are
-// split over a few host threads (OpenMP): per-thread histograms, one prefix, parallel scatter.
-void sort_candidates(adsbdec_b200 *h, const CandRec *c, size_t nc, int64_t n0, int64_t n1)
-{
-	static_assert(sizeof(CandRec) == sizeof(adsbdec_b200_candidate_t), "record layouts must agree");
-	const int shift = 12;
-	const size_t nb = (size_t)((n1 - n0) >> shift) + 2;
-	int T = 1;
-#ifdef _OPENMP
-	if (nc >= (1u << 15))
-		T = std::max(1, std::min(8, omp_get_max_threads()));
-#endif
-	h->bucket.assign((size_t)T * nb + 1, 0);
-	uint32_t *hist = h->bucket.data();
-	h->cand_tmp.resize(nc);
-	adsbdec_b200_candidate_t *out = h->cand_tmp.data();
-	std::vector<size_t> &bend = h->bucket_end;
-	bend.resize(nb);
-#pragma omp parallel num_threads(T)
-	{
-#ifdef _OPENMP
-		const int t = omp_get_thread_num();
-#else
-		const int t = 0;
-#endif
-		const size_t lo = nc * (size_t)t / T, hi = nc * (size_t)(t + 1) / T;
-		uint32_t *my = hist + (size_t)t * nb;
-		for (size_t i = lo; i < hi; i++)
-			my[(size_t)(((int64_t)c[i].n - n0) >> shift)]++;
-#pragma omp barrier
-#pragma omp single
-		{
-			// exclusive prefix in (bucket, thread) order: thread t's slice of bucket b
-			uint32_t run = 0;
-			for (size_t b = 0; b < nb; b++) {
-				for (int k = 0; k < T; k++) {
-					const uint32_t v = hist[(size_t)k * nb + b];
-					hist[(size_t)k * nb + b] = run;
-					run += v;
-				}
-				bend[b] = run;
-			}
-		}
-		for (size_t i = lo; i < hi; i++) {
-			const size_t b = (size_t)(((int64_t)c[i].n - n0) >> shift);
-			repack_candidate(out[my[b]++], c[i]);
-		}
-#pragma omp barrier
-		// insertion sort inside each bucket (a few entries), buckets split over the threads
-		const size_t blo = nb * (size_t)t / T, bhi = nb * (size_t)(t + 1) / T;
-		size_t s0 = blo ? bend[blo - 1] : 0;
-		for (size_t b = blo; b < bhi; b++) {
-			const size_t e0 = bend[b];
-			for (size_t i = s0 + 1; i < e0; i++) {
-				const adsbdec_b200_candidate_t v = out[i];
-				size_t k = i;
-				while (k > s0 && out[k - 1].n > v.n) {
-					out[k] = out[k - 1];
-					k--;
-				}
-				out[k] = v;
-			}
-			s0 = e0;
-		}
-	}
-}
-
-// Waits for job slot s, handles overflow / out-of-range fall-backs, resolves and emits.
+// Waits for job slot s, handles overflow / out-of-range fall-backs, feeds the resolver and emits.
 int complete_job(adsbdec_b200 *h, int s)
 {
 	Job &j = h->job[s];
@@ -550,6 +471,7 @@ int complete_job(adsbdec_b200 *h, int s)
 		return 0;
 	h->cand_tmp.clear();
 	const bool scanned = j.n1 > j.n0;
+	size_t n_res = 0;
 	if (scanned) {
 		bool force_generic = false;
 		for (int attempt = 0;; attempt++) {
@@ -569,37 +491,48 @@ int complete_job(adsbdec_b200 *h, int s)
 			if (j.used_fused && (c.wide || (c.overflow & 4u))) {
 				// samples beyond 12 bits (or an absurd survivor density): exact generic kernels
 				force_generic = true;
-			} else if (c.overflow & 3u) {
-				CU(cudaStreamSynchronize(h->st));
-				RC(alloc_slot_outputs(h, s, (c.overflow & 1u) ? h->cand_cap[s] * 4 : h->cand_cap[s],
-				                      (c.overflow & 2u) ? h->try_cap[s] * 4 : h->try_cap[s]));
-			} else {
+			} else if (!(c.overflow & 3u)) {
 				break;
 			}
+			// Redo.  Everything issued since this job started ran on a truncated list: drain the GPU,
+			// put the scan position back to where it was before this job, grow the lists and re-issue
+			// this job and the (newer) one in the other slot.
+			CU(cudaStreamSynchronize(h->st));
+			if (j.resolve)
+				CU(launch_set_state(h->d_state, h->h_slot[s]->span0_start, h->h_slot[s]->span0_end, h->st));
+			if (c.overflow & 3u)
+				RC(alloc_slot_outputs(h, s, (c.overflow & 1u) ? h->cand_cap[s] * 4 : h->cand_cap[s],
+				                      (c.overflow & 2u) ? h->try_cap[s] * 4 : h->try_cap[s]));
 			RC(enqueue_job(h, s, force_generic));
+			if (h->job[1 - s].active)
+				RC(enqueue_job(h, 1 - s, false));
 		}
-		const size_t nc = (size_t)h->h_ctr[s]->n_cand;
-		if (nc > kSpecCands) {
-			CU(cudaMemcpyAsync(h->h_cands[s] + kSpecCands, h->d_cands[s] + kSpecCands,
-			                   (nc - kSpecCands) * sizeof(CandRec), cudaMemcpyDeviceToHost, h->st));
+		n_res = j.resolve ? (size_t)h->h_slot[s]->n_accept : (size_t)std::min<unsigned long long>(h->h_ctr[s]->n_cand, h->cand_cap[s]);
+		if (n_res > kSpecCands) {
+			const CandRec *src = j.resolve ? h->d_acc[s] : h->rb[s].sorted;
+			CU(cudaMemcpyAsync(h->h_cands[s] + kSpecCands, src + kSpecCands, (n_res - kSpecCands) * sizeof(CandRec),
+			                   cudaMemcpyDeviceToHost, h->st));
 			CU(cudaStreamSynchronize(h->st));
 		}
-		const double t1 = now_ms();
-		if (nc)
-			sort_candidates(h, h->h_cands[s], nc, j.n0, j.n1);
-		h->host_ms[1] += now_ms() - t1;
 	} else {
 		CU(cudaEventSynchronize(h->ev_done[s]));
 	}
 	j.active = false;
-	if (!j.resolve)
+	static_assert(sizeof(CandRec) == sizeof(adsbdec_b200_candidate_t), "record layouts must agree");
+	const adsbdec_b200_candidate_t *res = reinterpret_cast<const adsbdec_b200_candidate_t *>(h->h_cands[s]);
+	if (!j.resolve) {
+		h->cand_tmp.assign(res, res + n_res);  // chunk mode: sorted candidates for the caller
 		return 0;
-	const size_t f0 = h->frames.size();
+	}
+	// The greedy skip has been applied on the GPU; the resolver adds the timestamps (demod.c:99) and
+	// the deqframe call schedule (air.c:94-99) over the accepted frames only.
 	const double t2 = now_ms();
-	h->res->feed(h->cand_tmp.data(), h->cand_tmp.size(), (uint64_t)std::max<int64_t>(j.n1, 0), (uint64_t)j.total_out,
-	             h->frames);
+	h->res->feed(res, n_res, (uint64_t)std::max<int64_t>(j.n1, 0), (uint64_t)j.total_out, h->frames);
 	const double t3 = now_ms();
-	RC(stats_pass(h, s, f0, scanned));
+	if (scanned) {
+		RC(stats_pass(h, s, true));
+		h->last_slot = s;
+	}
 	const double t4 = now_ms();
 	emit_new_frames(h);
 	h->host_ms[2] += t3 - t2;
@@ -767,6 +700,8 @@ int adsbdec_b200_open(const adsbdec_b200_config_t *cfg, adsbdec_b200_t **out)
 		          cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking) == cudaSuccess &&
 		          cudaEventCreateWithFlags(&h->ev_h2d, cudaEventDisableTiming) == cudaSuccess &&
 		          cudaMalloc(&h->d_stats, sizeof(StreamStats)) == cudaSuccess &&
+		          cudaMalloc(&h->d_state, sizeof(ResolveState)) == cudaSuccess &&
+		          cudaMemset(h->d_state, 0, sizeof(ResolveState)) == cudaSuccess &&
 		          cudaMallocHost(&h->h_stats, sizeof(StreamStats)) == cudaSuccess &&
 		          cudaMemset(h->d_stats, 0, sizeof(StreamStats)) == cudaSuccess;
 		for (int i = 0; ok && i < 2; i++) {
@@ -779,6 +714,9 @@ int adsbdec_b200_open(const adsbdec_b200_config_t *cfg, adsbdec_b200_t **out)
 			     cudaEventCreate(&h->ev_fa[s]) == cudaSuccess && cudaEventCreate(&h->ev_fb[s]) == cudaSuccess &&
 			     cudaEventCreateWithFlags(&h->ev_done[s], cudaEventDisableTiming) == cudaSuccess &&
 			     cudaMalloc(&h->d_ctr[s], sizeof(Counters)) == cudaSuccess &&
+			     cudaMalloc(&h->d_slot[s], sizeof(SlotResolve)) == cudaSuccess &&
+			     cudaMemset(h->d_slot[s], 0, sizeof(SlotResolve)) == cudaSuccess &&
+			     cudaMallocHost(&h->h_slot[s], sizeof(SlotResolve)) == cudaSuccess &&
 			     cudaMallocHost(&h->h_ctr[s], sizeof(Counters)) == cudaSuccess &&
 			     cudaMemset(h->d_ctr[s], 0, sizeof(Counters)) == cudaSuccess;
 			if (ok)
@@ -828,8 +766,16 @@ void adsbdec_b200_close(adsbdec_b200_t *h)
 		if (h->h_cands[s]) cudaFreeHost(h->h_cands[s]);
 		if (h->d_ctr[s]) cudaFree(h->d_ctr[s]);
 		if (h->h_ctr[s]) cudaFreeHost(h->h_ctr[s]);
-		if (h->d_spans[s]) cudaFree(h->d_spans[s]);
-		if (h->h_spans[s]) cudaFreeHost(h->h_spans[s]);
+		if (h->d_acc[s]) cudaFree(h->d_acc[s]);
+		if (h->rb[s].sorted) cudaFree(h->rb[s].sorted);
+		if (h->rb[s].accept) cudaFree(h->rb[s].accept);
+		if (h->rb[s].cnt) cudaFree(h->rb[s].cnt);
+		if (h->rb[s].cur) cudaFree(h->rb[s].cur);
+		if (h->rb[s].off) cudaFree(h->rb[s].off);
+		if (h->rb[s].bacc) cudaFree(h->rb[s].bacc);
+		if (h->rb[s].bacc_x) cudaFree(h->rb[s].bacc_x);
+		if (h->d_slot[s]) cudaFree(h->d_slot[s]);
+		if (h->h_slot[s]) cudaFreeHost(h->h_slot[s]);
 		if (h->d_fspans[s]) cudaFree(h->d_fspans[s]);
 		if (h->d_ticket[s]) cudaFree(h->d_ticket[s]);
 		if (h->ev_a[s]) cudaEventDestroy(h->ev_a[s]);
@@ -839,6 +785,7 @@ void adsbdec_b200_close(adsbdec_b200_t *h)
 		if (h->ev_done[s]) cudaEventDestroy(h->ev_done[s]);
 	}
 	if (h->d_stats) cudaFree(h->d_stats);
+	if (h->d_state) cudaFree(h->d_state);
 	if (h->h_stats) cudaFreeHost(h->h_stats);
 	if (h->d_amp) cudaFree(h->d_amp);
 	if (h->ev_h2d) cudaEventDestroy(h->ev_h2d);
@@ -879,6 +826,9 @@ int adsbdec_b200_reset(adsbdec_b200_t *h, uint64_t start_sample)
 	for (int i = 0; i < 3; i++)
 		h->stat_ok[i] = 0;
 	CU(cudaMemset(h->d_stats, 0, sizeof(StreamStats)));
+	CU(cudaMemset(h->d_state, 0, sizeof(ResolveState)));
+	for (int s = 0; s < kSlots; s++)
+		CU(cudaMemset(h->d_slot[s], 0, sizeof(SlotResolve)));
 	return 0;
 }
 
@@ -1014,9 +964,8 @@ int adsbdec_b200_finish(adsbdec_b200_t *h)
 	if (h->dev[0] && (h->pin_fill > 0 || h->dev_fill > 0))
 		RC(flush_batch(h));
 	RC(complete_all(h));
-	const size_t f0 = h->frames.size();
 	h->res->finish(h->frames);
-	RC(stats_pass(h, 0, f0, false));
+	RC(stats_pass(h, h->last_slot, false));  // pending tries against the final scan end
 	emit_new_frames(h);
 	CU(cudaStreamSynchronize(h->st));
 	h->finished = true;

@@ -1,0 +1,322 @@
+// kernels_resolve.cu - the sequential half of demod.c:84-144, done on the GPU over the sparse
+// candidate list of one scan job, so that only ACCEPTED frames travel back to the host.
+//
+//   1. order:   counting sort of the candidates by offset (4096-offset buckets: histogram, scan,
+//               scatter, insertion sort inside each bucket); frame bits are repacked to bytes here;
+//   2. greedy:  demod.c:128/:134 - after an accepted frame the scan resumes behind it.  A candidate
+//               that starts >= 1200 samples after its predecessor is accepted whatever happened
+//               before (no frame is longer than 1200), so the list falls apart into independent
+//               segments at such gaps; one thread walks each segment;
+//   3. compact: a bucket-level prefix sum gives every accepted candidate its slot; they are written
+//               out in offset order.
+//
+// The scan position that crosses jobs (end of the last accepted frame) lives in device memory and
+// is advanced in stream order, so jobs can be pipelined without the host in the loop.  What stays
+// on the host (resolver.cpp, fed with ACCEPTED frames only) is O(accepted): the iteration-count
+// timestamp (demod.c:99) and the deqframe call schedule (air.c:94-99) that decides where the scan ends.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/adsbdec_b200.h"
+#include "common.h"
+#include "kernels.h"
+
+namespace adsb {
+
+namespace {
+
+constexpr int kBShift = 12;  // bucket = 4096 offsets
+constexpr int kScanThreads = 1024;
+
+__device__ __forceinline__ unsigned long long job_count(const Counters *ctr, unsigned long long cap)
+{
+	const unsigned long long n = ctr->n_cand;
+	return n < cap ? n : cap;
+}
+
+__global__ void k_hist(const CandRec *__restrict__ c, const Counters *ctr, unsigned long long cap, long long n0,
+                       unsigned int *cnt)
+{
+	const unsigned long long m = job_count(ctr, cap);
+	for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < m;
+	     i += (unsigned long long)gridDim.x * blockDim.x)
+		atomicAdd(&cnt[(unsigned long long)((long long)c[i].n - n0) >> kBShift], 1u);
+}
+
+// Exclusive scan of `in` (nb entries) into `out` (nb+1 entries), single block.
+__global__ void k_scan_buckets(const unsigned int *__restrict__ in, unsigned int *__restrict__ out, int nb)
+{
+	__shared__ unsigned int s32[kScanThreads];
+	const int t = threadIdx.x;
+	const int per = (nb + kScanThreads - 1) / kScanThreads;
+	const int lo = min(t * per, nb), hi = min(lo + per, nb);
+	unsigned int a = 0;
+	for (int i = lo; i < hi; i++)
+		a += in[i];
+	s32[t] = a;
+	__syncthreads();
+	for (int d = 1; d < kScanThreads; d <<= 1) {
+		const unsigned int x = t >= d ? s32[t - d] : 0u;
+		__syncthreads();
+		s32[t] += x;
+		__syncthreads();
+	}
+	unsigned int ra = s32[t] - a;  // exclusive prefix of this thread's slice
+	for (int i = lo; i < hi; i++) {
+		out[i] = ra;
+		ra += in[i];
+	}
+	if (t == kScanThreads - 1)
+		out[nb] = s32[t];
+}
+
+__device__ __forceinline__ void repack(CandRec &o, const CandRec &c)
+{
+	o = c;
+	if (!(c.len & kCandNibbleWords))
+		return;
+	// four 28-bit words (MSB first) -> frame bytes
+	o.len = c.len & ~kCandNibbleWords;
+	uint32_t w[4];
+	memcpy(w, c.bytes, 16);
+	unsigned long long hi, lo;  // 112-bit frame as hi:lo (hi holds the top 48 bits) / 56-bit frame in lo
+	int nbits;
+	if (o.len == 14) {
+		// f = w0<<84 | w1<<56 | w2<<28 | w3
+		lo = ((unsigned long long)w[3]) | ((unsigned long long)w[2] << 28) | ((unsigned long long)w[1] << 56);
+		hi = ((unsigned long long)w[1] >> 8) | ((unsigned long long)w[0] << 20);
+		nbits = 112;
+	} else {
+		lo = ((unsigned long long)w[0] << 28) | w[1];
+		hi = 0;
+		nbits = 56;
+	}
+#pragma unroll
+	for (int k = 0; k < 16; k++) {
+		uint8_t v = 0;
+		if (k < (int)o.len) {
+			const int sh = nbits - 8 - 8 * k;  // bit position of this byte in the frame
+			v = sh >= 64 ? (uint8_t)(hi >> (sh - 64))
+			             : (sh > 56 ? (uint8_t)((lo >> sh) | (hi << (64 - sh))) : (uint8_t)(lo >> sh));
+		}
+		o.bytes[k] = v;
+	}
+}
+
+__global__ void k_scatter(const CandRec *__restrict__ c, const Counters *ctr, unsigned long long cap, long long n0,
+                          const unsigned int *__restrict__ off, unsigned int *cur, CandRec *__restrict__ sorted)
+{
+	const unsigned long long m = job_count(ctr, cap);
+	for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < m;
+	     i += (unsigned long long)gridDim.x * blockDim.x) {
+		const unsigned long long b = (unsigned long long)((long long)c[i].n - n0) >> kBShift;
+		const unsigned int p = off[b] + atomicAdd(&cur[b], 1u);
+		CandRec r;
+		repack(r, c[i]);
+		sorted[p] = r;
+	}
+}
+
+// Orders the few entries of each bucket (the scatter order inside a bucket is arbitrary).
+__global__ void k_bucket_sort(CandRec *sorted, const unsigned int *__restrict__ off, int nb)
+{
+	for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
+		const unsigned int lo = off[b], hi = off[b + 1];
+		for (unsigned int i = lo + 1; i < hi; i++) {
+			const CandRec v = sorted[i];
+			unsigned int k = i;
+			while (k > lo && sorted[k - 1].n > v.n) {
+				sorted[k] = sorted[k - 1];
+				k--;
+			}
+			sorted[k] = v;
+		}
+	}
+}
+
+__device__ __forceinline__ unsigned long long skip_of(uint32_t len) { return len == 7 ? kSkipShort : kSkipLong; }
+
+// Copies the scan position into the job's slot: the greedy kernel reads it from there while its
+// last segment writes the new one, and the statistics pass needs the "before" value later.
+__global__ void k_snapshot(const ResolveState *st, SlotResolve *slot)
+{
+	slot->span0_start = st->carry_start;
+	slot->span0_end = st->carry_pos;
+}
+
+// Greedy acceptance.  Thread i walks the segment that starts at candidate i (if one does).
+__global__ void k_greedy(const CandRec *__restrict__ sorted, const unsigned int *__restrict__ off, int nb,
+                         unsigned char *__restrict__ accept, ResolveState *st, const SlotResolve *slot)
+{
+	const unsigned long long m = off[nb];
+	for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < m;
+	     i += (unsigned long long)gridDim.x * blockDim.x) {
+		const unsigned long long ni = sorted[i].n;
+		if (i != 0 && ni - sorted[i - 1].n < (unsigned long long)kLookahead)
+			continue;  // inside somebody else's segment
+		// demod.c:128/:134: idx = lidx.  The first segment of a job inherits the scan position; any
+		// other segment starts >= 1200 behind a candidate of this job, i.e. behind every earlier frame.
+		unsigned long long pos = i == 0 ? slot->span0_end : 0ull, start = i == 0 ? slot->span0_start : 0ull;
+		unsigned long long j = i, prev;
+		for (;;) {
+			const CandRec &c = sorted[j];
+			const bool ok = c.n >= pos;
+			accept[j] = ok ? 1 : 0;
+			if (ok) {
+				start = c.n;
+				pos = c.n + skip_of(c.len);
+			}
+			prev = c.n;
+			j++;
+			if (j >= m || sorted[j].n - prev >= (unsigned long long)kLookahead)
+				break;
+		}
+		if (j >= m) {
+			// the last segment leaves the scan position for the next job (ordered by the stream)
+			st->carry_pos = pos;
+			st->carry_start = start;
+		}
+	}
+}
+
+__global__ void k_bucket_stats(const unsigned char *__restrict__ accept, const unsigned int *__restrict__ off, int nb,
+                               unsigned int *bacc)
+{
+	for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
+		unsigned int a = 0;
+		for (unsigned int i = off[b]; i < off[b + 1]; i++)
+			a += accept[i];
+		bacc[b] = a;
+	}
+}
+
+// Writes the accepted candidates, in offset order.
+__global__ void k_compact(const CandRec *__restrict__ sorted, const unsigned char *__restrict__ accept,
+                          const unsigned int *__restrict__ off, int nb, const unsigned int *__restrict__ bacc_x,
+                          CandRec *__restrict__ out, unsigned long long out_cap, SlotResolve *slot)
+{
+	for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
+		unsigned long long p = bacc_x[b];
+		for (unsigned int i = off[b]; i < off[b + 1]; i++)
+			if (accept[i]) {
+				if (p < out_cap)
+					out[p] = sorted[i];
+				p++;
+			}
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		slot->n_sorted = off[nb];
+		slot->n_accept = bacc_x[nb];
+	}
+}
+
+// Try statistics (valid.c:46, :68 as the sequential scan sees them) against the accepted frames
+// of this job, which are already on the device.
+__global__ void k_count_tries_frames(const unsigned long long *__restrict__ tries,
+                                     const unsigned long long *__restrict__ n_tries_ptr, unsigned long long cap,
+                                     const CandRec *__restrict__ frames, const SlotResolve *slot,
+                                     unsigned long long frames_cap, unsigned long long scan_end,
+                                     unsigned long long *pend_out, unsigned long long *n_pend_out,
+                                     unsigned long long pend_cap, StreamStats *st)
+{
+	unsigned long long n_tries = *n_tries_ptr;
+	if (n_tries > cap)
+		n_tries = cap;
+	const unsigned long long nf = slot->n_accept < frames_cap ? slot->n_accept : frames_cap;
+	const unsigned long long s0 = slot->span0_start, e0 = slot->span0_end;
+	for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_tries;
+	     i += (unsigned long long)gridDim.x * blockDim.x) {
+		const unsigned long long e = tries[i];
+		const unsigned long long n = e & kTryMask;
+		const uint32_t cls = (uint32_t)(e >> kTryClsShift);
+		// last accepted frame with start < n
+		unsigned long long lo = 0, hi = nf;
+		while (lo < hi) {
+			const unsigned long long mid = (lo + hi) >> 1;
+			if (frames[mid].n < n)
+				lo = mid + 1;
+			else
+				hi = mid;
+		}
+		bool inside;
+		if (lo > 0)
+			inside = n < frames[lo - 1].n + skip_of(frames[lo - 1].len);
+		else
+			inside = n > s0 && n < e0;  // the last frame accepted before this job
+		if (inside)
+			continue;  // skipped by `idx = lidx` (demod.c:128, :134), whenever the scan gets there
+		if (n >= scan_end) {
+			// not reached yet by the deqframe schedule: decide in a later pass.  It has been cleared
+			// against this job's frames already, and no later frame can start before it.
+			const unsigned long long k = atomicAdd(n_pend_out, 1ull);
+			if (k < pend_cap)
+				pend_out[k] = e;
+			else
+				st->pend_overflow = 1;
+			continue;
+		}
+		atomicAdd(&st->stat_try[cls], 1u);
+	}
+}
+
+}  // namespace
+
+int resolve_bucket_count(long long n0, long long n1) { return (int)(((n1 - n0) >> kBShift) + 2); }
+
+// Sort only (chunk mode): rb.sorted = candidates in offset order, bytes repacked, count in off[nb].
+cudaError_t launch_sort(const ResolveBuffers &rb, const CandRec *cands, const Counters *ctr, unsigned long long cap,
+                        long long n0, long long n1, cudaStream_t st)
+{
+	const int nb = resolve_bucket_count(n0, n1);
+	cudaError_t e = cudaMemsetAsync(rb.cnt, 0, (size_t)(nb + 1) * sizeof(unsigned int), st);
+	if (e != cudaSuccess) return e;
+	e = cudaMemsetAsync(rb.cur, 0, (size_t)(nb + 1) * sizeof(unsigned int), st);
+	if (e != cudaSuccess) return e;
+	k_hist<<<296, 256, 0, st>>>(cands, ctr, cap, n0, rb.cnt);
+	k_scan_buckets<<<1, kScanThreads, 0, st>>>(rb.cnt, rb.off, nb);
+	k_scatter<<<296, 256, 0, st>>>(cands, ctr, cap, n0, rb.off, rb.cur, rb.sorted);
+	k_bucket_sort<<<(nb + 127) / 128, 128, 0, st>>>(rb.sorted, rb.off, nb);
+	return cudaGetLastError();
+}
+
+// Sort + greedy + compaction: `out` receives the accepted candidates in order, slot->n_accept their number.
+cudaError_t launch_resolve(const ResolveBuffers &rb, const CandRec *cands, const Counters *ctr, unsigned long long cap,
+                           long long n0, long long n1, ResolveState *state, SlotResolve *slot, CandRec *out,
+                           unsigned long long out_cap, cudaStream_t st)
+{
+	const int nb = resolve_bucket_count(n0, n1);
+	cudaError_t e = launch_sort(rb, cands, ctr, cap, n0, n1, st);
+	if (e != cudaSuccess) return e;
+	k_snapshot<<<1, 1, 0, st>>>(state, slot);
+	k_greedy<<<296, 256, 0, st>>>(rb.sorted, rb.off, nb, rb.accept, state, slot);
+	k_bucket_stats<<<(nb + 127) / 128, 128, 0, st>>>(rb.accept, rb.off, nb, rb.bacc);
+	k_scan_buckets<<<1, kScanThreads, 0, st>>>(rb.bacc, rb.bacc_x, nb);
+	k_compact<<<(nb + 127) / 128, 128, 0, st>>>(rb.sorted, rb.accept, rb.off, nb, rb.bacc_x, out, out_cap, slot);
+	return cudaGetLastError();
+}
+
+__global__ void k_set_state(ResolveState *st, unsigned long long carry_start, unsigned long long carry_pos)
+{
+	st->carry_start = carry_start;
+	st->carry_pos = carry_pos;
+}
+
+cudaError_t launch_set_state(ResolveState *state, unsigned long long carry_start, unsigned long long carry_pos,
+                             cudaStream_t st)
+{
+	k_set_state<<<1, 1, 0, st>>>(state, carry_start, carry_pos);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_count_tries_frames(const unsigned long long *tries, const unsigned long long *n_tries_ptr,
+                                      unsigned long long cap, const CandRec *frames, const SlotResolve *slot,
+                                      unsigned long long frames_cap, unsigned long long scan_end,
+                                      unsigned long long *pend_out, unsigned long long *n_pend_out,
+                                      unsigned long long pend_cap, StreamStats *stt, cudaStream_t st)
+{
+	k_count_tries_frames<<<64, 256, 0, st>>>(tries, n_tries_ptr, cap, frames, slot, frames_cap, scan_end, pend_out,
+	                                         n_pend_out, pend_cap, stt);
+	return cudaGetLastError();
+}
+
+}  // namespace adsb
