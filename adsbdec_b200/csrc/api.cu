@@ -621,6 +621,10 @@ int flush_batch(adsbdec_b200 *h)
 	CU(cudaEventRecord(h->ev_h2d, h->st_copy));
 	CU(cudaStreamWaitEvent(h->st, h->ev_h2d, 0));
 	RC(submit_window(h, buf, u0, u1));
+	// The other device buffer is about to be refilled (carry copy now, uploads next), and a job may
+	// have to be re-run on its window (list overflow, out-of-range samples): finish the job that used
+	// it first.  Its host work overlaps the scan that was just submitted.
+	RC(complete_job(h, h->next_slot));
 	RC(carry_to_next(h, buf, u0, u1));
 	// dev[old] may be overwritten once this job and the carry copy out of it are done
 	CU(cudaEventRecord(h->ev_dev_free[old], h->st));
@@ -726,8 +730,11 @@ int adsbdec_b200_open(const adsbdec_b200_config_t *cfg, adsbdec_b200_t **out)
 			rc = fail(ADSB_B200_ECUDA, "stream/event/counter setup: %s", cudaGetErrorString(cudaGetLastError()));
 			break;
 		}
+		// reserved[0] / reserved[1]: initial list capacities (tests use tiny ones to exercise regrowth)
+		const unsigned long long cc = cfg->reserved[0] ? cfg->reserved[0] : 1ull << 18;
+		const unsigned long long tc = cfg->reserved[1] ? cfg->reserved[1] : 1ull << 20;
 		for (int s = 0; s < kSlots && !rc; s++)
-			rc = alloc_slot_outputs(h, s, 1ull << 18, 1ull << 20);
+			rc = alloc_slot_outputs(h, s, cc, tc);
 		if (rc) break;
 		if (cfg->kernel != 1) {
 			int per_sm = fused_prepare(cfg->device);

@@ -83,7 +83,8 @@ typedef struct {
 	uint64_t start_sample;           /* absolute index of the first pushed sample (0 for a file;
 	                                    a time-chunk of a longer capture passes its offset so the
 	                                    FIR rotation / fidx wrap (air.c:34,65) line up)           */
-	uint64_t reserved[4];
+	uint64_t reserved[4];            /* [0], [1]: initial candidate / try list capacities (0 = default;
+	                                    lists regrow on demand), [2], [3]: must be 0                  */
 } adsbdec_b200_config_t;
 
 /* Fills *cfg with defaults (device 0, reference-compatible behaviour). */

@@ -375,3 +375,18 @@ def test_full_size_60s_tiling_property(adsb, oracle):
     assert np.all(np.diff(fa["ts"].astype(np.int64)) > 0)
     tr, ok = d.stats()
     assert ok == tuple(reps * x for x in ref.ok) and tr == tuple(reps * x for x in ref.tried)
+
+
+@pytest.mark.parametrize("kernel", [0, 1], ids=["fused", "generic"])
+def test_list_overflow_regrows_and_redoes_in_flight_jobs(adsb, oracle, kernel):
+    """Tiny initial candidate / try lists on a multi-batch stream: every job overflows, the decoder
+    must rewind the device-side scan position, regrow and re-issue the jobs in flight - and still
+    produce exactly the oracle's output."""
+    cap = synth_capture(0.8, 900, snr_db=20, seed=160, df_mix=DF_MIX_ALL, pad=1 << 16)
+    ref = oracle.decode(cap.samples, accept_df18=True)
+    d = adsb.Decoder(accept_df18=True, kernel=kernel, batch_samples=1 << 21, initial_caps=(16, 64))
+    d.push(cap.samples)
+    d.finish()
+    assert frames_key(d.frames) == frames_key(ref.frames)
+    assert d.stats() == (ref.tried, ref.ok)
+    assert len(ref.frames) > 300
