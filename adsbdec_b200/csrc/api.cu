@@ -178,7 +178,7 @@ struct adsbdec_b200 {
 	int pend_in = 0;
 
 	float *d_amp = nullptr;
-	int fused_ctas = 0;      // grid size of the fused kernel (0 = unavailable)
+	int fused_ctas = 0;      // autonomous workers (warps) of the fused kernel on this device (0 = unavailable)
 
 	Resolver *res = nullptr;
 	std::vector<adsbdec_b200_frame_t> frames;
@@ -309,12 +309,13 @@ int launch_fused_range(adsbdec_b200 *h, int s, const Job &j, int64_t n0, int64_t
 	const int64_t total = n1 - n0;
 	// Span length: a whole number of sub-blocks INCLUDING the look-back tail, so that the last
 	// sub-block of a span is not mostly wasted: per = k*S - (lookback + alignment slack).
-	// Big ranges get 4 spans per CTA (the dynamic scheduler evens out the tail); small ones
-	// exactly one span per CTA or fewer - never "a few more spans than CTAs".
+	// A worker is one warp of the fused kernel.  Big ranges get 4 spans per worker (the dynamic
+	// scheduler evens out the tail); small ones at most one span per worker - never "a few more
+	// spans than workers".
 	const int64_t tail = lookback + 64;
 	const int want = total >= (int64_t)h->fused_ctas * 4 * 16 * S ? h->fused_ctas * 4 : h->fused_ctas;
 	int64_t nbk = ((total + want - 1) / want + tail + S - 1) / S;
-	nbk = std::max<int64_t>(nbk, 2);
+	nbk = std::max<int64_t>(nbk, 16);  // keep the per-span look-back overhead below ~12 %
 	nbk = std::min<int64_t>(nbk, (1ll << 29) / S);
 	const int64_t per = nbk * S - tail;
 	const int n_sp = (int)((total + per - 1) / per);
@@ -737,7 +738,7 @@ int adsbdec_b200_open(const adsbdec_b200_config_t *cfg, adsbdec_b200_t **out)
 			rc = alloc_slot_outputs(h, s, cc, tc);
 		if (rc) break;
 		if (cfg->kernel != 1) {
-			int per_sm = fused_prepare(cfg->device);
+			int per_sm = fused_prepare(cfg->device);  // workers (warps) per SM
 			if (per_sm <= 0) {
 				rc = fail(ADSB_B200_ENODEV, "fused kernel cannot be configured on device %d", cfg->device);
 				break;
@@ -1185,7 +1186,7 @@ int adsbdec_b200_debug_fused(adsbdec_b200_t *h, const uint16_t *samples, size_t 
 	CU(cudaMemset(h->dbg_b, 0, count / 8));
 	h->dbg_n = (long long)count;
 	const int saved_ctas = h->fused_ctas;
-	h->fused_ctas = 1;  // one CTA, so span 0 covers the head of the capture in order
+	h->fused_ctas = 1;  // one worker, so span 0 covers the head of the capture in order
 	const int s = h->next_slot;
 	Job j;
 	j.buf = d_raw;

@@ -7,36 +7,34 @@
 //   demod.c:46-81  DF11 / DF17 / DF18 gate on the first five bits
 //   demod.c:31-44  PPM bit decisions
 //   valid.c:39-82, crc.h:36-42  CRC-24 syndrome == 0
-// evaluated at EVERY offset; the sequential rules (greedy skip, ts, tail) are applied by the
-// host resolver on the sparse output, and pw (demod.c:127) is filled in for the few CRC-valid
-// candidates by a follow-up kernel (kernels_generic.cu: k_fill_pw).
+// evaluated at EVERY offset; the sequential rules (greedy skip, ts, tail) are applied afterwards on
+// the sparse output (kernels_resolve.cu + resolver.cpp), and pw (demod.c:127) is filled in for the
+// few CRC-valid candidates by a follow-up kernel (kernels_generic.cu: k_fill_pw).
 //
-// How (see DESIGN.md for the arithmetic identities and the roofline):
-//   * a CTA streams a contiguous span of the capture through shared memory in sub-blocks of
-//     S = 28*NT envelope samples; raw samples arrive by 1-D TMA bulk copies (cp.async.bulk +
-//     mbarrier) into a small stage ring, one elected thread issuing;
-//   * stage 1 (FIR): each thread owns 28 consecutive outputs.  28 = lcm(4,7): the ring-slot
-//     rotation of the reference's summation order has period 7 outputs, so with spans cut at
-//     phase 0 every FMA's tap and order is a compile-time constant.  I and Q accumulate as the
-//     two halves of packed fma.rn.f32x2 (the even/odd samples of a 32-bit word ARE the I/Q pair);
-//     u16 -> float by the 0x4B000000 magic-number trick (no I2F);
+// Organisation: every WARP is an autonomous worker.  It takes contiguous spans of the capture from a
+// ticket counter and streams them through its own slice of shared memory in sub-blocks of
+// S = 28*32 = 896 envelope samples.  There is no CTA barrier in the steady state - only
+// __syncwarp and one mbarrier per warp for its TMA loads - so the warps of an SM sit in
+// different stages at any time and the FMA-heavy and ALU-heavy stages overlap on the pipes.
+//
+//   * load:    raw samples of a sub-block arrive by a 1-D TMA bulk copy (cp.async.bulk + mbarrier,
+//              3.6 KB), issued by lane 0 as soon as the previous sub-block has been read;
+//   * stage 1 (FIR): each lane owns 28 consecutive outputs.  28 = lcm(4,7): the ring-slot rotation of
+//              the reference's summation order has period 7 outputs, so with spans cut at phase 0
+//              every FMA's tap and order is a compile-time constant.  I and Q accumulate as the two
+//              halves of packed fma.rn.f32x2 (the even/odd samples of a 32-bit word ARE the I/Q
+//              pair); u16 -> float by the 0x4B000000 magic-number trick (no I2F);
 //   * stage 2 (bits): per offset three decisions, all as sign bits collected by funnel shifts,
-//       with f[n] = (int)(a[n]+a[n+10])  (floor via add.rm against 2^23):
-//       P[n] = f[n] > 2*f[n+5]      (pulse pair at n, n+10 against the gap pair at n+5, n+15)
-//       Q[n] = f[n+5] > 2*f[n]      (the mirrored test; the preamble is P[n] & Q[n+30])
-//       B[n] = a[n] > a[n+5]        (PPM bit decision)
-//     transposed inside 8-lane groups (8 runs of 28 = 7 words of 32) into bit arrays;
-//   * stage 3 (gate): word-parallel: preamble = P[n] & Q[n+30]; DF gate = five bits of B at
-//     stride 10; survivors go to a shared-memory list;
-//   * stage 4 (slice+CRC): four lanes per survivor; a lane pulls its 7 nibbles of the frame out of
-//     B (one funnel shift + one multiply each), looks their syndromes up in a 28x16 table and the
-//     four lanes XOR-reduce; syndrome 0 -> the frame bits go to the candidate list.
-//
-// Software pipeline, two CTA barriers per sub-block k:
-//     phase A:  stage 1 (k)   +   stage 3 (k-1)   +   stage 4 (k-2)
-//     phase B:  stage 2 (k)   +   try-list write-out (k-2)
-// Stages 3 and 4 only read the bit arrays, which lag far enough behind to be stable while
-// stage 1 refills the envelope ring.
+//              with f[n] = (int)(a[n]+a[n+10])  (floor via add.rm against 2^23):
+//                P[n] = f[n] > 2*f[n+5]    (pulse pair at n, n+10 against the gap pair at n+5, n+15)
+//                Q[n] = f[n+5] > 2*f[n]    (the mirrored test; the preamble is P[n] & Q[n+30])
+//                B[n] = a[n] > a[n+5]      (PPM bit decision)
+//              transposed inside 8-lane groups (8 runs of 28 = 7 words of 32) into bit arrays;
+//   * stage 3 (gate): word-parallel: preamble = P[n] & Q[n+30]; DF gate = five bits of B at stride
+//              10; survivors go to a small list;
+//   * stage 4 (slice+CRC): four lanes per survivor; a lane pulls its 7 nibbles of the frame out of B
+//              (one funnel shift + one multiply each), looks their syndromes up in a 28x16 table and
+//              the four lanes XOR-reduce; syndrome 0 -> the frame bits go to the candidate list.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -47,46 +45,49 @@ namespace adsb {
 
 namespace {
 
-constexpr int R = 28;               // outputs per thread per sub-block
-#ifndef ADSB_NT
-#define ADSB_NT 256
-#endif
-#ifndef ADSB_STAGES
-#define ADSB_STAGES 1
+#ifndef ADSB_WPC
+#define ADSB_WPC 4   // warps per CTA
 #endif
 #ifndef ADSB_MINB
-#define ADSB_MINB 3
+#define ADSB_MINB 5  // CTAs per SM
 #endif
-constexpr int NT = ADSB_NT;         // threads per CTA
-constexpr int S = R * NT;           // envelope samples per sub-block (7168)
-constexpr int HIST = 8;             // words of FIR history in front of a raw stage (6 needed)
+
+constexpr int R = 28;               // outputs per lane per sub-block
+constexpr int WPC = ADSB_WPC;
+constexpr int NT = 32 * WPC;
+constexpr int S = R * 32;           // envelope samples per sub-block of one warp (896)
+constexpr int HIST = 8;             // words of FIR history in front of a sub-block (6 needed)
 constexpr int STAGE_WORDS = S + HIST;
 constexpr int LAG2 = 8;             // stage 2 works 8 runs behind the FIR front
-constexpr int LAG3 = 1472;          // stage 3 works this many offsets behind the front of ITS sub-block
-constexpr int RUNS = NT + 16;       // envelope ring, in runs of 28 floats
-constexpr int WR = 512;             // bit-array ring, in 32-bit words
-constexpr int WPB = S / 32;         // bit words per sub-block (224)
-constexpr int CAND_CAP = 768;       // survivors of the DF gate per sub-block
+constexpr int LAG3 = 1472;          // stages 3/4 work this many offsets behind the FIR front
+constexpr int RUNS = 32 + LAG2;     // envelope ring, in runs of 28 floats
+constexpr int WR = 128;             // bit-array ring, in 32-bit words
+constexpr int WPB = S / 32;         // bit words per sub-block (28)
+constexpr int CAND_CAP = 96;        // survivors of the DF gate per sub-block
+constexpr int TRY_CAP = 96;         // tries buffered per warp before they are flushed
 
 static_assert(LAG3 % 32 == 0 && LAG3 >= kLookahead + LAG2 * R + 32 + 8, "stage-3 lag");
-static_assert(RUNS >= NT + LAG2 + 2, "envelope ring too small");
-// stage 4 of sub-block k-2 runs while the newest bits are those of sub-block k-1
-static_assert(WR >= 2 * WPB + LAG3 / 32 + 8, "bit ring too small");
-static_assert(NT % 32 == 0 && WPB * 8 == NT * 7, "geometry");
+static_assert(WR >= WPB + LAG3 / 32 + 8, "bit ring too small");
+static_assert((WR & (WR - 1)) == 0, "bit ring must be a power of two");
 
-template <int NSTAGE>
-struct Smem {
-	uint32_t raw[NSTAGE][STAGE_WORDS];  // 28704 B per stage
-	float amp[RUNS * R];                // 30464 B
+struct WarpSmem {
+	uint32_t raw[STAGE_WORDS];          // 3616 B
+	float amp[RUNS * R];                // 4480 B
 	uint32_t pbits[WR];                 // P[n]: first pulse pair beats its gap
 	uint32_t qbits[WR];                 // Q[n]: pulse at n+5.. beats the gap at n..
 	uint32_t bbits[WR + 4];             // B[n]: PPM decision; bbits[WR] mirrors bbits[0]
-	uint32_t cand[2][CAND_CAP];         // survivor lists, by sub-block parity
+	uint32_t cand[CAND_CAP];            // survivors of the current sub-block
+	unsigned long long trybuf[TRY_CAP]; // tries waiting for a flush
+	unsigned long long full;            // mbarrier of the raw stage
+	int ncand;
+	int ntry;
+};
+static_assert(sizeof(WarpSmem) % 16 == 0, "per-warp shared memory must keep 16-byte alignment");
+
+struct Smem {
 	uint32_t lut[28 * 16];              // lut[g][v]: syndrome of nibble g of a 112-bit frame holding v
 	uint32_t syn[112];                  // x^(111-b) mod G
-	unsigned long long full[NSTAGE];    // mbarriers
-	int ncand[2];
-	int span;
+	WarpSmem w[WPC];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -141,28 +142,28 @@ constexpr float kMagicMid = 8388608.0f + 2048.0f;
 
 }  // namespace
 
-template <int NSTAGE, int MINB, bool DEBUG>
-__global__ void __launch_bounds__(NT, MINB) k_fused(const FusedParams p)
+template <bool DEBUG>
+__global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	Smem<NSTAGE> &sm = *reinterpret_cast<Smem<NSTAGE> *>(smem_raw);
+	Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
 	const int tid = threadIdx.x;
 	const int lane = tid & 31;
-	const int warp = tid >> 5;
+	WarpSmem &ws = sm.w[tid >> 5];
 
-	// ---- one-time setup --------------------------------------------------
-	if (tid < 112) {
+	// ---- one-time setup (the only CTA barriers) ---------------------------
+	for (int b = tid; b < 112; b += NT) {
 		// Frame bit b contributes x^(111-b) mod G to the syndrome (crc.h's table is the byte-wise
 		// form of the same polynomial division; the last 24 bits are XORed in unreduced, crc.h:40-42)
 		uint32_t r = 1;
-		for (int i = 0; i < 111 - tid; i++)
+		for (int i = 0; i < 111 - b; i++)
 			r = (r & 0x800000u) ? ((r << 1) ^ kCrcPoly) & 0xFFFFFFu : (r << 1);
-		sm.syn[tid] = r;
+		sm.syn[b] = r;
 	}
-	if (tid == 0) {
-		for (int s = 0; s < NSTAGE; s++)
-			mbar_init(&sm.full[s], 1);
-		sm.ncand[0] = sm.ncand[1] = 0;
+	if (lane == 0) {
+		mbar_init(&ws.full, 1);
+		ws.ncand = 0;
+		ws.ntry = 0;
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
@@ -173,7 +174,8 @@ __global__ void __launch_bounds__(NT, MINB) k_fused(const FusedParams p)
 		sm.lut[e] = ((v & 8) ? sm.syn[4 * g] : 0u) ^ ((v & 4) ? sm.syn[4 * g + 1] : 0u) ^
 		            ((v & 2) ? sm.syn[4 * g + 2] : 0u) ^ ((v & 1) ? sm.syn[4 * g + 3] : 0u);
 	}
-	uint32_t phase_bits = 0;  // mbarrier phase parity, one bit per stage
+	__syncthreads();
+	uint32_t phase = 0;  // mbarrier phase parity
 
 	// air.c:36-45 taps paired for a 32-bit word of age g (0 = newest): the even sample (I, low
 	// half) has age 2g+1, the odd sample (Q, high half) age 2g; tap = h[13-age] = h[age].
@@ -185,18 +187,39 @@ __global__ void __launch_bounds__(NT, MINB) k_fused(const FusedParams p)
 		tp[g] = make_float2(h[ai < 7 ? ai : 13 - ai], h[aq < 7 ? aq : 13 - aq]);
 	}
 
+	// Appends the buffered tries to the global list (one atomic per flush).
+	auto flush_tries = [&]() {
+		const int nt = ws.ntry;
+		if (nt > 0) {
+			unsigned long long base = 0;
+			if (lane == 0)
+				base = atomicAdd(&p.ctr->n_try, (unsigned long long)nt);
+			base = __shfl_sync(0xFFFFFFFFu, base, 0);
+			for (int i = lane; i < nt; i += 32) {
+				if (base + i < p.try_cap)
+					p.tries[base + i] = ws.trybuf[i];
+				else
+					atomicOr(&p.ctr->overflow, 2u);
+			}
+		}
+		__syncwarp();
+		if (lane == 0)
+			ws.ntry = 0;
+		__syncwarp();
+	};
+
 	for (;;) {
-		// ---- fetch a span (dynamic scheduler) ----------------------------
-		if (tid == 0)
-			sm.span = atomicAdd(p.span_ticket, 1);
-		__syncthreads();
-		const int span_idx = sm.span;
+		// ---- fetch a span (dynamic scheduler, one ticket per warp) --------
+		int span_idx = 0;
+		if (lane == 0)
+			span_idx = atomicAdd(p.span_ticket, 1);
+		span_idx = __shfl_sync(0xFFFFFFFFu, span_idx, 0);
 		if (span_idx >= p.n_spans)
 			break;
 		const FusedSpan sp = p.spans[span_idx];
 		const long long jb = sp.j_begin;
 		const int nb = sp.n_blocks;
-		// address of the first word of stage 0 (word jb - HIST); only valid words are touched
+		// address of the first word of sub-block 0 (word jb - HIST); only valid words are touched
 		const char *raw_s0 = reinterpret_cast<const char *>(sp.raw_w0) + 4 * (jb - HIST);
 		const uint32_t own_lo = (uint32_t)(sp.own_begin - jb), own_hi = (uint32_t)(sp.own_end - jb);
 		// valid words of the window, relative to word jb - HIST (clamped to int range)
@@ -204,50 +227,41 @@ __global__ void __launch_bounds__(NT, MINB) k_fused(const FusedParams p)
 		const int vlo = (int)(lo64 < 0 ? 0 : lo64);
 		const int vhi = (int)(hi64 > 0x7FFFFFF0ll ? 0x7FFFFFF0ll : (hi64 < 0 ? 0 : hi64));
 
-		auto issue = [&](int kb, int s) {
-			// elected thread: one bulk copy for the part of sub-block kb that the window holds
+		auto issue = [&](int kb) {
+			// lane 0: one bulk copy for the part of sub-block kb that the window holds
 			const int start = kb * S;
 			const int a = max(start, vlo), b = min(start + STAGE_WORDS, vhi);
 			if (b > a) {
 				const uint32_t bytes = (uint32_t)(b - a) * 4u;
-				mbar_expect_tx(&sm.full[s], bytes);
-				tma_load_1d(&sm.raw[s][a - start], raw_s0 + 4ll * a, bytes, &sm.full[s]);
+				mbar_expect_tx(&ws.full, bytes);
+				tma_load_1d(&ws.raw[a - start], raw_s0 + 4ll * a, bytes, &ws.full);
 			} else {
-				mbar_arrive(&sm.full[s]);
+				mbar_arrive(&ws.full);
 			}
 		};
-		if (tid == 0) {
-			issue(0, 0);
-			if (NSTAGE > 1 && nb > 1)
-				issue(1, 1);
-		}
+		if (lane == 0)
+			issue(0);
 
-		int q_fir = tid;  // ring run of this thread's FIR output, (k*NT + tid) % RUNS
+		int q_fir = lane;  // ring run of this lane's FIR output, (k*32 + lane) % RUNS
 
-		for (int k = 0; k < nb + 2; k++) {
-			// =====================================================================
-			// phase A
-			// =====================================================================
-			// ----------------- stage 1 (k): envelope ------------------------------
-			if (k < nb) {
-				const int s = NSTAGE > 1 ? (k & 1) : 0;
+		for (int k = 0; k < nb; k++) {
+			// ================= stage 1: envelope ============================
+			{
 				const int start = k * S;
 				// words the window does not hold read as mid-scale: before the stream start the
 				// reference's ring is zero (air.c:33), past the end they are never used
 				const int va = max(start, vlo) - start, vb = min(start + STAGE_WORDS, vhi) - start;
-				const bool partial = va > 0 || vb < STAGE_WORDS;
-				if (partial) {
-					for (int i = tid; i < STAGE_WORDS; i += NT)
+				if (va > 0 || vb < STAGE_WORDS) {
+					for (int i = lane; i < STAGE_WORDS; i += 32)
 						if (i < va || i >= vb)
-							sm.raw[s][i] = 0x08000800u;
+							ws.raw[i] = 0x08000800u;
 				}
-				mbar_wait(&sm.full[s], (phase_bits >> s) & 1u);
-				phase_bits ^= 1u << s;
-				if (partial)
-					__syncthreads();
+				mbar_wait(&ws.full, phase);
+				phase ^= 1u;
+				__syncwarp();
 
 				uint32_t w[36];
-				const uint4 *src = reinterpret_cast<const uint4 *>(&sm.raw[s][R * tid]);
+				const uint4 *src = reinterpret_cast<const uint4 *>(&ws.raw[R * lane]);
 #pragma unroll
 				for (int i = 0; i < 9; i++) {
 					const uint4 t = src[i];
@@ -256,6 +270,10 @@ __global__ void __launch_bounds__(NT, MINB) k_fused(const FusedParams p)
 					w[4 * i + 2] = t.z;
 					w[4 * i + 3] = t.w;
 				}
+				__syncwarp();  // the raw stage has been read: the next sub-block may land in it
+				if (lane == 0 && k + 1 < nb)
+					issue(k + 1);
+
 				// 12-bit domain check (the float tricks below are exact for samples < 4096)
 				uint32_t any = 0;
 #pragma unroll
@@ -265,7 +283,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused(const FusedParams p)
 					p.ctr->wide = 1;
 
 				// u16 pair -> (x-2048) * sign as float2.  Word parity == parity of its index here
-				// (jb, S, R*tid are even): odd words are samples t%4 in {2,3}, negated (air.c:79-82)
+				// (jb, S, R*lane are even): odd words are samples t%4 in {2,3}, negated (air.c:79-82)
 				float2 v[36];
 #pragma unroll
 				for (int L = 2; L < 36; L++) {
@@ -277,7 +295,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused(const FusedParams p)
 					else
 						v[L] = __fadd2_rn(make_float2(lo, hi), make_float2(-kMagicMid, -kMagicMid));
 				}
-				float4 *dst = reinterpret_cast<float4 *>(&sm.amp[q_fir * R]);
+				float4 *dst = reinterpret_cast<float4 *>(&ws.amp[q_fir * R]);
 				float o[4];
 #pragma unroll
 				for (int r_ = 0; r_ < R; r_++) {
@@ -295,134 +313,18 @@ __global__ void __launch_bounds__(NT, MINB) k_fused(const FusedParams p)
 					if ((r_ & 3) == 3) {
 						dst[r_ >> 2] = make_float4(o[0], o[1], o[2], o[3]);
 						if (DEBUG && p.dbg_amp && span_idx == 0) {
-							const long long at = (long long)k * S + R * tid + (r_ - 3);
+							const long long at = (long long)k * S + R * lane + (r_ - 3);
 							if (at + 4 <= p.dbg_n)
 								*reinterpret_cast<float4 *>(&p.dbg_amp[at]) = make_float4(o[0], o[1], o[2], o[3]);
 						}
 					}
 				}
 			}
+			__syncwarp();  // envelope of sub-block k visible to the warp
 
-			// ----------------- stage 3 (k-1): preamble AND + DF gate ---------------
-			if (k >= 1 && k <= nb && tid < WPB) {
-				const int k3 = k - 1;
-				const int wd = k3 * WPB + tid - LAG3 / 32;
-				if (wd >= 0) {
-					const uint32_t p0 = sm.pbits[wd & (WR - 1)];
-					const uint32_t q0 = sm.qbits[wd & (WR - 1)], q1 = sm.qbits[(wd + 1) & (WR - 1)];
-					// demod.c:107: p1 > 2*s1 at n, p2 > 2*s2 at n+30
-					uint32_t pre = p0 & __funnelshift_l(q1, q0, 30);
-					// ownership: only offsets in [own_lo, own_hi) (relative to j_begin) are emitted here
-					const uint32_t o0 = (uint32_t)wd * 32u;
-					if (o0 < own_lo || o0 + 32u > own_hi) {
-						const uint32_t lo = own_lo > o0 ? own_lo - o0 : 0u;            // first owned bit index
-						const uint32_t hi = own_hi > o0 ? min(own_hi - o0, 32u) : 0u;  // one past the last
-						const uint32_t m_lo = lo >= 32u ? 0u : 0xFFFFFFFFu >> lo;
-						const uint32_t m_hi = hi >= 32u ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> hi);
-						pre &= m_lo & m_hi;
-					}
-					if (pre) {
-						const uint32_t b2 = sm.bbits[(wd + 2) & (WR - 1)], b3 = sm.bbits[(wd + 3) & (WR - 1)],
-						               b4 = sm.bbits[(wd + 4) & (WR - 1)];
-						// first five data bits sit at n+80, +90, +100, +110, +120 (demod.c:110, :46-81)
-						const uint32_t x7 = __funnelshift_l(b3, b2, 16);  // 80  = 64 + 16
-						const uint32_t x6 = __funnelshift_l(b3, b2, 26);  // 90  = 64 + 26
-						const uint32_t x5 = __funnelshift_l(b4, b3, 4);   // 100 = 96 + 4
-						const uint32_t x4 = __funnelshift_l(b4, b3, 14);  // 110 = 96 + 14
-						const uint32_t x3 = __funnelshift_l(b4, b3, 24);  // 120 = 96 + 24
-						const uint32_t m17 = pre & x7 & ~x6 & ~x5 & ~x4 & x3;                         // 10001
-						const uint32_t m18 = p.accept_df18 ? (pre & x7 & ~x6 & ~x5 & x4 & ~x3) : 0u;  // 10010
-						const uint32_t m11 = pre & ~x7 & x6 & ~x5 & x4 & x3;                          // 01011
-						uint32_t any = m17 | m18 | m11;
-						if (any) {
-							int slot = atomicAdd(&sm.ncand[k3 & 1], __popc(any));
-							uint32_t *list = sm.cand[k3 & 1];
-							do {
-								const int i = __clz(any);
-								const uint32_t bit = 0x80000000u >> i;
-								any &= ~bit;
-								const uint32_t cls = (m17 & bit) ? kClsDF17 : (m11 & bit) ? kClsDF11 : kClsDF18;
-								if (slot < CAND_CAP)
-									list[slot] = (o0 + (uint32_t)i) | (cls << 30);
-								slot++;
-							} while (any);
-						}
-					}
-				}
-			}
-
-			// ----------------- stage 4 (k-2): slice + CRC, four lanes per survivor --
-			if (k >= 2) {
-				const int par = k & 1;
-				const int ncand = min(sm.ncand[par], CAND_CAP);
-				const uint32_t *list = sm.cand[par];
-				const int sub = lane & 3;  // quarter of the frame this lane slices: nibbles 7*sub .. 7*sub+6
-				// the slicing starts with the last warp, which has no stage-3 words (WPB = 7/8 NT)
-				constexpr int NW = NT / 32;
-				for (int c0 = (NW - 1 - warp) * 8; c0 < ncand; c0 += NW * 8) {
-					const int ci = c0 + (lane >> 2);
-					const bool have = ci < ncand;
-					const uint32_t ent = have ? list[ci] : 0u;
-					const uint32_t n_rel = ent & 0x3FFFFFFFu;
-					const bool is_long = (ent >> 30) != kClsDF11;
-					// short frames are the last 56 bits of the syndrome table and only use sub 0, 1
-					const bool active = have && (is_long || sub < 2);
-					// frame bit b sits at n + 80 + 10 b; nibble g starts at bit 4g
-					const uint32_t pb0 = n_rel + 80u + 280u * (uint32_t)sub;
-					const uint32_t lut0 = (uint32_t)(7 * sub + (is_long ? 0 : 14)) * 64u;  // byte offset of row g
-					uint32_t acc = 0, bits28 = 0;
-					if (active) {
-#pragma unroll
-						for (int s_ = 0; s_ < 7; s_++) {
-							const uint32_t pb = pb0 + 40u * s_;
-							const uint32_t wa = (pb >> 3) & ((WR - 1) << 2);  // byte offset of the word in the ring
-							const uint32_t w0 = *reinterpret_cast<const uint32_t *>(
-							    reinterpret_cast<const char *>(sm.bbits) + wa);
-							const uint32_t w1 = *reinterpret_cast<const uint32_t *>(
-							    reinterpret_cast<const char *>(sm.bbits) + wa + 4);  // bbits[WR] mirrors bbits[0]
-							const uint32_t x = __funnelshift_l(w1, w0, pb & 31u);  // bits 31, 21, 11, 1
-							const uint32_t nib = ((x & 0x80200802u) * 0x08040201u) >> 28;
-							acc ^= *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(sm.lut) + lut0 +
-							                                            64u * s_ + 4u * nib);
-							bits28 = bits28 * 16u + nib;
-						}
-					}
-					// valid.c:48-52 / :70-74: CRC over all but the last 3 bytes, XOR the last 3, == 0
-					acc ^= __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
-					acc ^= __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
-					const bool ok = have && acc == 0;
-					if (__any_sync(0xFFFFFFFFu, ok)) {
-						unsigned long long slot = 0;
-						if (ok && sub == 0)
-							slot = atomicAdd(&p.ctr->n_cand, 1ull);
-						slot = __shfl_sync(0xFFFFFFFFu, slot, lane & ~3);
-						if (ok) {
-							if (slot < p.cand_cap) {
-								uint32_t *out = reinterpret_cast<uint32_t *>(&p.cands[slot]);
-								if (sub == 0) {
-									const unsigned long long n = (unsigned long long)(jb + (long long)n_rel);
-									// pw is filled in by k_fill_pw (demod.c:127)
-									*reinterpret_cast<uint4 *>(out) = make_uint4(
-									    (uint32_t)n, (uint32_t)(n >> 32), 0u, (is_long ? 14u : 7u) | kCandNibbleWords);
-								}
-								out[4 + sub] = bits28;
-							} else if (sub == 0) {
-								atomicOr(&p.ctr->overflow, 1u);
-							}
-						}
-					}
-				}
-			}
-			__syncthreads();  // (A) envelope of sub-block k visible; raw stage consumed; lists settled
-			if (tid == 0 && k + NSTAGE < nb)
-				issue(k + NSTAGE, NSTAGE > 1 ? (k & 1) : 0);
-
-			// =====================================================================
-			// phase B
-			// =====================================================================
-			// ----------------- stage 2 (k): decision bits ---------------------------
-			if (k < nb) {
-				const int g2 = k * NT + tid - LAG2;  // run handled here (uniform sign per 8-lane group)
+			// ================= stage 2: decision bits ========================
+			{
+				const int g2 = k * 32 + lane - LAG2;  // run handled here (uniform sign per 8-lane group)
 				uint32_t P = 0, Q = 0, B = 0;
 				if (g2 >= 0) {
 					int q2 = q_fir - LAG2;
@@ -430,8 +332,8 @@ __global__ void __launch_bounds__(NT, MINB) k_fused(const FusedParams p)
 					int q2n = q2 + 1;
 					if (q2n == RUNS) q2n = 0;
 					float a[44];
-					const float4 *s0 = reinterpret_cast<const float4 *>(&sm.amp[q2 * R]);
-					const float4 *s1 = reinterpret_cast<const float4 *>(&sm.amp[q2n * R]);
+					const float4 *s0 = reinterpret_cast<const float4 *>(&ws.amp[q2 * R]);
+					const float4 *s1 = reinterpret_cast<const float4 *>(&ws.amp[q2n * R]);
 #pragma unroll
 					for (int i = 0; i < 7; i++) {
 						const float4 t = s0[i];
@@ -477,11 +379,11 @@ __global__ void __launch_bounds__(NT, MINB) k_fused(const FusedParams p)
 					const uint32_t qw_ = (Q << (4 + 4 * j)) | (Qn >> (24 - 4 * j));
 					const uint32_t bw_ = (B << (4 + 4 * j)) | (Bn >> (24 - 4 * j));
 					const int wi = (((g2 - j) >> 3) * 7 + j) & (WR - 1);
-					sm.pbits[wi] = pw_;
-					sm.qbits[wi] = qw_;
-					sm.bbits[wi] = bw_;
+					ws.pbits[wi] = pw_;
+					ws.qbits[wi] = qw_;
+					ws.bbits[wi] = bw_;
 					if (wi == 0)
-						sm.bbits[WR] = bw_;  // mirror: stage 4 reads word pairs without wrapping
+						ws.bbits[WR] = bw_;  // mirror: stage 4 reads word pairs without wrapping
 					if (DEBUG && p.dbg_p && span_idx == 0) {
 						const long long at = (long long)((g2 - j) >> 3) * 7 + j;
 						if (at < p.dbg_n / 32) {
@@ -492,80 +394,173 @@ __global__ void __launch_bounds__(NT, MINB) k_fused(const FusedParams p)
 					}
 				}
 			}
-			// ----------------- try list of sub-block k-2 (valid.c:46, :68) ----------
-			if (k >= 2 && warp == 0) {
-				const int par = k & 1;
-				const int n_all = sm.ncand[par];
+			__syncwarp();  // bit arrays of sub-block k visible to the warp
+
+			// ================= stage 3: preamble AND + DF gate ===============
+			if (lane < WPB) {
+				const int wd = k * WPB + lane - LAG3 / 32;
+				if (wd >= 0) {
+					const uint32_t p0 = ws.pbits[wd & (WR - 1)];
+					const uint32_t q0 = ws.qbits[wd & (WR - 1)], q1 = ws.qbits[(wd + 1) & (WR - 1)];
+					// demod.c:107: p1 > 2*s1 at n, p2 > 2*s2 at n+30
+					uint32_t pre = p0 & __funnelshift_l(q1, q0, 30);
+					// ownership: only offsets in [own_lo, own_hi) (relative to j_begin) are emitted here
+					const uint32_t o0 = (uint32_t)wd * 32u;
+					if (o0 < own_lo || o0 + 32u > own_hi) {
+						const uint32_t lo = own_lo > o0 ? own_lo - o0 : 0u;            // first owned bit index
+						const uint32_t hi = own_hi > o0 ? min(own_hi - o0, 32u) : 0u;  // one past the last
+						const uint32_t m_lo = lo >= 32u ? 0u : 0xFFFFFFFFu >> lo;
+						const uint32_t m_hi = hi >= 32u ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> hi);
+						pre &= m_lo & m_hi;
+					}
+					if (pre) {
+						const uint32_t b2 = ws.bbits[(wd + 2) & (WR - 1)], b3 = ws.bbits[(wd + 3) & (WR - 1)],
+						               b4 = ws.bbits[(wd + 4) & (WR - 1)];
+						// first five data bits sit at n+80, +90, +100, +110, +120 (demod.c:110, :46-81)
+						const uint32_t x7 = __funnelshift_l(b3, b2, 16);  // 80  = 64 + 16
+						const uint32_t x6 = __funnelshift_l(b3, b2, 26);  // 90  = 64 + 26
+						const uint32_t x5 = __funnelshift_l(b4, b3, 4);   // 100 = 96 + 4
+						const uint32_t x4 = __funnelshift_l(b4, b3, 14);  // 110 = 96 + 14
+						const uint32_t x3 = __funnelshift_l(b4, b3, 24);  // 120 = 96 + 24
+						const uint32_t m17 = pre & x7 & ~x6 & ~x5 & ~x4 & x3;                         // 10001
+						const uint32_t m18 = p.accept_df18 ? (pre & x7 & ~x6 & ~x5 & x4 & ~x3) : 0u;  // 10010
+						const uint32_t m11 = pre & ~x7 & x6 & ~x5 & x4 & x3;                          // 01011
+						uint32_t any = m17 | m18 | m11;
+						if (any) {
+							int slot = atomicAdd(&ws.ncand, __popc(any));
+							do {
+								const int i = __clz(any);
+								const uint32_t bit = 0x80000000u >> i;
+								any &= ~bit;
+								const uint32_t cls = (m17 & bit) ? kClsDF17 : (m11 & bit) ? kClsDF11 : kClsDF18;
+								if (slot < CAND_CAP)
+									ws.cand[slot] = (o0 + (uint32_t)i) | (cls << 30);
+								slot++;
+							} while (any);
+						}
+					}
+				}
+			}
+			__syncwarp();  // survivor list complete
+
+			// ================= stage 4: slice + CRC, four lanes per survivor ==
+			const int n_all = ws.ncand;
+			if (n_all > 0) {
 				const int ncand = min(n_all, CAND_CAP);
 				if (n_all > CAND_CAP && lane == 0)
 					atomicOr(&p.ctr->overflow, 4u);
-				if (p.want_tries && ncand > 0) {
-					unsigned long long base = 0;
-					if (lane == 0)
-						base = atomicAdd(&p.ctr->n_try, (unsigned long long)ncand);
-					base = __shfl_sync(0xFFFFFFFFu, base, 0);
-					for (int i = lane; i < ncand; i += 32) {
-						const uint32_t ent = sm.cand[par][i];
-						const unsigned long long n = (unsigned long long)(jb + (long long)(ent & 0x3FFFFFFFu));
-						if (base + i < p.try_cap)
-							p.tries[base + i] = ((unsigned long long)(ent >> 30) << kTryClsShift) | n;
-						else
-							atomicOr(&p.ctr->overflow, 2u);
+				const int sub = lane & 3;  // quarter of the frame this lane slices: nibbles 7*sub .. 7*sub+6
+				for (int c0 = 0; c0 < ncand; c0 += 8) {
+					const int ci = c0 + (lane >> 2);
+					const bool have = ci < ncand;
+					const uint32_t ent = have ? ws.cand[ci] : 0u;
+					const uint32_t n_rel = ent & 0x3FFFFFFFu;
+					const bool is_long = (ent >> 30) != kClsDF11;
+					// short frames are the last 56 bits of the syndrome table and only use sub 0, 1
+					const bool active = have && (is_long || sub < 2);
+					// frame bit b sits at n + 80 + 10 b; nibble g starts at bit 4g
+					const uint32_t pb0 = n_rel + 80u + 280u * (uint32_t)sub;
+					const uint32_t lut0 = (uint32_t)(7 * sub + (is_long ? 0 : 14)) * 64u;  // byte offset of row g
+					uint32_t acc = 0, bits28 = 0;
+					if (active) {
+#pragma unroll
+						for (int s_ = 0; s_ < 7; s_++) {
+							const uint32_t pb = pb0 + 40u * s_;
+							const uint32_t wa = (pb >> 3) & ((WR - 1) << 2);  // byte offset of the word in the ring
+							const uint32_t w0 = *reinterpret_cast<const uint32_t *>(
+							    reinterpret_cast<const char *>(ws.bbits) + wa);
+							const uint32_t w1 = *reinterpret_cast<const uint32_t *>(
+							    reinterpret_cast<const char *>(ws.bbits) + wa + 4);  // bbits[WR] mirrors bbits[0]
+							const uint32_t x = __funnelshift_l(w1, w0, pb & 31u);  // bits 31, 21, 11, 1
+							const uint32_t nib = ((x & 0x80200802u) * 0x08040201u) >> 28;
+							acc ^= *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(sm.lut) + lut0 +
+							                                            64u * s_ + 4u * nib);
+							bits28 = bits28 * 16u + nib;
+						}
 					}
+					// valid.c:48-52 / :70-74: CRC over all but the last 3 bytes, XOR the last 3, == 0
+					acc ^= __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
+					acc ^= __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
+					const bool ok = have && acc == 0;
+					if (__any_sync(0xFFFFFFFFu, ok)) {
+						unsigned long long slot = 0;
+						if (ok && sub == 0)
+							slot = atomicAdd(&p.ctr->n_cand, 1ull);
+						slot = __shfl_sync(0xFFFFFFFFu, slot, lane & ~3);
+						if (ok) {
+							if (slot < p.cand_cap) {
+								uint32_t *out = reinterpret_cast<uint32_t *>(&p.cands[slot]);
+								if (sub == 0) {
+									const unsigned long long n = (unsigned long long)(jb + (long long)n_rel);
+									// pw is filled in by k_fill_pw (demod.c:127)
+									*reinterpret_cast<uint4 *>(out) = make_uint4(
+									    (uint32_t)n, (uint32_t)(n >> 32), 0u, (is_long ? 14u : 7u) | kCandNibbleWords);
+								}
+								out[4 + sub] = bits28;
+							} else if (sub == 0) {
+								atomicOr(&p.ctr->overflow, 1u);
+							}
+						}
+					}
+				}
+				// ---- try list (valid.c:46, :68): buffered per warp, flushed in batches ----
+				if (p.want_tries) {
+					if (ws.ntry + ncand > TRY_CAP)
+						flush_tries();
+					const int base = ws.ntry;
+					for (int i = lane; i < ncand; i += 32) {
+						const uint32_t ent = ws.cand[i];
+						ws.trybuf[base + i] = ((unsigned long long)(ent >> 30) << kTryClsShift) |
+						                      (unsigned long long)(jb + (long long)(ent & 0x3FFFFFFFu));
+					}
+					__syncwarp();
+					if (lane == 0)
+						ws.ntry = base + ncand;
 				}
 				__syncwarp();
 				if (lane == 0)
-					sm.ncand[par] = 0;  // stage 3 of sub-block k refills this list in the next phase A
+					ws.ncand = 0;
 			}
-			__syncthreads();  // (B) bit arrays of sub-block k visible; list k-2 recycled
-			q_fir += NT;
+			__syncwarp();
+			q_fir += 32;
 			if (q_fir >= RUNS) q_fir -= RUNS;
 		}
+		if (p.want_tries)
+			flush_tries();
 	}
 }
-
-namespace {
-
-// Production configuration and the parity-tap build.
-constexpr int kStages = ADSB_STAGES;
-constexpr int kMinBlocks = ADSB_MINB;
-
-template <bool DEBUG>
-auto kernel_ptr()
-{
-	return k_fused<kStages, kMinBlocks, DEBUG>;
-}
-
-}  // namespace
 
 int fused_block_outputs() { return S; }
 int fused_lookback() { return LAG3; }
 int fused_threads() { return NT; }
-size_t fused_smem_bytes() { return sizeof(Smem<kStages>); }
+size_t fused_smem_bytes() { return sizeof(Smem); }
 
+// Configures the kernel and returns the number of autonomous workers (warps) per SM.
 int fused_prepare(int device)
 {
 	(void)device;
-	if (cudaFuncSetAttribute(kernel_ptr<false>(), cudaFuncAttributeMaxDynamicSharedMemorySize,
+	if (cudaFuncSetAttribute(k_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                         (int)fused_smem_bytes()) != cudaSuccess ||
-	    cudaFuncSetAttribute(kernel_ptr<true>(), cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    cudaFuncSetAttribute(k_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                         (int)fused_smem_bytes()) != cudaSuccess)
 		return -1;
 	int per_sm = 0;
-	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel_ptr<false>(), NT, fused_smem_bytes()) !=
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<false>, NT, fused_smem_bytes()) !=
 	    cudaSuccess)
 		return -1;
-	return per_sm;
+	return per_sm * WPC;
 }
 
-cudaError_t launch_fused(const FusedParams &p, int grid, cudaStream_t st)
+// `workers` = number of warps wanted (at most one per span).
+cudaError_t launch_fused(const FusedParams &p, int workers, cudaStream_t st)
 {
-	if (grid <= 0)
+	if (workers <= 0)
 		return cudaSuccess;
+	const int grid = (workers + WPC - 1) / WPC;
 	if (p.dbg_amp)
-		k_fused<kStages, kMinBlocks, true><<<grid, NT, fused_smem_bytes(), st>>>(p);
+		k_fused<true><<<grid, NT, fused_smem_bytes(), st>>>(p);
 	else
-		k_fused<kStages, kMinBlocks, false><<<grid, NT, fused_smem_bytes(), st>>>(p);
+		k_fused<false><<<grid, NT, fused_smem_bytes(), st>>>(p);
 	return cudaGetLastError();
 }
 
