@@ -63,8 +63,9 @@ constexpr int LAG3 = 1472;          // stages 3/4 work this many offsets behind 
 constexpr int RUNS = 32 + LAG2;     // envelope ring, in runs of 28 floats
 constexpr int WR = 128;             // bit-array ring, in 32-bit words
 constexpr int WPB = S / 32;         // bit words per sub-block (28)
-constexpr int CAND_CAP = 96;        // survivors of the DF gate per sub-block
-constexpr int TRY_CAP = 96;         // tries buffered per warp before they are flushed
+constexpr int CAND_CAP = 96;        // survivors of the DF gate one sub-block may add
+constexpr int LIST_CAP = 192;       // survivor list of a warp: doubles as its try buffer between flushes
+constexpr int MIRROR = 8;           // words 0..7 of the bit rings are mirrored behind the end
 
 static_assert(LAG3 % 32 == 0 && LAG3 >= kLookahead + LAG2 * R + 32 + 8, "stage-3 lag");
 static_assert(WR >= WPB + LAG3 / 32 + 8, "bit ring too small");
@@ -73,22 +74,26 @@ static_assert((WR & (WR - 1)) == 0, "bit ring must be a power of two");
 struct WarpSmem {
 	uint32_t raw[STAGE_WORDS];          // 3616 B
 	float amp[RUNS * R];                // 4480 B
-	uint32_t pbits[WR];                 // P[n]: first pulse pair beats its gap
-	uint32_t qbits[WR];                 // Q[n]: pulse at n+5.. beats the gap at n..
-	uint32_t bbits[WR + 4];             // B[n]: PPM decision; bbits[WR] mirrors bbits[0]
-	uint32_t cand[CAND_CAP];            // survivors of the current sub-block
-	unsigned long long trybuf[TRY_CAP]; // tries waiting for a flush
+	uint32_t pbits[WR + MIRROR];        // P[n]: first pulse pair beats its gap
+	uint32_t qbits[WR + MIRROR];        // Q[n]: pulse at n+5.. beats the gap at n..
+	uint32_t bbits[WR + MIRROR];        // B[n]: PPM decision
+	uint32_t cand[LIST_CAP];            // survivors (offset relative to the span, class in the top bits)
 	unsigned long long full;            // mbarrier of the raw stage
-	int ncand;
-	int ntry;
+	int ncand;                          // entries in cand[]
+	int pad_;
 };
 static_assert(sizeof(WarpSmem) % 16 == 0, "per-warp shared memory must keep 16-byte alignment");
 
 struct Smem {
 	uint32_t lut[28 * 16];              // lut[g][v]: syndrome of nibble g of a 112-bit frame holding v
-	uint32_t syn[112];                  // x^(111-b) mod G
 	WarpSmem w[WPC];
 };
+
+// The syndrome table, built once per device by fused_prepare().  Frame bit b contributes
+// x^(111-b) mod G (crc.h's table is the byte-wise form of the same polynomial division; the last
+// 24 bits are XORed in unreduced, crc.h:40-42).  Entry [g][v]: nibble g (frame bits 4g..4g+3, MSB
+// first) holding value v.  A 56-bit frame is the tail of the table: its nibble g is row g+14.
+__device__ uint32_t g_lut[28 * 16];
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
@@ -151,28 +156,13 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 	const int lane = tid & 31;
 	WarpSmem &ws = sm.w[tid >> 5];
 
-	// ---- one-time setup (the only CTA barriers) ---------------------------
-	for (int b = tid; b < 112; b += NT) {
-		// Frame bit b contributes x^(111-b) mod G to the syndrome (crc.h's table is the byte-wise
-		// form of the same polynomial division; the last 24 bits are XORed in unreduced, crc.h:40-42)
-		uint32_t r = 1;
-		for (int i = 0; i < 111 - b; i++)
-			r = (r & 0x800000u) ? ((r << 1) ^ kCrcPoly) & 0xFFFFFFu : (r << 1);
-		sm.syn[b] = r;
-	}
+	// ---- one-time setup (the only CTA barrier) ----------------------------
+	for (int e = tid; e < 28 * 16; e += NT)
+		sm.lut[e] = g_lut[e];
 	if (lane == 0) {
 		mbar_init(&ws.full, 1);
 		ws.ncand = 0;
-		ws.ntry = 0;
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-	}
-	__syncthreads();
-	for (int e = tid; e < 28 * 16; e += NT) {
-		// Entry [g][v]: nibble g (frame bits 4g..4g+3, MSB first) holding value v.  A 56-bit frame
-		// is the tail of the table: its nibble g is row g+14.
-		const int g = e >> 4, v = e & 15;
-		sm.lut[e] = ((v & 8) ? sm.syn[4 * g] : 0u) ^ ((v & 4) ? sm.syn[4 * g + 1] : 0u) ^
-		            ((v & 2) ? sm.syn[4 * g + 2] : 0u) ^ ((v & 1) ? sm.syn[4 * g + 3] : 0u);
 	}
 	__syncthreads();
 	uint32_t phase = 0;  // mbarrier phase parity
@@ -186,27 +176,6 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 		const int ai = 2 * g + 1, aq = 2 * g;  // ages
 		tp[g] = make_float2(h[ai < 7 ? ai : 13 - ai], h[aq < 7 ? aq : 13 - aq]);
 	}
-
-	// Appends the buffered tries to the global list (one atomic per flush).
-	auto flush_tries = [&]() {
-		const int nt = ws.ntry;
-		if (nt > 0) {
-			unsigned long long base = 0;
-			if (lane == 0)
-				base = atomicAdd(&p.ctr->n_try, (unsigned long long)nt);
-			base = __shfl_sync(0xFFFFFFFFu, base, 0);
-			for (int i = lane; i < nt; i += 32) {
-				if (base + i < p.try_cap)
-					p.tries[base + i] = ws.trybuf[i];
-				else
-					atomicOr(&p.ctr->overflow, 2u);
-			}
-		}
-		__syncwarp();
-		if (lane == 0)
-			ws.ntry = 0;
-		__syncwarp();
-	};
 
 	for (;;) {
 		// ---- fetch a span (dynamic scheduler, one ticket per warp) --------
@@ -241,6 +210,30 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 		};
 		if (lane == 0)
 			issue(0);
+
+		// The survivor list doubles as the try list (valid.c:46, :68): entries stay until the list
+		// runs full or the span ends, then go to the global try list with one atomic.
+		auto flush_list = [&]() {
+			const int nt = ws.ncand;
+			if (p.want_tries && nt > 0) {
+				unsigned long long base = 0;
+				if (lane == 0)
+					base = atomicAdd(&p.ctr->n_try, (unsigned long long)nt);
+				base = __shfl_sync(0xFFFFFFFFu, base, 0);
+				for (int i = lane; i < nt; i += 32) {
+					const uint32_t ent = ws.cand[i];
+					if (base + i < p.try_cap)
+						p.tries[base + i] = ((unsigned long long)(ent >> 30) << kTryClsShift) |
+						                    (unsigned long long)(jb + (long long)(ent & 0x3FFFFFFFu));
+					else
+						atomicOr(&p.ctr->overflow, 2u);
+				}
+			}
+			__syncwarp();
+			if (lane == 0)
+				ws.ncand = 0;
+			__syncwarp();
+		};
 
 		int q_fir = lane;  // ring run of this lane's FIR output, (k*32 + lane) % RUNS
 
@@ -382,8 +375,11 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 					ws.pbits[wi] = pw_;
 					ws.qbits[wi] = qw_;
 					ws.bbits[wi] = bw_;
-					if (wi == 0)
-						ws.bbits[WR] = bw_;  // mirror: stage 4 reads word pairs without wrapping
+					if (wi < MIRROR) {  // mirror: stages 3/4 read runs of words without wrapping
+						ws.pbits[WR + wi] = pw_;
+						ws.qbits[WR + wi] = qw_;
+						ws.bbits[WR + wi] = bw_;
+					}
 					if (DEBUG && p.dbg_p && span_idx == 0) {
 						const long long at = (long long)((g2 - j) >> 3) * 7 + j;
 						if (at < p.dbg_n / 32) {
@@ -397,11 +393,13 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 			__syncwarp();  // bit arrays of sub-block k visible to the warp
 
 			// ================= stage 3: preamble AND + DF gate ===============
+			const int list0 = p.want_tries ? ws.ncand : 0;  // survivors of earlier sub-blocks still listed
 			if (lane < WPB) {
 				const int wd = k * WPB + lane - LAG3 / 32;
 				if (wd >= 0) {
-					const uint32_t p0 = ws.pbits[wd & (WR - 1)];
-					const uint32_t q0 = ws.qbits[wd & (WR - 1)], q1 = ws.qbits[(wd + 1) & (WR - 1)];
+					const int wb = wd & (WR - 1);  // wb .. wb+4 are readable thanks to the mirror
+					const uint32_t p0 = ws.pbits[wb];
+					const uint32_t q0 = ws.qbits[wb], q1 = ws.qbits[wb + 1];
 					// demod.c:107: p1 > 2*s1 at n, p2 > 2*s2 at n+30
 					uint32_t pre = p0 & __funnelshift_l(q1, q0, 30);
 					// ownership: only offsets in [own_lo, own_hi) (relative to j_begin) are emitted here
@@ -414,8 +412,7 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 						pre &= m_lo & m_hi;
 					}
 					if (pre) {
-						const uint32_t b2 = ws.bbits[(wd + 2) & (WR - 1)], b3 = ws.bbits[(wd + 3) & (WR - 1)],
-						               b4 = ws.bbits[(wd + 4) & (WR - 1)];
+						const uint32_t b2 = ws.bbits[wb + 2], b3 = ws.bbits[wb + 3], b4 = ws.bbits[wb + 4];
 						// first five data bits sit at n+80, +90, +100, +110, +120 (demod.c:110, :46-81)
 						const uint32_t x7 = __funnelshift_l(b3, b2, 16);  // 80  = 64 + 16
 						const uint32_t x6 = __funnelshift_l(b3, b2, 26);  // 90  = 64 + 26
@@ -433,7 +430,7 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 								const uint32_t bit = 0x80000000u >> i;
 								any &= ~bit;
 								const uint32_t cls = (m17 & bit) ? kClsDF17 : (m11 & bit) ? kClsDF11 : kClsDF18;
-								if (slot < CAND_CAP)
+								if (slot < LIST_CAP)
 									ws.cand[slot] = (o0 + (uint32_t)i) | (cls << 30);
 								slot++;
 							} while (any);
@@ -445,14 +442,19 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 
 			// ================= stage 4: slice + CRC, four lanes per survivor ==
 			const int n_all = ws.ncand;
-			if (n_all > 0) {
-				const int ncand = min(n_all, CAND_CAP);
-				if (n_all > CAND_CAP && lane == 0)
-					atomicOr(&p.ctr->overflow, 4u);
+			if (n_all > list0) {
+				const int list1 = min(n_all, LIST_CAP);
+				if (n_all > LIST_CAP) {  // absurd survivor density: the host re-runs the job generically
+					if (lane == 0) {
+						atomicOr(&p.ctr->overflow, 4u);
+						ws.ncand = LIST_CAP;
+					}
+					__syncwarp();
+				}
 				const int sub = lane & 3;  // quarter of the frame this lane slices: nibbles 7*sub .. 7*sub+6
-				for (int c0 = 0; c0 < ncand; c0 += 8) {
+				for (int c0 = list0; c0 < list1; c0 += 8) {
 					const int ci = c0 + (lane >> 2);
-					const bool have = ci < ncand;
+					const bool have = ci < list1;
 					const uint32_t ent = have ? ws.cand[ci] : 0u;
 					const uint32_t n_rel = ent & 0x3FFFFFFFu;
 					const bool is_long = (ent >> 30) != kClsDF11;
@@ -460,22 +462,20 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 					const bool active = have && (is_long || sub < 2);
 					// frame bit b sits at n + 80 + 10 b; nibble g starts at bit 4g
 					const uint32_t pb0 = n_rel + 80u + 280u * (uint32_t)sub;
-					const uint32_t lut0 = (uint32_t)(7 * sub + (is_long ? 0 : 14)) * 64u;  // byte offset of row g
-					uint32_t acc = 0, bits28 = 0;
+					const char *lutp = reinterpret_cast<const char *>(sm.lut) + (7 * sub + (is_long ? 0 : 14)) * 64;
+					const char *bbp = reinterpret_cast<const char *>(ws.bbits);
+					uint32_t acc = 0;
 					if (active) {
 #pragma unroll
 						for (int s_ = 0; s_ < 7; s_++) {
 							const uint32_t pb = pb0 + 40u * s_;
 							const uint32_t wa = (pb >> 3) & ((WR - 1) << 2);  // byte offset of the word in the ring
-							const uint32_t w0 = *reinterpret_cast<const uint32_t *>(
-							    reinterpret_cast<const char *>(ws.bbits) + wa);
-							const uint32_t w1 = *reinterpret_cast<const uint32_t *>(
-							    reinterpret_cast<const char *>(ws.bbits) + wa + 4);  // bbits[WR] mirrors bbits[0]
+							const uint32_t w0 = *reinterpret_cast<const uint32_t *>(bbp + wa);
+							const uint32_t w1 = *reinterpret_cast<const uint32_t *>(bbp + wa + 4);  // mirrored past the end
 							const uint32_t x = __funnelshift_l(w1, w0, pb & 31u);  // bits 31, 21, 11, 1
-							const uint32_t nib = ((x & 0x80200802u) * 0x08040201u) >> 28;
-							acc ^= *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(sm.lut) + lut0 +
-							                                            64u * s_ + 4u * nib);
-							bits28 = bits28 * 16u + nib;
+							// nibble value * 4 = byte offset into the LUT row
+							const uint32_t nib4 = (((x & 0x80200802u) * 0x08040201u) >> 26) & 0x3Cu;
+							acc ^= *reinterpret_cast<const uint32_t *>(lutp + 64 * s_ + nib4);
 						}
 					}
 					// valid.c:48-52 / :70-74: CRC over all but the last 3 bytes, XOR the last 3, == 0
@@ -489,6 +489,19 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 						slot = __shfl_sync(0xFFFFFFFFu, slot, lane & ~3);
 						if (ok) {
 							if (slot < p.cand_cap) {
+								// the frame bits of this quarter, gathered again (rare path)
+								uint32_t bits28 = 0;
+								if (active) {
+#pragma unroll
+									for (int s_ = 0; s_ < 7; s_++) {
+										const uint32_t pb = pb0 + 40u * s_;
+										const uint32_t wa = (pb >> 3) & ((WR - 1) << 2);
+										const uint32_t w0 = *reinterpret_cast<const uint32_t *>(bbp + wa);
+										const uint32_t w1 = *reinterpret_cast<const uint32_t *>(bbp + wa + 4);
+										const uint32_t x = __funnelshift_l(w1, w0, pb & 31u);
+										bits28 = bits28 * 16u + (((x & 0x80200802u) * 0x08040201u) >> 28);
+									}
+								}
 								uint32_t *out = reinterpret_cast<uint32_t *>(&p.cands[slot]);
 								if (sub == 0) {
 									const unsigned long long n = (unsigned long long)(jb + (long long)n_rel);
@@ -503,30 +516,16 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 						}
 					}
 				}
-				// ---- try list (valid.c:46, :68): buffered per warp, flushed in batches ----
-				if (p.want_tries) {
-					if (ws.ntry + ncand > TRY_CAP)
-						flush_tries();
-					const int base = ws.ntry;
-					for (int i = lane; i < ncand; i += 32) {
-						const uint32_t ent = ws.cand[i];
-						ws.trybuf[base + i] = ((unsigned long long)(ent >> 30) << kTryClsShift) |
-						                      (unsigned long long)(jb + (long long)(ent & 0x3FFFFFFFu));
-					}
-					__syncwarp();
-					if (lane == 0)
-						ws.ntry = base + ncand;
-				}
 				__syncwarp();
-				if (lane == 0)
-					ws.ncand = 0;
+				// keep the entries as tries until the list runs short of room for another sub-block
+				if (!p.want_tries || list1 > LIST_CAP - CAND_CAP)
+					flush_list();
 			}
 			__syncwarp();
 			q_fir += 32;
 			if (q_fir >= RUNS) q_fir -= RUNS;
 		}
-		if (p.want_tries)
-			flush_tries();
+		flush_list();
 	}
 }
 
@@ -539,6 +538,20 @@ size_t fused_smem_bytes() { return sizeof(Smem); }
 int fused_prepare(int device)
 {
 	(void)device;
+	uint32_t syn[112], lut[28 * 16];
+	for (int b = 0; b < 112; b++) {
+		uint32_t r = 1;
+		for (int i = 0; i < 111 - b; i++)
+			r = (r & 0x800000u) ? ((r << 1) ^ kCrcPoly) & 0xFFFFFFu : (r << 1);
+		syn[b] = r;
+	}
+	for (int e = 0; e < 28 * 16; e++) {
+		const int g = e >> 4, v = e & 15;
+		lut[e] = ((v & 8) ? syn[4 * g] : 0u) ^ ((v & 4) ? syn[4 * g + 1] : 0u) ^ ((v & 2) ? syn[4 * g + 2] : 0u) ^
+		         ((v & 1) ? syn[4 * g + 3] : 0u);
+	}
+	if (cudaMemcpyToSymbol(g_lut, lut, sizeof lut) != cudaSuccess)
+		return -1;
 	if (cudaFuncSetAttribute(k_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                         (int)fused_smem_bytes()) != cudaSuccess ||
 	    cudaFuncSetAttribute(k_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
