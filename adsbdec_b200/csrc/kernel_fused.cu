@@ -199,6 +199,11 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 		auto issue = [&](int kb) {
 			// lane 0: one bulk copy for the part of sub-block kb that the window holds
 			const int start = kb * S;
+			if (start >= vlo && start + STAGE_WORDS <= vhi) {  // the common case: all of it
+				mbar_expect_tx(&ws.full, STAGE_WORDS * 4u);
+				tma_load_1d(&ws.raw[0], raw_s0 + 4ll * start, STAGE_WORDS * 4u, &ws.full);
+				return;
+			}
 			const int a = max(start, vlo), b = min(start + STAGE_WORDS, vhi);
 			if (b > a) {
 				const uint32_t bytes = (uint32_t)(b - a) * 4u;
@@ -464,7 +469,7 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 					const uint32_t pb0 = n_rel + 80u + 280u * (uint32_t)sub;
 					const char *lutp = reinterpret_cast<const char *>(sm.lut) + (7 * sub + (is_long ? 0 : 14)) * 64;
 					const char *bbp = reinterpret_cast<const char *>(ws.bbits);
-					uint32_t acc = 0;
+					uint32_t acc = 0, bits28 = 0;
 					if (active) {
 #pragma unroll
 						for (int s_ = 0; s_ < 7; s_++) {
@@ -473,9 +478,9 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 							const uint32_t w0 = *reinterpret_cast<const uint32_t *>(bbp + wa);
 							const uint32_t w1 = *reinterpret_cast<const uint32_t *>(bbp + wa + 4);  // mirrored past the end
 							const uint32_t x = __funnelshift_l(w1, w0, pb & 31u);  // bits 31, 21, 11, 1
-							// nibble value * 4 = byte offset into the LUT row
-							const uint32_t nib4 = (((x & 0x80200802u) * 0x08040201u) >> 26) & 0x3Cu;
-							acc ^= *reinterpret_cast<const uint32_t *>(lutp + 64 * s_ + nib4);
+							const uint32_t nib = ((x & 0x80200802u) * 0x08040201u) >> 28;
+							acc ^= *reinterpret_cast<const uint32_t *>(lutp + 64 * s_ + 4u * nib);
+							bits28 = bits28 * 16u + nib;
 						}
 					}
 					// valid.c:48-52 / :70-74: CRC over all but the last 3 bytes, XOR the last 3, == 0
@@ -489,19 +494,6 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 						slot = __shfl_sync(0xFFFFFFFFu, slot, lane & ~3);
 						if (ok) {
 							if (slot < p.cand_cap) {
-								// the frame bits of this quarter, gathered again (rare path)
-								uint32_t bits28 = 0;
-								if (active) {
-#pragma unroll
-									for (int s_ = 0; s_ < 7; s_++) {
-										const uint32_t pb = pb0 + 40u * s_;
-										const uint32_t wa = (pb >> 3) & ((WR - 1) << 2);
-										const uint32_t w0 = *reinterpret_cast<const uint32_t *>(bbp + wa);
-										const uint32_t w1 = *reinterpret_cast<const uint32_t *>(bbp + wa + 4);
-										const uint32_t x = __funnelshift_l(w1, w0, pb & 31u);
-										bits28 = bits28 * 16u + (((x & 0x80200802u) * 0x08040201u) >> 28);
-									}
-								}
 								uint32_t *out = reinterpret_cast<uint32_t *>(&p.cands[slot]);
 								if (sub == 0) {
 									const unsigned long long n = (unsigned long long)(jb + (long long)n_rel);
