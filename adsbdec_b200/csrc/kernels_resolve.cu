@@ -43,31 +43,59 @@ __global__ void k_hist(const CandRec *__restrict__ c, const Counters *ctr, unsig
 		atomicAdd(&cnt[(unsigned long long)((long long)c[i].n - n0) >> kBShift], 1u);
 }
 
-// Exclusive scan of `in` (nb entries) into `out` (nb+1 entries), single block.
+// Exclusive scan of `in` (nb entries) into `out` (nb+1 entries), single block: tiles of 4096
+// entries (one uint4 per thread, coalesced), warp-shuffle scans inside the tile, running carry.
 __global__ void k_scan_buckets(const unsigned int *__restrict__ in, unsigned int *__restrict__ out, int nb)
 {
-	__shared__ unsigned int s32[kScanThreads];
-	const int t = threadIdx.x;
-	const int per = (nb + kScanThreads - 1) / kScanThreads;
-	const int lo = min(t * per, nb), hi = min(lo + per, nb);
-	unsigned int a = 0;
-	for (int i = lo; i < hi; i++)
-		a += in[i];
-	s32[t] = a;
+	__shared__ unsigned int warp_sum[kScanThreads / 32];
+	__shared__ unsigned int carry_s;
+	const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+	if (t == 0)
+		carry_s = 0;
 	__syncthreads();
-	for (int d = 1; d < kScanThreads; d <<= 1) {
-		const unsigned int x = t >= d ? s32[t - d] : 0u;
+	for (int base = 0; base < nb; base += 4 * kScanThreads) {
+		const int i0 = base + 4 * t;
+		unsigned int v[4];
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+			v[k] = i0 + k < nb ? in[i0 + k] : 0u;
+		const unsigned int mine = v[0] + v[1] + v[2] + v[3];
+		unsigned int x = mine;  // inclusive scan across the warp
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const unsigned int y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+			if (lane >= d)
+				x += y;
+		}
+		if (lane == 31)
+			warp_sum[w] = x;
 		__syncthreads();
-		s32[t] += x;
+		if (w == 0) {
+			unsigned int s = warp_sum[lane];
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const unsigned int y = __shfl_up_sync(0xFFFFFFFFu, s, d);
+				if (lane >= d)
+					s += y;
+			}
+			warp_sum[lane] = s;  // inclusive over warps
+		}
+		__syncthreads();
+		const unsigned int carry = carry_s;
+		unsigned int pre = carry + (w ? warp_sum[w - 1] : 0u) + (x - mine);  // exclusive prefix of this thread
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			if (i0 + k < nb)
+				out[i0 + k] = pre;
+			pre += v[k];
+		}
+		__syncthreads();
+		if (t == kScanThreads - 1)
+			carry_s = carry + warp_sum[31];
 		__syncthreads();
 	}
-	unsigned int ra = s32[t] - a;  // exclusive prefix of this thread's slice
-	for (int i = lo; i < hi; i++) {
-		out[i] = ra;
-		ra += in[i];
-	}
-	if (t == kScanThreads - 1)
-		out[nb] = s32[t];
+	if (t == 0)
+		out[nb] = carry_s;
 }
 
 __device__ __forceinline__ void repack(CandRec &o, const CandRec &c)
@@ -314,7 +342,7 @@ cudaError_t launch_count_tries_frames(const unsigned long long *tries, const uns
                                       unsigned long long *pend_out, unsigned long long *n_pend_out,
                                       unsigned long long pend_cap, StreamStats *stt, cudaStream_t st)
 {
-	k_count_tries_frames<<<64, 256, 0, st>>>(tries, n_tries_ptr, cap, frames, slot, frames_cap, scan_end, pend_out,
+	k_count_tries_frames<<<592, 256, 0, st>>>(tries, n_tries_ptr, cap, frames, slot, frames_cap, scan_end, pend_out,
 	                                         n_pend_out, pend_cap, stt);
 	return cudaGetLastError();
 }
