@@ -450,13 +450,13 @@ int stats_pass(adsbdec_b200 *h, int s, bool with_slot_list)
 	const unsigned long long scan_end = h->res->scan_end();
 	if (with_slot_list) {
 		CU(launch_count_tries_frames(h->d_tries[s], &h->d_ctr[s]->n_try, h->try_cap[s], h->d_acc[s], h->d_slot[s],
-		                             h->cand_cap[s], scan_end, h->d_pend[pout], &h->d_stats->n_pend[pout], kPendCap,
-		                             h->d_stats, h->st));
+		                             h->cand_cap[s], h->rb[s], h->job[s].n0, h->job[s].n1, scan_end, h->d_pend[pout],
+		                             &h->d_stats->n_pend[pout], kPendCap, h->d_stats, h->st));
 		h->launches += 1;
 	}
 	CU(launch_count_tries_frames(h->d_pend[pin], &h->d_stats->n_pend[pin], kPendCap, h->d_acc[s], h->d_slot[s],
-	                             h->cand_cap[s], scan_end, h->d_pend[pout], &h->d_stats->n_pend[pout], kPendCap,
-	                             h->d_stats, h->st));
+	                             h->cand_cap[s], h->rb[s], h->job[s].n0, h->job[s].n1, scan_end, h->d_pend[pout],
+	                             &h->d_stats->n_pend[pout], kPendCap, h->d_stats, h->st));
 	k_zero_u64<<<1, 1, 0, h->st>>>(&h->d_stats->n_pend[pin]);
 	CU(cudaGetLastError());
 	h->launches += 2;

@@ -56,9 +56,10 @@ cudaError_t launch_set_state(ResolveState *state, unsigned long long carry_start
                              cudaStream_t st);
 cudaError_t launch_count_tries_frames(const unsigned long long *tries, const unsigned long long *n_tries_ptr,
                                       unsigned long long cap, const CandRec *frames, const SlotResolve *slot,
-                                      unsigned long long frames_cap, unsigned long long scan_end,
-                                      unsigned long long *pend_out, unsigned long long *n_pend_out,
-                                      unsigned long long pend_cap, StreamStats *stt, cudaStream_t st);
+                                      unsigned long long frames_cap, const ResolveBuffers &rb, long long n0,
+                                      long long n1, unsigned long long scan_end, unsigned long long *pend_out,
+                                      unsigned long long *n_pend_out, unsigned long long pend_cap, StreamStats *stt,
+                                      cudaStream_t st);
 
 // ---- fused path (kernel_fused.cu) -----------------------------------------
 

@@ -34,40 +34,54 @@ __device__ float envelope_at(const uint16_t *__restrict__ raw, long long u_raw0,
 	const uint32_t pos = (uint32_t)((unsigned long long)(T + 1) + phase_origin);
 	const uint32_t rot = kTaps - pos % kTaps;  // air.c:68: o = DSFLTLEN - fidx%DSFLTLEN
 	float si = 0.0f, sq = 0.0f;
-	// No 2^32 wrap of fidx among the last 32 samples: slot k simply holds the sample that is
-	// (slot(T) - k) mod 14 back.  Otherwise search (the ring is briefly "scrambled").
 	const uint32_t posT = pos - 1u;  // (uint32)(T + origin)
-	const bool plain = posT >= 32u;
-	const uint32_t slotT = posT % kTaps;
+	if (posT >= 32u) {
+		// No 2^32 wrap of fidx among the last 32 samples: slot k simply holds the sample that is
+		// (slot(T) - k) mod 14 back.  All 14 loads are independent of the FMA chain.
+		const uint32_t slotT = posT % kTaps;
+		float v[kTaps];
+#pragma unroll
+		for (int k = 0; k < kTaps; k++) {
+			const long long u = T - (long long)((slotT + kTaps - (uint32_t)k) % kTaps);
+			float x = 0.0f;  // never written: the static ring is zero (air.c:33)
+			if (u >= 0) {
+				x = (float)raw[u - u_raw0] - 2048.0f;  // air.c:64
+				x = (u & 2) ? -x : x;                  // air.c:79-82: 2nd pair of each 4 negated
+			}
+			v[k] = x;
+		}
+#pragma unroll
+		for (int k = 0; k < kTaps; k++) {
+			const float tap = c_taps[(k + rot) % kTaps];  // dsfilter[k+o], the table is one period doubled
+			if (k & 1)
+				sq = __fmaf_rn(tap, v[k], sq);  // air.c:71 (contracted by the reference's -O3 -march=native)
+			else
+				si = __fmaf_rn(tap, v[k], si);  // air.c:70
+		}
+		return __fmaf_rn(si, si, __fmul_rn(sq, sq));  // air.c:76: vmulss q,q ; vfmadd i,i
+	}
+	// Around a wrap the ring is briefly "scrambled" (SURVEY F12): slot k holds the newest sample
+	// u <= T with (uint32)(u+origin)%14 == k, which can be up to 17 back.  Search for it.
 #pragma unroll 1
 	for (int k = 0; k < kTaps; k++) {
-		// slot k holds the newest sample u <= T with (uint32)(u+origin)%14 == k; away from a
-		// 2^32 wrap that is within the last 14 samples, across one it can be up to 17 back.
 		float v = 0.0f;
-		if (plain) {
-			const long long u = T - (long long)((slotT + kTaps - (uint32_t)k) % kTaps);
-			if (u >= 0) {
-				const float x = (float)raw[u - u_raw0] - 2048.0f;  // air.c:64
-				v = (u & 2) ? -x : x;                              // air.c:79-82
-			}
-		} else
 		for (int back = 0; back < 32; back++) {
 			long long u = T - back;
 			if (u < 0)
-				break;  // never written: static ring is zero
+				break;
 			if ((uint32_t)((unsigned long long)u + phase_origin) % kTaps == (uint32_t)k) {
-				float x = (float)raw[u - u_raw0] - 2048.0f;  // air.c:64
-				v = (u & 2) ? -x : x;                        // air.c:79-82: 2nd pair of each 4 negated
+				float x = (float)raw[u - u_raw0] - 2048.0f;
+				v = (u & 2) ? -x : x;
 				break;
 			}
 		}
-		float tap = c_taps[(k + rot) % kTaps];  // dsfilter[k+o], the table is one period doubled
+		const float tap = c_taps[(k + rot) % kTaps];
 		if (k & 1)
-			sq = __fmaf_rn(tap, v, sq);  // air.c:71 (contracted by the reference's -O3 -march=native)
+			sq = __fmaf_rn(tap, v, sq);
 		else
-			si = __fmaf_rn(tap, v, si);  // air.c:70
+			si = __fmaf_rn(tap, v, si);
 	}
-	return __fmaf_rn(si, si, __fmul_rn(sq, sq));  // air.c:76: vmulss q,q ; vfmadd i,i
+	return __fmaf_rn(si, si, __fmul_rn(sq, sq));
 }
 
 __global__ void k_envelope_generic(const uint16_t *__restrict__ raw, long long u_raw0,

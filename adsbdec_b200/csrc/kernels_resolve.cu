@@ -239,11 +239,13 @@ __global__ void k_compact(const CandRec *__restrict__ sorted, const unsigned cha
 }
 
 // Try statistics (valid.c:46, :68 as the sequential scan sees them) against the accepted frames
-// of this job, which are already on the device.
+// of this job, which are still on the device.  The bucket prefix counts of the compaction tell
+// where the frames near a try sit, so no search is needed.
 __global__ void k_count_tries_frames(const unsigned long long *__restrict__ tries,
                                      const unsigned long long *__restrict__ n_tries_ptr, unsigned long long cap,
                                      const CandRec *__restrict__ frames, const SlotResolve *slot,
-                                     unsigned long long frames_cap, unsigned long long scan_end,
+                                     unsigned long long frames_cap, const unsigned int *__restrict__ bacc_x,
+                                     long long n0, int nb, unsigned long long scan_end,
                                      unsigned long long *pend_out, unsigned long long *n_pend_out,
                                      unsigned long long pend_cap, StreamStats *st)
 {
@@ -252,25 +254,30 @@ __global__ void k_count_tries_frames(const unsigned long long *__restrict__ trie
 		n_tries = cap;
 	const unsigned long long nf = slot->n_accept < frames_cap ? slot->n_accept : frames_cap;
 	const unsigned long long s0 = slot->span0_start, e0 = slot->span0_end;
+	unsigned int mine[3] = {0, 0, 0};  // visited tries per class, added to the global counters once per warp
 	for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_tries;
 	     i += (unsigned long long)gridDim.x * blockDim.x) {
 		const unsigned long long e = tries[i];
 		const unsigned long long n = e & kTryMask;
 		const uint32_t cls = (uint32_t)(e >> kTryClsShift);
-		// last accepted frame with start < n
-		unsigned long long lo = 0, hi = nf;
-		while (lo < hi) {
-			const unsigned long long mid = (lo + hi) >> 1;
-			if (frames[mid].n < n)
-				lo = mid + 1;
-			else
-				hi = mid;
+		// Is n strictly inside an accepted frame?  Only a frame that starts in n's bucket or the one
+		// before can reach it (a frame spans <= 1200 < 4096 offsets); before this job's range only the
+		// last frame accepted earlier can.
+		bool inside = n > s0 && n < e0;
+		const long long rel = (long long)n - n0;
+		if (nb > 0 && rel >= 0) {
+			long long b = rel >> kBShift;
+			if (b > nb - 1) b = nb - 1;
+			unsigned long long lo = bacc_x[b > 0 ? b - 1 : 0], hi = bacc_x[b + 1];
+			if (hi > nf) hi = nf;
+			for (unsigned long long q = lo; q < hi; q++) {
+				const unsigned long long fs = frames[q].n;
+				if (fs >= n)
+					break;
+				if (n < fs + skip_of(frames[q].len))
+					inside = true;
+			}
 		}
-		bool inside;
-		if (lo > 0)
-			inside = n < frames[lo - 1].n + skip_of(frames[lo - 1].len);
-		else
-			inside = n > s0 && n < e0;  // the last frame accepted before this job
 		if (inside)
 			continue;  // skipped by `idx = lidx` (demod.c:128, :134), whenever the scan gets there
 		if (n >= scan_end) {
@@ -283,7 +290,15 @@ __global__ void k_count_tries_frames(const unsigned long long *__restrict__ trie
 				st->pend_overflow = 1;
 			continue;
 		}
-		atomicAdd(&st->stat_try[cls], 1u);
+		mine[0] += cls == 0;
+		mine[1] += cls == 1;
+		mine[2] += cls == 2;
+	}
+#pragma unroll
+	for (int c = 0; c < 3; c++) {
+		const unsigned int w = __reduce_add_sync(0xFFFFFFFFu, mine[c]);
+		if ((threadIdx.x & 31) == 0 && w)
+			atomicAdd(&st->stat_try[c], w);
 	}
 }
 
@@ -338,12 +353,14 @@ cudaError_t launch_set_state(ResolveState *state, unsigned long long carry_start
 
 cudaError_t launch_count_tries_frames(const unsigned long long *tries, const unsigned long long *n_tries_ptr,
                                       unsigned long long cap, const CandRec *frames, const SlotResolve *slot,
-                                      unsigned long long frames_cap, unsigned long long scan_end,
-                                      unsigned long long *pend_out, unsigned long long *n_pend_out,
-                                      unsigned long long pend_cap, StreamStats *stt, cudaStream_t st)
+                                      unsigned long long frames_cap, const ResolveBuffers &rb, long long n0,
+                                      long long n1, unsigned long long scan_end, unsigned long long *pend_out,
+                                      unsigned long long *n_pend_out, unsigned long long pend_cap, StreamStats *stt,
+                                      cudaStream_t st)
 {
-	k_count_tries_frames<<<592, 256, 0, st>>>(tries, n_tries_ptr, cap, frames, slot, frames_cap, scan_end, pend_out,
-	                                         n_pend_out, pend_cap, stt);
+	const int nb = n1 > n0 ? resolve_bucket_count(n0, n1) : 0;
+	k_count_tries_frames<<<592, 256, 0, st>>>(tries, n_tries_ptr, cap, frames, slot, frames_cap, rb.bacc_x, n0, nb,
+	                                         scan_end, pend_out, n_pend_out, pend_cap, stt);
 	return cudaGetLastError();
 }
 
