@@ -368,8 +368,17 @@ def main():
     if fused_launches:
         per_launch_ms = fused_ms / fused_launches
         achieved = 2.0 * fused_samples / fused_launches / (per_launch_ms * 1e-3) / 1e9
+        # DRAM traffic of the kernel from the committed ncu capture (bytes moved per algorithmic byte),
+        # scaled to this run's average launch
+        traffic, traffic_src = None, None
+        tp = ROOT / "profiles" / "r1_traffic.json"
+        if tp.exists():
+            t = json.loads(tp.read_text())
+            ratio = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["algorithmic_bytes"]
+            traffic = ratio * 2.0 * fused_samples / fused_launches
+            traffic_src = f"profiles/r1_traffic.json: DRAM read+write = {ratio:.3f} x algorithmic bytes"
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_fused", "ms_per_launch": per_launch_ms,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": "k_fused", "ms_per_launch": per_launch_ms,
                 "algorithmic_bytes_per_launch": 2.0 * fused_samples / fused_launches, "peak_source": peak_src,
                 "kernel_share_of_step": fused_ms / (ms_step * args.steps)}
 
