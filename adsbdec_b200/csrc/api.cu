@@ -17,6 +17,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -984,29 +985,76 @@ int adsbdec_b200_decode_file(adsbdec_b200_t *h, const char *path)
 {
 	if (!h || !path)
 		return fail(ADSB_B200_EINVAL, "null argument");
+	if (h->finished)
+		return fail(ADSB_B200_ESTATE, "decode after finish");
 	int fd = open(path, O_RDONLY);
 	if (fd < 0)
 		return fail(ADSB_B200_EIO, "cannot open %s: %s", path, strerror(errno));
-	// air.c:233-239: one reused IQBUFFSZ buffer, read() then decodeiq(buf, n/2).  decodeiq eats
-	// groups of 4 and so reads up to 3 stale entries behind a ragged tail; reusing one
-	// zero-initialised buffer reproduces exactly what it would see.
-	uint16_t *buf = (uint16_t *)calloc(kReadSamples + 4, sizeof(uint16_t));
-	if (!buf) {
-		close(fd);
-		return fail(ADSB_B200_ENOMEM, "out of memory");
-	}
+	CU(cudaSetDevice(h->device));
+	struct stat sb;
+	const bool regular = fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && h->batch >= 4 * (int64_t)kReadSamples;
 	int rc = 0;
-	for (;;) {
-		ssize_t got = read(fd, buf, kReadSamples * sizeof(uint16_t));
-		if (got <= 0)
-			break;
-		size_t ns = (size_t)got / 2;
-		ns = (ns + 3) & ~(size_t)3;
-		rc = adsbdec_b200_push(h, buf, ns);
-		if (rc)
-			break;
+	if (regular) {
+		// air.c:233-239 reads 2 MiB at a time into ONE reused buffer and calls decodeiq(buf, n/2), which
+		// eats groups of 4 and therefore reads up to 3 stale entries behind a ragged tail: whatever
+		// the previous read left at those positions (zero if there was none).  Here every read goes
+		// straight into the page-locked staging buffer; the stale entries are fetched from the file.
+		rc = ensure_batch_buffers(h, true);
+		off_t pos = 0;
+		bool had_full_read = false;
+		while (!rc) {
+			if (batch_room(h) < (int64_t)kReadSamples + 4) {
+				rc = flush_batch(h);
+				if (rc) break;
+			}
+			if (h->pin_pos == 0 && cudaEventSynchronize(h->ev_pin_free[h->cur]) != cudaSuccess) {
+				rc = fail(ADSB_B200_ECUDA, "waiting for the staging buffer");
+				break;
+			}
+			uint16_t *dst = h->pin[h->cur] + h->pin_pos;
+			const ssize_t got = read(fd, dst, kReadSamples * sizeof(uint16_t));
+			if (got <= 0)
+				break;
+			size_t ns = (size_t)got / 2;
+			if (ns % 4) {
+				const size_t need = 4 - ns % 4;
+				uint16_t stale[4] = {0, 0, 0, 0};
+				if (had_full_read)  // same buffer positions, one read earlier
+					if (pread(fd, stale, (need + 1) * sizeof(uint16_t), pos - (off_t)(kReadSamples * 2) + (off_t)(ns * 2)) < 0)
+						memset(stale, 0, sizeof stale);
+				if (got & 1)  // the odd byte overwrote the low half of the first stale entry
+					stale[0] = (uint16_t)((stale[0] & 0xFF00u) | ((const uint8_t *)dst)[got - 1]);
+				for (size_t i = 0; i < need; i++)
+					dst[ns + i] = stale[i];
+				ns += need;
+			}
+			had_full_read = (size_t)got == kReadSamples * sizeof(uint16_t);
+			pos += got;
+			h->pin_pos += (int64_t)ns;
+			h->pin_fill += (int64_t)ns;
+			h->pushed += (int64_t)ns;
+			if (h->pin_fill >= kStageSlice)
+				rc = drain_pinned(h);
+		}
+	} else {
+		// pipes and the like: the reference's loop as it is, through push()
+		uint16_t *buf = (uint16_t *)calloc(kReadSamples + 4, sizeof(uint16_t));
+		if (!buf) {
+			close(fd);
+			return fail(ADSB_B200_ENOMEM, "out of memory");
+		}
+		for (;;) {
+			ssize_t got = read(fd, buf, kReadSamples * sizeof(uint16_t));
+			if (got <= 0)
+				break;
+			size_t ns = (size_t)got / 2;
+			ns = (ns + 3) & ~(size_t)3;
+			rc = adsbdec_b200_push(h, buf, ns);
+			if (rc)
+				break;
+		}
+		free(buf);
 	}
-	free(buf);
 	close(fd);
 	if (rc)
 		return rc;

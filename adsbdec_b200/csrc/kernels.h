@@ -20,12 +20,6 @@ cudaError_t launch_scan_generic(const float *amp, long long j_amp0, long long n0
                                 unsigned long long cand_cap, unsigned long long *tries,
                                 unsigned long long try_cap, Counters *ctr, cudaStream_t st);
 
-cudaError_t launch_count_tries(const unsigned long long *tries, const unsigned long long *n_tries_ptr,
-                               unsigned long long cap, const unsigned long long *spans, int n_spans,
-                               unsigned long long scan_end, unsigned long long *pend_out,
-                               unsigned long long *n_pend_out, unsigned long long pend_cap, StreamStats *st,
-                               cudaStream_t stream);
-
 // ---- on-GPU ordering and greedy resolve (kernels_resolve.cu) ----------------
 
 struct ResolveState {        // per stream: where the sequential scan stands (demod.c:128, :134)

@@ -204,47 +204,6 @@ __global__ void k_scan_generic(const float *__restrict__ amp, long long j_amp0, 
 	cands[k] = r;
 }
 
-// Stats pass (valid.c:46, :68 as seen by the sequential scan): a try counts iff the scan visits
-// its offset, i.e. n < scan_end and n is not strictly inside an accepted frame's span.
-// Tries at n >= scan_end go to the pending list for the next pass.  spans = [start, end) pairs,
-// sorted.  The list length is read from device memory so that no host round trip is needed.
-__global__ void k_count_tries(const unsigned long long *__restrict__ tries,
-                              const unsigned long long *__restrict__ n_tries_ptr, unsigned long long cap,
-                              const unsigned long long *__restrict__ spans, int n_spans,
-                              unsigned long long scan_end, unsigned long long *pend_out,
-                              unsigned long long *n_pend_out, unsigned long long pend_cap, StreamStats *st)
-{
-	unsigned long long n_tries = *n_tries_ptr;
-	if (n_tries > cap)
-		n_tries = cap;
-	for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_tries;
-	     i += (unsigned long long)gridDim.x * blockDim.x) {
-		const unsigned long long e = tries[i];
-		const unsigned long long n = e & kTryMask;
-		const uint32_t cls = (uint32_t)(e >> kTryClsShift);
-		if (n >= scan_end) {
-			const unsigned long long k = atomicAdd(n_pend_out, 1ull);
-			if (k < pend_cap)
-				pend_out[k] = e;
-			else
-				st->pend_overflow = 1;
-			continue;
-		}
-		// last span with start < n
-		int lo = 0, hi = n_spans;
-		while (lo < hi) {
-			const int mid = (lo + hi) >> 1;
-			if (spans[2 * mid] < n)
-				lo = mid + 1;
-			else
-				hi = mid;
-		}
-		if (lo > 0 && n < spans[2 * (lo - 1) + 1])
-			continue;  // skipped by `idx = lidx` (demod.c:128, :134)
-		atomicAdd(&st->stat_try[cls], 1u);
-	}
-}
-
 // ---- launch wrappers -----------------------------------------------------
 
 cudaError_t launch_envelope_generic(const uint16_t *raw, long long u_raw0, unsigned long long origin,
@@ -274,17 +233,6 @@ cudaError_t launch_scan_generic(const float *amp, long long j_amp0, long long n0
 	const int bs = 256;
 	k_scan_generic<<<(unsigned)((count + bs - 1) / bs), bs, 0, st>>>(
 	    amp, j_amp0, n0, count, accept_df18, want_tries, cands, cand_cap, tries, try_cap, ctr);
-	return cudaGetLastError();
-}
-
-cudaError_t launch_count_tries(const unsigned long long *tries, const unsigned long long *n_tries_ptr,
-                               unsigned long long cap, const unsigned long long *spans, int n_spans,
-                               unsigned long long scan_end, unsigned long long *pend_out,
-                               unsigned long long *n_pend_out, unsigned long long pend_cap, StreamStats *st,
-                               cudaStream_t stream)
-{
-	k_count_tries<<<64, 256, 0, stream>>>(tries, n_tries_ptr, cap, spans, n_spans, scan_end, pend_out,
-	                                      n_pend_out, pend_cap, st);
 	return cudaGetLastError();
 }
 

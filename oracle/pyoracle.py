@@ -126,6 +126,26 @@ def decode(samples: np.ndarray, *, accept_df18: bool = False, fma: bool = True,
         L.oracle_free(ctx)
 
 
+def decode_file(path, *, accept_df18: bool = False, fma: bool = True) -> Result:
+    """fileInput() semantics on a file as it is on disk (2 MiB reads through one reused buffer, ragged
+    and odd-length tails included)."""
+    L = lib()
+    ctx = L.oracle_new(int(accept_df18), int(fma))
+    try:
+        if L.oracle_decode_file(ctx, str(path).encode()) != 0:
+            raise FileNotFoundError(path)
+        n = L.oracle_num_frames(ctx)
+        fr = L.oracle_frames(ctx)
+        frames = [Frame(int(fr[i].n), int(fr[i].ts), int(fr[i].pw), bytes(fr[i].bytes[:fr[i].len]))
+                  for i in range(n)]
+        t = (C.c_uint32 * 3)()
+        k = (C.c_uint32 * 3)()
+        L.oracle_stats(ctx, t, k)
+        return Result(frames, tuple(t), tuple(k), None)
+    finally:
+        L.oracle_free(ctx)
+
+
 def crc_table() -> np.ndarray:
     return np.ctypeslib.as_array(lib().oracle_crc_table(), shape=(256,)).copy()
 

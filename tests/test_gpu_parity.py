@@ -390,3 +390,19 @@ def test_list_overflow_regrows_and_redoes_in_flight_jobs(adsb, oracle, kernel):
     assert frames_key(d.frames) == frames_key(ref.frames)
     assert d.stats() == (ref.tried, ref.ok)
     assert len(ref.frames) > 300
+
+
+@pytest.mark.parametrize("extra_bytes", [0, 2 * 100001 + 1, 2 * 6, 2 * 4 + 1])
+def test_decode_file_multi_read_ragged_tail(adsb, oracle, tmp_path, extra_bytes):
+    """decode_file reads straight into page-locked staging; the stale entries decodeiq would see
+    behind a ragged / odd tail (air.c:59-82) are fetched from the previous read's file positions."""
+    cap = capture_basic(seed=170, seconds=0.12, n_frames=60, pad=0)
+    raw = cap.samples.astype("<u2").tobytes()[:2 * (2 << 20) + extra_bytes]
+    f = tmp_path / "ragged.bin"
+    f.write_bytes(raw)
+    ref = oracle.decode_file(f, accept_df18=True)
+    d = adsb.Decoder(accept_df18=True)
+    assert d.decode_file(f) == 0
+    assert frames_key(d.frames) == frames_key(ref.frames) and d.stats() == (ref.tried, ref.ok)
+    r = subprocess.run([str(adsb.CLI_PATH), "-a", "-m", "-f", str(f)], capture_output=True)
+    assert r.stdout == ref.text(1)

@@ -131,3 +131,16 @@ def test_fma_flavour_differs(oracle):
     a = oracle.decode(cap.samples, want_amp=True, fma=True).amp
     b = oracle.decode(cap.samples, want_amp=True, fma=False).amp
     assert 0.2 < np.mean(a.view(np.uint32) != b.view(np.uint32)) < 0.8
+
+
+def test_oracle_file_ragged_odd_tail_vs_live_reference(oracle, tmp_path):
+    """A file of two 2 MiB reads plus a ragged, odd-length tail: decodeiq reads stale entries of the
+    reused buffer behind the tail (air.c:59-82, :233-239)."""
+    _ref_or_skip(oracle)
+    cap = capture_basic(seed=9, seconds=0.12, n_frames=60, pad=0)
+    raw = cap.samples.astype("<u2").tobytes()[:2 * (2 << 20) + 2 * 100001 + 1]
+    f = tmp_path / "ragged.bin"
+    f.write_bytes(raw)
+    ref = _run_ref_complete(oracle, f, ("-a", "-m"))
+    r = oracle.decode_file(f, accept_df18=True)
+    assert r.text(1) == ref.stdout and (r.tried, r.ok) == ref.stats()
