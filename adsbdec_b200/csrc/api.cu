@@ -830,7 +830,7 @@ int adsbdec_b200_reset(adsbdec_b200_t *h, uint64_t start_sample)
 		h->job[s].active = false;
 	delete h->res;
 	h->res = new Resolver(h->cfg.emulate_reference_tail != 0);
-	h->frames.clear();
+	h->frames.clear();  // keeps its capacity
 	h->emitted = 0;
 	for (int i = 0; i < 3; i++)
 		h->stat_ok[i] = 0;

@@ -12,23 +12,38 @@ namespace adsb {
 void Resolver::scan_to(uint64_t cutoff, std::vector<adsbdec_b200_frame_t> &accepted)
 {
 	// One deqframe(ampbuff, len) call whose loop bound len-DECOFFSET is `cutoff` in absolute
-	// offsets (demod.c:89).  idx starts at ampbuff[0] = base_.
+	// offsets (demod.c:89).  idx starts at ampbuff[0] = base_.  Candidates come from the few left
+	// over from earlier feeds (pending_) and then, in place, from the array being fed.
 	uint64_t pos = base_;
-	while (head_ < pending_.size() && pending_[head_].n < cutoff) {
-		const adsbdec_b200_candidate_t &c = pending_[head_++];
-		if (c.n < pos)
+	for (;;) {
+		const adsbdec_b200_candidate_t *c;
+		if (head_ < pending_.size())
+			c = &pending_[head_];
+		else if (in_i_ < in_n_)
+			c = &in_[in_i_];
+		else
+			break;
+		if (c->n >= cutoff)
+			break;
+		if (head_ < pending_.size())
+			head_++;
+		else
+			in_i_++;
+		if (c->n < pos)
 			continue;  // inside the frame just accepted: never evaluated (demod.c:128, :134)
-		const uint64_t skip = c.len == 7 ? kSkipShort : kSkipLong;
-		adsbdec_b200_frame_t f;
-		memset(&f, 0, sizeof f);
-		f.n = c.n;
-		f.ts = c.n + 1 - drift_;  // demod.c:99: one tick per loop iteration, not per sample
-		f.pw = c.pw;
-		f.len = (int32_t)c.len;
-		memcpy(f.bytes, c.bytes, c.len);
-		accepted.push_back(f);
+		const uint64_t skip = c->len == 7 ? kSkipShort : kSkipLong;
+		accepted.emplace_back();
+		adsbdec_b200_frame_t &f = accepted.back();
+		f.ts = c->n + 1 - drift_;  // demod.c:99: one tick per loop iteration, not per sample
+		f.n = c->n;
+		f.pw = c->pw;
+		f.len = (int32_t)c->len;
+		memcpy(f.bytes, c->bytes, 14);
+		if (c->len == 7)
+			memset(f.bytes + 7, 0, 7);
+		f.pad_[0] = f.pad_[1] = 0;
 		drift_ += skip - 1;
-		pos = c.n + skip;  // demod.c:110, :119-123: idx = lidx
+		pos = c->n + skip;  // demod.c:110, :119-123: idx = lidx
 	}
 	base_ = std::max(cutoff, pos);  // deqframe returns idx; air.c:96-98 keeps the rest
 	scan_end_ = cutoff;
@@ -56,14 +71,21 @@ void Resolver::feed(const adsbdec_b200_candidate_t *c, size_t count, uint64_t sc
 	if (head_ == pending_.size()) {
 		pending_.clear();
 		head_ = 0;
-	} else if (head_ > (1u << 16)) {
-		pending_.erase(pending_.begin(), pending_.begin() + (ptrdiff_t)head_);
-		head_ = 0;
 	}
-	pending_.insert(pending_.end(), c, c + count);
+	in_ = c;
+	in_n_ = count;
+	in_i_ = 0;
 	scanned_upto_ = std::max(scanned_upto_, scanned_upto);
 	total_out_ = std::max(total_out_, total_out);
 	run_calls(accepted);
+	// keep what the call schedule has not reached yet (the caller's array goes away)
+	if (head_ == pending_.size()) {
+		pending_.clear();
+		head_ = 0;
+	}
+	pending_.insert(pending_.end(), c + in_i_, c + count);
+	in_ = nullptr;
+	in_n_ = in_i_ = 0;
 }
 
 void Resolver::finish(std::vector<adsbdec_b200_frame_t> &accepted)

@@ -43,6 +43,8 @@ private:
 	uint64_t total_out_ = 0;
 	std::vector<adsbdec_b200_candidate_t> pending_;  // sorted by n; [head_, size) not yet consumed
 	size_t head_ = 0;
+	const adsbdec_b200_candidate_t *in_ = nullptr;  // array being fed, consumed in place
+	size_t in_n_ = 0, in_i_ = 0;
 };
 
 }  // namespace adsb
