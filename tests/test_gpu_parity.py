@@ -406,3 +406,60 @@ def test_decode_file_multi_read_ragged_tail(adsb, oracle, tmp_path, extra_bytes)
     assert frames_key(d.frames) == frames_key(ref.frames) and d.stats() == (ref.tried, ref.ok)
     r = subprocess.run([str(adsb.CLI_PATH), "-a", "-m", "-f", str(f)], capture_output=True)
     assert r.stdout == ref.text(1)
+
+
+# ---- handle life cycle and error behaviour ---------------------------------------------------
+
+def test_reset_reuses_the_handle(adsb, oracle):
+    a = capture_basic(seed=180, seconds=0.2, n_frames=80)
+    b = capture_basic(seed=181, seconds=0.15, n_frames=60)
+    d = adsb.Decoder(accept_df18=True)
+    for cap, origin in ((a, 0), (b, 0), (a, 2**32 - 1_000_000), (b, 8)):
+        d.reset(origin)
+        d.push(cap.samples)
+        d.finish()
+        ref = oracle.decode(cap.samples, accept_df18=True, origin=origin)
+        assert frames_key(d.frames) == frames_key(ref.frames) and d.stats() == (ref.tried, ref.ok)
+
+
+def test_state_errors(adsb):
+    d = adsb.Decoder()
+    d.push(np.full(4000, 2048, dtype="<u2"))
+    d.finish()
+    d.finish()                                   # idempotent
+    with pytest.raises(adsb.AdsbError) as e:
+        d.push(np.full(8, 2048, dtype="<u2"))    # push after finish
+    assert e.value.code == -5
+    with pytest.raises(adsb.AdsbError) as e:
+        adsb.Decoder(start_sample=2)             # must be a multiple of 4
+    assert e.value.code == -1
+    with pytest.raises(adsb.AdsbError) as e:
+        adsb.Decoder(device=99)
+    assert e.value.code == -2
+    with pytest.raises(adsb.AdsbError) as e:
+        d.decode_file("/nonexistent/file.bin")   # finished handle
+    assert e.value.code == -5
+    assert adsb.Decoder().decode_file("/nonexistent/file.bin") == -6   # air.c:225-228: no frames, no error exit
+
+
+def test_stats_can_be_switched_off(adsb, oracle):
+    cap = capture_basic(seed=182, seconds=0.2, n_frames=80)
+    ref = oracle.decode(cap.samples)
+    d = adsb.decode(cap.samples, collect_stats=False)
+    assert frames_key(d.frames) == frames_key(ref.frames)
+    tr, ok = d.stats()
+    assert tr == (0, 0, 0) and ok == ref.ok
+
+
+def test_clear_frames_on_a_long_running_stream(adsb, oracle):
+    cap = capture_basic(seed=183, seconds=0.5, n_frames=250)
+    ref = oracle.decode(cap.samples)
+    got = []
+    d = adsb.Decoder(batch_samples=1 << 20, sink=lambda fr, ts, pw: got.append((ts, pw, fr)))
+    for i in range(0, cap.samples.size, 1 << 20):
+        d.push(cap.samples[i:i + (1 << 20)])
+        adsb.lib().adsbdec_b200_clear_frames(d._h)
+    d.finish()
+    assert got == [(f.ts, f.pw, f.data) for f in ref.frames]
+    assert d.stats() == (ref.tried, ref.ok)
+    assert d.num_frames <= len(ref.frames)
