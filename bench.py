@@ -274,6 +274,10 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     A.lib()   # fail loudly if the extension is missing
+    if world > 1:
+        # keep each rank (and the page-locked memory it allocates) on the NUMA node of its GPU
+        from adsbdec_b200.parallel import bind_to_gpu_numa_node
+        bind_to_gpu_numa_node(local)
 
     seed = 1234 + rank     # every rank = its own receiver stream (weak scaling, no data-path collective)
     cap, injected, sig = build_device_capture(torch, dev, args.seconds, seed)
