@@ -44,7 +44,7 @@ SIGMA = 25.0
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seconds", type=float, default=60.0, help="capture length per GPU (default: configs[1])")
@@ -134,7 +134,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.004)
 
     def __enter__(self):
         if self.nv:
