@@ -733,8 +733,12 @@ int adsbdec_b200_open(const adsbdec_b200_config_t *cfg, adsbdec_b200_t **out)
 			break;
 		}
 		// reserved[0] / reserved[1]: initial list capacities (tests use tiny ones to exercise regrowth)
-		const unsigned long long cc = cfg->reserved[0] ? cfg->reserved[0] : 1ull << 18;
-		const unsigned long long tc = cfg->reserved[1] ? cfg->reserved[1] : 1ull << 20;
+		// default: sized for a dense capture at this batch size (they regrow on demand anyway), so that
+		// hundreds of small-batch decoders - one per receiver stream - stay cheap
+		const unsigned long long cc =
+		    cfg->reserved[0] ? cfg->reserved[0] : std::min<unsigned long long>(1ull << 18, std::max<unsigned long long>(4096, (unsigned long long)h->batch / 128));
+		const unsigned long long tc =
+		    cfg->reserved[1] ? cfg->reserved[1] : std::min<unsigned long long>(1ull << 20, std::max<unsigned long long>(16384, (unsigned long long)h->batch / 32));
 		for (int s = 0; s < kSlots && !rc; s++)
 			rc = alloc_slot_outputs(h, s, cc, tc);
 		if (rc) break;

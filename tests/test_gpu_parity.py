@@ -463,3 +463,26 @@ def test_clear_frames_on_a_long_running_stream(adsb, oracle):
     assert got == [(f.ts, f.pw, f.data) for f in ref.frames]
     assert d.stats() == (ref.tried, ref.ok)
     assert d.num_frames <= len(ref.frames)
+
+
+def test_many_concurrent_receiver_streams(adsb, oracle):
+    """Config 5 shape: many independent receiver streams decoded side by side on one GPU, their
+    pushes interleaved; every stream must equal its own oracle run."""
+    import torch
+    n_streams = 24
+    caps = [synth_capture(0.15, 50 + 3 * i, snr_db=14 + (i % 8), seed=300 + i, df_mix=DF_MIX_ALL, pad=1 << 15)
+            for i in range(n_streams)]
+    refs = [oracle.decode(c.samples, accept_df18=bool(i & 1)) for i, c in enumerate(caps)]
+    decs = [adsb.Decoder(accept_df18=bool(i & 1), batch_samples=1 << 19) for i in range(n_streams)]
+    free0 = torch.cuda.mem_get_info()[0]
+    piece = 262144
+    for pos in range(0, max(c.samples.size for c in caps), piece):
+        for d, c in zip(decs, caps):
+            if pos < c.samples.size:
+                d.push(c.samples[pos:pos + piece])
+    for d in decs:
+        d.finish()
+    used = free0 - torch.cuda.mem_get_info()[0]
+    for d, r in zip(decs, refs):
+        assert frames_key(d.frames) == frames_key(r.frames) and d.stats() == (r.tried, r.ok)
+    assert used / n_streams < 64 << 20, f"{used / n_streams / 2**20:.0f} MiB of HBM per stream"
