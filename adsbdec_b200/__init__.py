@@ -267,10 +267,11 @@ class Decoder:
         return ms.value, n.value
 
     def host_time(self, reset: bool = False):
-        """Host wall ms by phase: wait_job, sort, resolve, stats_issue, sink, -, wait_upload, jobs."""
+        """Host wall ms by phase (and two counters): wait_job, candidates, resolve, stats_issue, sink,
+        tries, wait_upload, jobs."""
         a = (C.c_double * 8)()
         _check(lib().adsbdec_b200_host_time(self._h, a, int(reset)))
-        return dict(zip(("wait_job", "sort", "resolve", "stats_issue", "sink", "rsv", "wait_upload", "jobs"), a))
+        return dict(zip(("wait_job", "candidates", "resolve", "stats_issue", "sink", "tries", "wait_upload", "jobs"), a))
 
     def fused_time(self, reset: bool = False):
         ms = C.c_double()

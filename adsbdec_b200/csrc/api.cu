@@ -192,7 +192,7 @@ struct adsbdec_b200 {
 	uint64_t launches = 0, fused_launches = 0, fused_samples = 0;
 
 	std::vector<adsbdec_b200_candidate_t> cand_tmp;
-	// host-side wall time by phase (ms): 0 wait for job, 1 (unused), 2 resolve, 3 stats pass issue,
+	// host-side wall time by phase (ms): 0 wait for job, 1 CRC-valid candidates (count), 2 resolve, 3 stats pass issue,
 	// 4 sink/emit, 5 upload issue + staging memcpy, 6 wait for uploads, 7 jobs completed
 	double host_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
@@ -509,6 +509,8 @@ int complete_job(adsbdec_b200 *h, int s)
 			if (h->job[1 - s].active)
 				RC(enqueue_job(h, 1 - s, false));
 		}
+		h->host_ms[1] += (double)h->h_ctr[s]->n_cand;  // CRC-valid candidates seen (before the greedy rule)
+		h->host_ms[5] += (double)h->h_ctr[s]->n_try;   // gate-passing offsets seen
 		n_res = j.resolve ? (size_t)h->h_slot[s]->n_accept : (size_t)std::min<unsigned long long>(h->h_ctr[s]->n_cand, h->cand_cap[s]);
 		if (n_res > kSpecCands) {
 			const CandRec *src = j.resolve ? h->d_acc[s] : h->rb[s].sorted;

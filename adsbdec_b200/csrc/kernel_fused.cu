@@ -268,9 +268,6 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 					w[4 * i + 2] = t.z;
 					w[4 * i + 3] = t.w;
 				}
-				__syncwarp();  // the raw stage has been read: the next sub-block may land in it
-				if (lane == 0 && k + 1 < nb)
-					issue(k + 1);
 
 				// 12-bit domain check (the float tricks below are exact for samples < 4096)
 				uint32_t any = 0;
@@ -279,6 +276,14 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 					any |= w[i];
 				if (any & 0xF000F000u)
 					p.ctr->wide = 1;
+				// The raw stage may be refilled only once every lane HOLDS its words: the test above
+				// consumed all of them, so past this barrier the loads have returned (issuing the copy
+				// right behind the load instructions lost words to the incoming data now and then).
+				__syncwarp();
+				if (lane == 0 && k + 1 < nb) {
+					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+					issue(k + 1);
+				}
 
 				// u16 pair -> (x-2048) * sign as float2.  Word parity == parity of its index here
 				// (jb, S, R*lane are even): odd words are samples t%4 in {2,3}, negated (air.c:79-82)
@@ -399,6 +404,7 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 
 			// ================= stage 3: preamble AND + DF gate ===============
 			const int list0 = p.want_tries ? ws.ncand : 0;  // survivors of earlier sub-blocks still listed
+			__syncwarp();  // every lane has read the list length before any lane appends to it
 			if (lane < WPB) {
 				const int wd = k * WPB + lane - LAG3 / 32;
 				if (wd >= 0) {

@@ -131,9 +131,10 @@ void adsbdec_b200_clear_frames(adsbdec_b200_t *h);
 int adsbdec_b200_kernel_time(adsbdec_b200_t *h, double *ms, uint64_t *launches, int reset);
 
 /* Host wall time (ms) by phase since open / the last reset of the counters: [0] blocked waiting
- * for a scan job, [1] candidate bucket sort + repack, [2] sequential resolver, [3] issuing the
- * statistics pass, [4] sink calls, [5] reserved, [6] blocked waiting for uploads at the end of
- * push(), [7] number of jobs completed. */
+ * for a scan job, [1] COUNT of CRC-valid candidates the kernels reported (before the greedy rule),
+ * [2] sequential resolver, [3] issuing the statistics pass, [4] sink calls, [5] COUNT of
+ * gate-passing offsets ("tries") reported, [6] blocked waiting for uploads at the end of push(),
+ * [7] number of jobs completed. */
 int adsbdec_b200_host_time(adsbdec_b200_t *h, double ms[8], int reset);
 
 /* Per-kernel timing of the fused kernel alone (for the roofline line). */
