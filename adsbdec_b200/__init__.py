@@ -29,7 +29,7 @@ EXPORTS = [
     "adsbdec_b200_set_sink",
     "adsbdec_b200_push", "adsbdec_b200_push_device", "adsbdec_b200_finish", "adsbdec_b200_decode_file",
     "adsbdec_b200_stats", "adsbdec_b200_num_frames", "adsbdec_b200_frames", "adsbdec_b200_clear_frames",
-    "adsbdec_b200_kernel_time", "adsbdec_b200_host_time", "adsbdec_b200_fused_time", "adsbdec_b200_format_packet",
+    "adsbdec_b200_kernel_time", "adsbdec_b200_telemetry", "adsbdec_b200_fused_time", "adsbdec_b200_format_packet",
     "adsbdec_b200_envelope", "adsbdec_b200_resolver_new", "adsbdec_b200_resolver_free",
     "adsbdec_b200_resolver_feed", "adsbdec_b200_resolver_finish", "adsbdec_b200_resolver_scan_end",
     "adsbdec_b200_chunk_candidates", "adsbdec_b200_debug_fused", "adsbdec_b200_last_error",
@@ -41,6 +41,12 @@ class Config(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("accept_df18", C.c_int32),
                 ("emulate_reference_tail", C.c_int32), ("collect_stats", C.c_int32), ("kernel", C.c_int32),
                 ("batch_samples", C.c_uint64), ("start_sample", C.c_uint64), ("reserved", C.c_uint64 * 4)]
+
+
+class Telemetry(C.Structure):
+    _fields_ = [("wait_job_ms", C.c_double), ("resolve_ms", C.c_double), ("stats_issue_ms", C.c_double),
+                ("sink_ms", C.c_double), ("wait_upload_ms", C.c_double), ("jobs", C.c_uint64),
+                ("candidates", C.c_uint64), ("tries", C.c_uint64)]
 
 
 class CFrame(C.Structure):
@@ -115,7 +121,7 @@ def lib():
         L.adsbdec_b200_clear_frames.argtypes = [vp]
         L.adsbdec_b200_clear_frames.restype = None
         L.adsbdec_b200_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64), C.c_int]
-        L.adsbdec_b200_host_time.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
+        L.adsbdec_b200_telemetry.argtypes = [vp, C.POINTER(Telemetry), C.c_int]
         L.adsbdec_b200_fused_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64), C.POINTER(u64), C.c_int]
         L.adsbdec_b200_format_packet.argtypes = [C.c_int, C.c_char_p, C.c_int, u64, C.c_uint32, C.c_char_p]
         L.adsbdec_b200_envelope.argtypes = [C.c_int, vp, C.c_size_t, C.c_int, u64, vp, C.c_size_t]
@@ -266,12 +272,12 @@ class Decoder:
         _check(lib().adsbdec_b200_kernel_time(self._h, C.byref(ms), C.byref(n), int(reset)))
         return ms.value, n.value
 
-    def host_time(self, reset: bool = False):
-        """Host wall ms by phase (and two counters): wait_job, candidates, resolve, stats_issue, sink,
-        tries, wait_upload, jobs."""
-        a = (C.c_double * 8)()
-        _check(lib().adsbdec_b200_host_time(self._h, a, int(reset)))
-        return dict(zip(("wait_job", "candidates", "resolve", "stats_issue", "sink", "tries", "wait_upload", "jobs"), a))
+    def host_time(self, reset: bool = False) -> dict:
+        """Host-side telemetry: wall ms per phase of the caller's thread plus what the kernels reported
+        (jobs, CRC-valid candidates, gate-passing offsets)."""
+        t = Telemetry()
+        _check(lib().adsbdec_b200_telemetry(self._h, C.byref(t), int(reset)))
+        return {name: getattr(t, name) for name, _ in Telemetry._fields_}
 
     def fused_time(self, reset: bool = False):
         ms = C.c_double()

@@ -192,9 +192,7 @@ struct adsbdec_b200 {
 	uint64_t launches = 0, fused_launches = 0, fused_samples = 0;
 
 	std::vector<adsbdec_b200_candidate_t> cand_tmp;
-	// host-side wall time by phase (ms): 0 wait for job, 1 CRC-valid candidates (count), 2 resolve, 3 stats pass issue,
-	// 4 sink/emit, 5 upload issue + staging memcpy, 6 wait for uploads, 7 jobs completed
-	double host_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	adsbdec_b200_telemetry_t tel = {};
 
 	// parity taps of the fused kernel (adsbdec_b200_debug_fused)
 	float *dbg_amp = nullptr;
@@ -479,7 +477,7 @@ int complete_job(adsbdec_b200 *h, int s)
 		for (int attempt = 0;; attempt++) {
 			const double t0 = now_ms();
 			CU(cudaEventSynchronize(h->ev_done[s]));
-			h->host_ms[0] += now_ms() - t0;
+			h->tel.wait_job_ms += now_ms() - t0;
 			float ms = 0;
 			cudaEventElapsedTime(&ms, h->ev_a[s], h->ev_b[s]);
 			h->kernel_ms += ms;
@@ -509,8 +507,8 @@ int complete_job(adsbdec_b200 *h, int s)
 			if (h->job[1 - s].active)
 				RC(enqueue_job(h, 1 - s, false));
 		}
-		h->host_ms[1] += (double)h->h_ctr[s]->n_cand;  // CRC-valid candidates seen (before the greedy rule)
-		h->host_ms[5] += (double)h->h_ctr[s]->n_try;   // gate-passing offsets seen
+		h->tel.candidates += h->h_ctr[s]->n_cand;
+		h->tel.tries += h->cfg.collect_stats ? h->h_ctr[s]->n_try : 0;
 		n_res = j.resolve ? (size_t)h->h_slot[s]->n_accept : (size_t)std::min<unsigned long long>(h->h_ctr[s]->n_cand, h->cand_cap[s]);
 		if (n_res > kSpecCands) {
 			const CandRec *src = j.resolve ? h->d_acc[s] : h->rb[s].sorted;
@@ -539,10 +537,10 @@ int complete_job(adsbdec_b200 *h, int s)
 	}
 	const double t4 = now_ms();
 	emit_new_frames(h);
-	h->host_ms[2] += t3 - t2;
-	h->host_ms[3] += t4 - t3;
-	h->host_ms[4] += now_ms() - t4;
-	h->host_ms[7] += 1;
+	h->tel.resolve_ms += t3 - t2;
+	h->tel.stats_issue_ms += t4 - t3;
+	h->tel.sink_ms += now_ms() - t4;
+	h->tel.jobs += 1;
 	return 0;
 }
 
@@ -901,7 +899,7 @@ int adsbdec_b200_push(adsbdec_b200_t *h, const uint16_t *samples, size_t n)
 	if (direct) {
 		const double t0 = now_ms();
 		CU(cudaStreamSynchronize(h->st_copy));  // the caller may reuse its buffer on return
-		h->host_ms[6] += now_ms() - t0;
+		h->tel.wait_upload_ms += now_ms() - t0;
 	}
 	return 0;
 }
@@ -1113,15 +1111,13 @@ int adsbdec_b200_kernel_time(adsbdec_b200_t *h, double *ms, uint64_t *launches, 
 	return 0;
 }
 
-int adsbdec_b200_host_time(adsbdec_b200_t *h, double ms[8], int reset)
+int adsbdec_b200_telemetry(adsbdec_b200_t *h, adsbdec_b200_telemetry_t *out, int reset)
 {
-	if (!h || !ms)
+	if (!h || !out)
 		return fail(ADSB_B200_EINVAL, "null argument");
-	for (int i = 0; i < 8; i++) {
-		ms[i] = h->host_ms[i];
-		if (reset)
-			h->host_ms[i] = 0;
-	}
+	*out = h->tel;
+	if (reset)
+		h->tel = adsbdec_b200_telemetry_t{};
 	return 0;
 }
 

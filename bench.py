@@ -59,7 +59,7 @@ def parse_args():
 
 def dense_segment(seed: int, seconds: float = SEG_SECONDS):
     """Noise-free dense traffic (float32, centred on 0) for `seconds`, rendered on the host."""
-    from adsbdec_b200.modulator import Burst, amplitude_for_snr, envelope, make_frame
+    from adsbdec_b200.modulator import amplitude_for_snr, envelope, make_frame
     rng = np.random.default_rng(seed)
     n = int(seconds * FS)
     n -= n % 8

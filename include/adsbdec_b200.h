@@ -130,12 +130,19 @@ void adsbdec_b200_clear_frames(adsbdec_b200_t *h);
  * kernels since open / since the last call, and how many kernels were launched. */
 int adsbdec_b200_kernel_time(adsbdec_b200_t *h, double *ms, uint64_t *launches, int reset);
 
-/* Host wall time (ms) by phase since open / the last reset of the counters: [0] blocked waiting
- * for a scan job, [1] COUNT of CRC-valid candidates the kernels reported (before the greedy rule),
- * [2] sequential resolver, [3] issuing the statistics pass, [4] sink calls, [5] COUNT of
- * gate-passing offsets ("tries") reported, [6] blocked waiting for uploads at the end of push(),
- * [7] number of jobs completed. */
-int adsbdec_b200_host_time(adsbdec_b200_t *h, double ms[8], int reset);
+/* Host-side telemetry since open / the last reset: where the caller's thread spent its time and
+ * what the kernels reported. */
+typedef struct {
+	double wait_job_ms;      /* blocked waiting for a scan job to finish                      */
+	double resolve_ms;       /* timestamps + deqframe call schedule over accepted frames       */
+	double stats_issue_ms;   /* issuing the statistics pass                                    */
+	double sink_ms;          /* sink calls and Ok counters                                     */
+	double wait_upload_ms;   /* blocked at the end of push() until the caller's buffer is free */
+	uint64_t jobs;           /* scan jobs completed                                            */
+	uint64_t candidates;     /* CRC-valid candidates reported by the kernels (before the greedy rule) */
+	uint64_t tries;          /* gate-passing offsets reported (valid.c:46, :68 before exclusion)     */
+} adsbdec_b200_telemetry_t;
+int adsbdec_b200_telemetry(adsbdec_b200_t *h, adsbdec_b200_telemetry_t *out, int reset);
 
 /* Per-kernel timing of the fused kernel alone (for the roofline line). */
 int adsbdec_b200_fused_time(adsbdec_b200_t *h, double *ms, uint64_t *launches,

@@ -1,3 +1,4 @@
+"""Stress: an 8.8 GB device-resident stream across the real 2^32 fidx wrap, fused vs generic kernels and the oracle tile property."""
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
