@@ -22,12 +22,15 @@
 
 #include <algorithm>
 #include <chrono>
+#include <memory>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "../../include/adsbdec_b200.h"
 #include "common.h"
 #include "kernels.h"
+#include "readpool.h"
 #include "resolver.h"
 
 using namespace adsb;
@@ -67,6 +70,7 @@ constexpr int64_t kDeviceJob = 256ll << 20;  // samples per scan job when the da
 constexpr int64_t kAmpChunk = 8ll << 20;   // generic path: offsets per envelope scratch pass
 constexpr int64_t kMinFused = 1 << 16;     // ranges smaller than this use the generic kernels
 constexpr int64_t kStageSlice = 4ll << 20; // pageable pushes are staged and uploaded in slices
+constexpr int64_t kBulkRead = 16ll << 20;  // decode_file: samples fetched per parallel read
 constexpr unsigned long long kSpecCands = 1ull << 15;  // candidates copied back speculatively
 constexpr unsigned long long kPendCap = 1ull << 18;
 constexpr int kSlots = 2;
@@ -193,6 +197,7 @@ struct adsbdec_b200 {
 
 	std::vector<adsbdec_b200_candidate_t> cand_tmp;
 	adsbdec_b200_telemetry_t tel = {};
+	std::unique_ptr<ReadPool> readers;  // decode_file helpers, started on first use
 
 	// parity taps of the fused kernel (adsbdec_b200_debug_fused)
 	float *dbg_amp = nullptr;
@@ -1006,6 +1011,17 @@ int adsbdec_b200_decode_file(adsbdec_b200_t *h, const char *path)
 		rc = ensure_batch_buffers(h, true);
 		off_t pos = 0;
 		bool had_full_read = false;
+		// every read but the last returns 2 MiB whatever the order it is issued in: fetch those in
+		// parallel (readpool.h); reserved[2] = reader threads, 0 = up to 12, 1 = this thread alone
+		int64_t bulk_left = (int64_t)(sb.st_size / (off_t)(kReadSamples * sizeof(uint16_t))) * kReadSamples;
+		if (!rc && bulk_left > 0 && !h->readers) {
+			int nthr = (int)h->cfg.reserved[2];
+			if (nthr <= 0)
+				nthr = std::max(1, std::min(12, (int)std::thread::hardware_concurrency() * 3 / 4));
+			h->readers.reset(new (std::nothrow) ReadPool(std::min(nthr, 64) - 1));
+			if (!h->readers)
+				rc = fail(ADSB_B200_ENOMEM, "out of memory");
+		}
 		while (!rc) {
 			if (batch_room(h) < (int64_t)kReadSamples + 4) {
 				rc = flush_batch(h);
@@ -1015,8 +1031,24 @@ int adsbdec_b200_decode_file(adsbdec_b200_t *h, const char *path)
 				rc = fail(ADSB_B200_ECUDA, "waiting for the staging buffer");
 				break;
 			}
+			if (bulk_left > 0) {
+				int64_t take = std::min(bulk_left, std::min(kBulkRead, batch_room(h) - 4));
+				take -= take % kReadSamples;
+				if (!h->readers->read(fd, h->pin[h->cur] + h->pin_pos, pos, (size_t)take * sizeof(uint16_t))) {
+					rc = fail(ADSB_B200_EIO, "short read from %s (file changed while decoding?)", path);
+					break;
+				}
+				had_full_read = true;
+				bulk_left -= take;
+				pos += (off_t)take * (off_t)sizeof(uint16_t);
+				h->pin_pos += take;
+				h->pin_fill += take;
+				h->pushed += take;
+				rc = drain_pinned(h);
+				continue;
+			}
 			uint16_t *dst = h->pin[h->cur] + h->pin_pos;
-			const ssize_t got = read(fd, dst, kReadSamples * sizeof(uint16_t));
+			const ssize_t got = pread(fd, dst, kReadSamples * sizeof(uint16_t), pos);
 			if (got <= 0)
 				break;
 			size_t ns = (size_t)got / 2;

@@ -84,7 +84,8 @@ typedef struct {
 	                                    a time-chunk of a longer capture passes its offset so the
 	                                    FIR rotation / fidx wrap (air.c:34,65) line up)           */
 	uint64_t reserved[4];            /* [0], [1]: initial candidate / try list capacities (0 = default;
-	                                    lists regrow on demand), [2], [3]: must be 0                  */
+	                                    lists regrow on demand), [2]: threads decode_file reads a regular
+	                                    file with (0 = up to 12, 1 = the calling thread only), [3]: 0  */
 } adsbdec_b200_config_t;
 
 /* Fills *cfg with defaults (device 0, reference-compatible behaviour). */
