@@ -159,7 +159,8 @@ struct adsbdec_b200 {
 	Job job[kSlots];
 	int next_slot = 0;
 	Counters *d_ctr[kSlots] = {nullptr, nullptr}, *h_ctr[kSlots] = {nullptr, nullptr};
-	CandRec *d_cands[kSlots] = {nullptr, nullptr}, *h_cands[kSlots] = {nullptr, nullptr};
+	CandRec *d_cands[kSlots] = {nullptr, nullptr};
+	unsigned char *h_cands[kSlots] = {nullptr, nullptr};  // accepted frames (FrameRec) or sorted candidates (CandRec)
 	unsigned long long cand_cap[kSlots] = {0, 0};
 	unsigned long long *d_tries[kSlots] = {nullptr, nullptr};
 	unsigned long long try_cap[kSlots] = {0, 0};
@@ -167,7 +168,7 @@ struct adsbdec_b200 {
 	ResolveBuffers rb[kSlots] = {};
 	int nb_cap[kSlots] = {0, 0};
 	SlotResolve *d_slot[kSlots] = {nullptr, nullptr}, *h_slot[kSlots] = {nullptr, nullptr};
-	CandRec *d_acc[kSlots] = {nullptr, nullptr};  // accepted candidates of the job, in order
+	FrameRec *d_acc[kSlots] = {nullptr, nullptr};  // accepted frames of the job, in order, stamped
 	ResolveState *d_state = nullptr;
 	int last_slot = 0;
 	FusedSpan *d_fspans[kSlots] = {nullptr, nullptr};
@@ -215,13 +216,15 @@ int alloc_slot_outputs(adsbdec_b200 *h, int s, unsigned long long cand_cap, unsi
 		if (h->d_acc[s]) cudaFree(h->d_acc[s]);
 		if (h->rb[s].sorted) cudaFree(h->rb[s].sorted);
 		if (h->rb[s].accept) cudaFree(h->rb[s].accept);
-		h->d_cands[s] = h->h_cands[s] = h->d_acc[s] = h->rb[s].sorted = nullptr;
+		h->d_cands[s] = h->rb[s].sorted = nullptr;
+		h->h_cands[s] = nullptr;
+		h->d_acc[s] = nullptr;
 		h->rb[s].accept = nullptr;
 		CU(cudaMalloc(&h->d_cands[s], cand_cap * sizeof(CandRec)));
-		CU(cudaMalloc(&h->d_acc[s], cand_cap * sizeof(CandRec)));
+		CU(cudaMalloc(&h->d_acc[s], cand_cap * sizeof(FrameRec)));
 		CU(cudaMalloc(&h->rb[s].sorted, cand_cap * sizeof(CandRec)));
 		CU(cudaMalloc(&h->rb[s].accept, cand_cap));
-		CU(cudaMallocHost(&h->h_cands[s], cand_cap * sizeof(CandRec)));  // accepted / sorted candidates land here
+		CU(cudaMallocHost(&h->h_cands[s], cand_cap * sizeof(FrameRec)));  // accepted frames / sorted candidates land here
 		h->cand_cap[s] = cand_cap;
 	}
 	if (try_cap != h->try_cap[s]) {
@@ -239,7 +242,7 @@ int ensure_buckets(adsbdec_b200 *h, int s, int nb)
 		return 0;
 	CU(cudaStreamSynchronize(h->st));
 	ResolveBuffers &rb = h->rb[s];
-	unsigned int **arr[5] = {&rb.cnt, &rb.cur, &rb.off, &rb.bacc, &rb.bacc_x};
+	unsigned int **arr[7] = {&rb.cnt, &rb.cur, &rb.off, &rb.bacc, &rb.bacc_x, &rb.bdrift, &rb.bdrift_x};
 	const int cap = nb + 1 + 4096;
 	for (unsigned int **a : arr) {
 		if (*a) cudaFree(*a);
@@ -411,7 +414,8 @@ int enqueue_job(adsbdec_b200 *h, int s, bool force_generic)
 	// order the candidates on the GPU; for a stream job also apply the greedy skip there, so that
 	// only accepted frames come back
 	RC(ensure_buckets(h, s, resolve_bucket_count(j.n0, j.n1)));
-	const CandRec *result;
+	const void *result;
+	const size_t rec = j.resolve ? sizeof(FrameRec) : sizeof(CandRec);
 	if (j.resolve) {
 		CU(launch_resolve(h->rb[s], h->d_cands[s], h->d_ctr[s], h->cand_cap[s], j.n0, j.n1, h->d_state, h->d_slot[s],
 		                  h->d_acc[s], h->cand_cap[s], h->st));
@@ -426,8 +430,8 @@ int enqueue_job(adsbdec_b200 *h, int s, bool force_generic)
 	CU(cudaMemcpyAsync(h->h_ctr[s], h->d_ctr[s], sizeof(Counters), cudaMemcpyDeviceToHost, h->st));
 	if (j.resolve)
 		CU(cudaMemcpyAsync(h->h_slot[s], h->d_slot[s], sizeof(SlotResolve), cudaMemcpyDeviceToHost, h->st));
-	CU(cudaMemcpyAsync(h->h_cands[s], result, std::min(kSpecCands, h->cand_cap[s]) * sizeof(CandRec),
-	                   cudaMemcpyDeviceToHost, h->st));
+	CU(cudaMemcpyAsync(h->h_cands[s], result, std::min(kSpecCands, h->cand_cap[s]) * rec, cudaMemcpyDeviceToHost,
+	                   h->st));
 	CU(cudaEventRecord(h->ev_done[s], h->st));
 	return 0;
 }
@@ -504,7 +508,8 @@ int complete_job(adsbdec_b200 *h, int s)
 			// this job and the (newer) one in the other slot.
 			CU(cudaStreamSynchronize(h->st));
 			if (j.resolve)
-				CU(launch_set_state(h->d_state, h->h_slot[s]->span0_start, h->h_slot[s]->span0_end, h->st));
+				CU(launch_set_state(h->d_state, h->h_slot[s]->span0_start, h->h_slot[s]->span0_end,
+				                    h->h_slot[s]->drift0, h->st));
 			if (c.overflow & 3u)
 				RC(alloc_slot_outputs(h, s, (c.overflow & 1u) ? h->cand_cap[s] * 4 : h->cand_cap[s],
 				                      (c.overflow & 2u) ? h->try_cap[s] * 4 : h->try_cap[s]));
@@ -516,8 +521,10 @@ int complete_job(adsbdec_b200 *h, int s)
 		h->tel.tries += h->cfg.collect_stats ? h->h_ctr[s]->n_try : 0;
 		n_res = j.resolve ? (size_t)h->h_slot[s]->n_accept : (size_t)std::min<unsigned long long>(h->h_ctr[s]->n_cand, h->cand_cap[s]);
 		if (n_res > kSpecCands) {
-			const CandRec *src = j.resolve ? h->d_acc[s] : h->rb[s].sorted;
-			CU(cudaMemcpyAsync(h->h_cands[s] + kSpecCands, src + kSpecCands, (n_res - kSpecCands) * sizeof(CandRec),
+			const size_t rec = j.resolve ? sizeof(FrameRec) : sizeof(CandRec);
+			const unsigned char *src = j.resolve ? reinterpret_cast<const unsigned char *>(h->d_acc[s])
+			                                     : reinterpret_cast<const unsigned char *>(h->rb[s].sorted);
+			CU(cudaMemcpyAsync(h->h_cands[s] + kSpecCands * rec, src + kSpecCands * rec, (n_res - kSpecCands) * rec,
 			                   cudaMemcpyDeviceToHost, h->st));
 			CU(cudaStreamSynchronize(h->st));
 		}
@@ -526,15 +533,17 @@ int complete_job(adsbdec_b200 *h, int s)
 	}
 	j.active = false;
 	static_assert(sizeof(CandRec) == sizeof(adsbdec_b200_candidate_t), "record layouts must agree");
-	const adsbdec_b200_candidate_t *res = reinterpret_cast<const adsbdec_b200_candidate_t *>(h->h_cands[s]);
+	static_assert(sizeof(FrameRec) == sizeof(adsbdec_b200_frame_t), "record layouts must agree");
 	if (!j.resolve) {
+		const adsbdec_b200_candidate_t *res = reinterpret_cast<const adsbdec_b200_candidate_t *>(h->h_cands[s]);
 		h->cand_tmp.assign(res, res + n_res);  // chunk mode: sorted candidates for the caller
 		return 0;
 	}
-	// The greedy skip has been applied on the GPU; the resolver adds the timestamps (demod.c:99) and
-	// the deqframe call schedule (air.c:94-99) over the accepted frames only.
+	// The greedy skip and the timestamps (demod.c:99, :128, :134) have been applied on the GPU; what
+	// is left is the deqframe call schedule (air.c:94-99), which decides how far the scan has come.
 	const double t2 = now_ms();
-	h->res->feed(res, n_res, (uint64_t)std::max<int64_t>(j.n1, 0), (uint64_t)j.total_out, h->frames);
+	h->res->feed_frames(reinterpret_cast<const adsbdec_b200_frame_t *>(h->h_cands[s]), n_res,
+	                    (uint64_t)std::max<int64_t>(j.n1, 0), (uint64_t)j.total_out, h->frames);
 	const double t3 = now_ms();
 	if (scanned) {
 		RC(stats_pass(h, s, true));
@@ -792,6 +801,8 @@ void adsbdec_b200_close(adsbdec_b200_t *h)
 		if (h->rb[s].off) cudaFree(h->rb[s].off);
 		if (h->rb[s].bacc) cudaFree(h->rb[s].bacc);
 		if (h->rb[s].bacc_x) cudaFree(h->rb[s].bacc_x);
+		if (h->rb[s].bdrift) cudaFree(h->rb[s].bdrift);
+		if (h->rb[s].bdrift_x) cudaFree(h->rb[s].bdrift_x);
 		if (h->d_slot[s]) cudaFree(h->d_slot[s]);
 		if (h->h_slot[s]) cudaFreeHost(h->h_slot[s]);
 		if (h->d_fspans[s]) cudaFree(h->d_fspans[s]);

@@ -25,6 +25,17 @@ struct alignas(16) CandRec {
 	uint8_t bytes[16]; // first len bytes
 };
 static_assert(sizeof(CandRec) == 32, "CandRec layout");
+
+// One accepted frame as the host API hands it out: same layout as adsbdec_b200_frame_t.
+struct FrameRec {
+	uint64_t ts;       // demod.c:99 iteration counter
+	uint64_t n;
+	uint32_t pw;
+	int32_t len;
+	uint8_t bytes[14];
+	uint8_t pad_[2];
+};
+static_assert(sizeof(FrameRec) == 40, "FrameRec must match adsbdec_b200_frame_t");
 // Flag in CandRec::len: `bytes` holds four 28-bit words (frame bits 28k..28k+27, MSB first in bits
 // 27..0 of word k) instead of the frame bytes; the host repacks them.
 constexpr uint32_t kCandNibbleWords = 0x100u;

@@ -25,6 +25,7 @@ cudaError_t launch_scan_generic(const float *amp, long long j_amp0, long long n0
 struct ResolveState {        // per stream: where the sequential scan stands (demod.c:128, :134)
 	unsigned long long carry_start;  // start of the last accepted frame
 	unsigned long long carry_pos;    // first offset behind it
+	unsigned long long drift;        // iterations saved by skips so far: sum(skip - 1) (demod.c:99)
 };
 
 struct SlotResolve {         // per job, copied back to the host
@@ -32,24 +33,26 @@ struct SlotResolve {         // per job, copied back to the host
 	unsigned long long n_accept;     // of which accepted
 	unsigned long long span0_start;  // scan position before this job (for the statistics pass and redo)
 	unsigned long long span0_end;
+	unsigned long long drift0;       // ResolveState::drift before this job
 };
 
 struct ResolveBuffers {      // per job slot scratch
 	CandRec *sorted;         // cand_cap entries
 	unsigned char *accept;   // cand_cap entries
 	unsigned int *cnt, *cur, *off, *bacc, *bacc_x;  // bucket arrays, nb_cap + 1 entries each
+	unsigned int *bdrift, *bdrift_x;                // sum(skip - 1) of the accepted frames per bucket / scanned
 };
 
 int resolve_bucket_count(long long n0, long long n1);
 cudaError_t launch_sort(const ResolveBuffers &rb, const CandRec *cands, const Counters *ctr, unsigned long long cap,
                         long long n0, long long n1, cudaStream_t st);
 cudaError_t launch_resolve(const ResolveBuffers &rb, const CandRec *cands, const Counters *ctr, unsigned long long cap,
-                           long long n0, long long n1, ResolveState *state, SlotResolve *slot, CandRec *out,
+                           long long n0, long long n1, ResolveState *state, SlotResolve *slot, FrameRec *out,
                            unsigned long long out_cap, cudaStream_t st);
 cudaError_t launch_set_state(ResolveState *state, unsigned long long carry_start, unsigned long long carry_pos,
-                             cudaStream_t st);
+                             unsigned long long drift, cudaStream_t st);
 cudaError_t launch_count_tries_frames(const unsigned long long *tries, const unsigned long long *n_tries_ptr,
-                                      unsigned long long cap, const CandRec *frames, const SlotResolve *slot,
+                                      unsigned long long cap, const FrameRec *frames, const SlotResolve *slot,
                                       unsigned long long frames_cap, const ResolveBuffers &rb, long long n0,
                                       long long n1, unsigned long long scan_end, unsigned long long *pend_out,
                                       unsigned long long *n_pend_out, unsigned long long pend_cap, StreamStats *stt,

@@ -98,6 +98,66 @@ __global__ void k_scan_buckets(const unsigned int *__restrict__ in, unsigned int
 		out[nb] = carry_s;
 }
 
+// The same scan over two arrays at once (accepted frames and their timestamp drift per bucket),
+// packed into one 64-bit value per entry: both totals stay below 2^32 (a job holds < 2^28 offsets).
+__global__ void k_scan_buckets2(const unsigned int *__restrict__ in_a, const unsigned int *__restrict__ in_b,
+                                unsigned int *__restrict__ out_a, unsigned int *__restrict__ out_b, int nb)
+{
+	__shared__ unsigned long long warp_sum[kScanThreads / 32];
+	__shared__ unsigned long long carry_s;
+	const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+	if (t == 0)
+		carry_s = 0;
+	__syncthreads();
+	for (int base = 0; base < nb; base += 4 * kScanThreads) {
+		const int i0 = base + 4 * t;
+		unsigned long long v[4];
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+			v[k] = i0 + k < nb ? ((unsigned long long)in_b[i0 + k] << 32) | in_a[i0 + k] : 0ull;
+		const unsigned long long mine = v[0] + v[1] + v[2] + v[3];
+		unsigned long long x = mine;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+			if (lane >= d)
+				x += y;
+		}
+		if (lane == 31)
+			warp_sum[w] = x;
+		__syncthreads();
+		if (w == 0) {
+			unsigned long long s = warp_sum[lane];
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, s, d);
+				if (lane >= d)
+					s += y;
+			}
+			warp_sum[lane] = s;
+		}
+		__syncthreads();
+		const unsigned long long carry = carry_s;
+		unsigned long long pre = carry + (w ? warp_sum[w - 1] : 0ull) + (x - mine);
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			if (i0 + k < nb) {
+				out_a[i0 + k] = (unsigned int)pre;
+				out_b[i0 + k] = (unsigned int)(pre >> 32);
+			}
+			pre += v[k];
+		}
+		__syncthreads();
+		if (t == kScanThreads - 1)
+			carry_s = carry + warp_sum[31];
+		__syncthreads();
+	}
+	if (t == 0) {
+		out_a[nb] = (unsigned int)carry_s;
+		out_b[nb] = (unsigned int)(carry_s >> 32);
+	}
+}
+
 __device__ __forceinline__ void repack(CandRec &o, const CandRec &c)
 {
 	o = c;
@@ -170,6 +230,7 @@ __global__ void k_snapshot(const ResolveState *st, SlotResolve *slot)
 {
 	slot->span0_start = st->carry_start;
 	slot->span0_end = st->carry_pos;
+	slot->drift0 = st->drift;
 }
 
 // Greedy acceptance.  Thread i walks the segment that starts at candidate i (if one does).
@@ -207,34 +268,62 @@ __global__ void k_greedy(const CandRec *__restrict__ sorted, const unsigned int 
 	}
 }
 
-__global__ void k_bucket_stats(const unsigned char *__restrict__ accept, const unsigned int *__restrict__ off, int nb,
-                               unsigned int *bacc)
+__global__ void k_bucket_stats(const CandRec *__restrict__ sorted, const unsigned char *__restrict__ accept,
+                               const unsigned int *__restrict__ off, int nb, unsigned int *bacc, unsigned int *bdrift)
 {
 	for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
-		unsigned int a = 0;
+		unsigned int a = 0, d = 0;
 		for (unsigned int i = off[b]; i < off[b + 1]; i++)
-			a += accept[i];
+			if (accept[i]) {
+				a++;
+				d += (unsigned int)skip_of(sorted[i].len) - 1u;
+			}
 		bacc[b] = a;
+		bdrift[b] = d;
 	}
 }
 
-// Writes the accepted candidates, in offset order.
+// Writes the accepted frames, in offset order, as the API hands them out.  ts counts the loop
+// iterations of deqframe (demod.c:86, :99): every accepted frame before this one saved skip-1 of them.
 __global__ void k_compact(const CandRec *__restrict__ sorted, const unsigned char *__restrict__ accept,
                           const unsigned int *__restrict__ off, int nb, const unsigned int *__restrict__ bacc_x,
-                          CandRec *__restrict__ out, unsigned long long out_cap, SlotResolve *slot)
+                          const unsigned int *__restrict__ bdrift_x, FrameRec *__restrict__ out,
+                          unsigned long long out_cap, ResolveState *st, SlotResolve *slot)
 {
+	const unsigned long long drift0 = slot->drift0;
 	for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
 		unsigned long long p = bacc_x[b];
+		unsigned long long drift = drift0 + bdrift_x[b];
 		for (unsigned int i = off[b]; i < off[b + 1]; i++)
 			if (accept[i]) {
-				if (p < out_cap)
-					out[p] = sorted[i];
+				const CandRec c = sorted[i];
+				if (p < out_cap) {
+					// 40 bytes as five 8-byte words
+					unsigned long long w[5];
+					w[0] = c.n + 1ull - drift;
+					w[1] = c.n;
+					w[2] = (unsigned long long)c.pw | ((unsigned long long)c.len << 32);
+					memcpy(&w[3], c.bytes, 8);
+					unsigned long long t = 0;
+					memcpy(&t, c.bytes + 8, 6);
+					if (c.len == 7) {  // a short frame leaves bytes 7..13 zero
+						w[3] &= 0x00FFFFFFFFFFFFFFull;
+						t = 0;
+					}
+					w[4] = t;
+					unsigned long long *o = reinterpret_cast<unsigned long long *>(&out[p]);
+#pragma unroll
+					for (int k = 0; k < 5; k++)
+						o[k] = w[k];
+				}
+				drift += skip_of(c.len) - 1ull;
 				p++;
 			}
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) {
 		slot->n_sorted = off[nb];
 		slot->n_accept = bacc_x[nb];
+		st->drift = drift0 + bdrift_x[nb];  // read by the next job's snapshot only
 	}
 }
 
@@ -243,7 +332,7 @@ __global__ void k_compact(const CandRec *__restrict__ sorted, const unsigned cha
 // where the frames near a try sit, so no search is needed.
 __global__ void k_count_tries_frames(const unsigned long long *__restrict__ tries,
                                      const unsigned long long *__restrict__ n_tries_ptr, unsigned long long cap,
-                                     const CandRec *__restrict__ frames, const SlotResolve *slot,
+                                     const FrameRec *__restrict__ frames, const SlotResolve *slot,
                                      unsigned long long frames_cap, const unsigned int *__restrict__ bacc_x,
                                      long long n0, int nb, unsigned long long scan_end,
                                      unsigned long long *pend_out, unsigned long long *n_pend_out,
@@ -274,7 +363,7 @@ __global__ void k_count_tries_frames(const unsigned long long *__restrict__ trie
 				const unsigned long long fs = frames[q].n;
 				if (fs >= n)
 					break;
-				if (n < fs + skip_of(frames[q].len))
+				if (n < fs + skip_of((uint32_t)frames[q].len))
 					inside = true;
 			}
 		}
@@ -324,7 +413,7 @@ cudaError_t launch_sort(const ResolveBuffers &rb, const CandRec *cands, const Co
 
 // Sort + greedy + compaction: `out` receives the accepted candidates in order, slot->n_accept their number.
 cudaError_t launch_resolve(const ResolveBuffers &rb, const CandRec *cands, const Counters *ctr, unsigned long long cap,
-                           long long n0, long long n1, ResolveState *state, SlotResolve *slot, CandRec *out,
+                           long long n0, long long n1, ResolveState *state, SlotResolve *slot, FrameRec *out,
                            unsigned long long out_cap, cudaStream_t st)
 {
 	const int nb = resolve_bucket_count(n0, n1);
@@ -332,27 +421,30 @@ cudaError_t launch_resolve(const ResolveBuffers &rb, const CandRec *cands, const
 	if (e != cudaSuccess) return e;
 	k_snapshot<<<1, 1, 0, st>>>(state, slot);
 	k_greedy<<<296, 256, 0, st>>>(rb.sorted, rb.off, nb, rb.accept, state, slot);
-	k_bucket_stats<<<(nb + 127) / 128, 128, 0, st>>>(rb.accept, rb.off, nb, rb.bacc);
-	k_scan_buckets<<<1, kScanThreads, 0, st>>>(rb.bacc, rb.bacc_x, nb);
-	k_compact<<<(nb + 127) / 128, 128, 0, st>>>(rb.sorted, rb.accept, rb.off, nb, rb.bacc_x, out, out_cap, slot);
+	k_bucket_stats<<<(nb + 127) / 128, 128, 0, st>>>(rb.sorted, rb.accept, rb.off, nb, rb.bacc, rb.bdrift);
+	k_scan_buckets2<<<1, kScanThreads, 0, st>>>(rb.bacc, rb.bdrift, rb.bacc_x, rb.bdrift_x, nb);
+	k_compact<<<(nb + 127) / 128, 128, 0, st>>>(rb.sorted, rb.accept, rb.off, nb, rb.bacc_x, rb.bdrift_x, out, out_cap,
+	                                             state, slot);
 	return cudaGetLastError();
 }
 
-__global__ void k_set_state(ResolveState *st, unsigned long long carry_start, unsigned long long carry_pos)
+__global__ void k_set_state(ResolveState *st, unsigned long long carry_start, unsigned long long carry_pos,
+                            unsigned long long drift)
 {
 	st->carry_start = carry_start;
 	st->carry_pos = carry_pos;
+	st->drift = drift;
 }
 
 cudaError_t launch_set_state(ResolveState *state, unsigned long long carry_start, unsigned long long carry_pos,
-                             cudaStream_t st)
+                             unsigned long long drift, cudaStream_t st)
 {
-	k_set_state<<<1, 1, 0, st>>>(state, carry_start, carry_pos);
+	k_set_state<<<1, 1, 0, st>>>(state, carry_start, carry_pos, drift);
 	return cudaGetLastError();
 }
 
 cudaError_t launch_count_tries_frames(const unsigned long long *tries, const unsigned long long *n_tries_ptr,
-                                      unsigned long long cap, const CandRec *frames, const SlotResolve *slot,
+                                      unsigned long long cap, const FrameRec *frames, const SlotResolve *slot,
                                       unsigned long long frames_cap, const ResolveBuffers &rb, long long n0,
                                       long long n1, unsigned long long scan_end, unsigned long long *pend_out,
                                       unsigned long long *n_pend_out, unsigned long long pend_cap, StreamStats *stt,

@@ -15,6 +15,20 @@ void Resolver::scan_to(uint64_t cutoff, std::vector<adsbdec_b200_frame_t> &accep
 	// offsets (demod.c:89).  idx starts at ampbuff[0] = base_.  Candidates come from the few left
 	// over from earlier feeds (pending_) and then, in place, from the array being fed.
 	uint64_t pos = base_;
+	// stamped frames: everything below the cutoff is accepted as it is
+	for (int src = 0; src < 2; src++) {
+		const adsbdec_b200_frame_t *f = src == 0 ? fpending_.data() : fin_;
+		size_t &i = src == 0 ? fhead_ : fin_i_;
+		const size_t n = src == 0 ? fpending_.size() : fin_n_, i0 = i;
+		while (i < n && f[i].n < cutoff)
+			i++;
+		if (i > i0) {
+			accepted.insert(accepted.end(), f + i0, f + i);
+			pos = f[i - 1].n + (f[i - 1].len == 7 ? kSkipShort : kSkipLong);
+		}
+		if (i < n)
+			break;  // the pending frames come before the fed ones
+	}
 	for (;;) {
 		const adsbdec_b200_candidate_t *c;
 		if (head_ < pending_.size())
@@ -88,6 +102,28 @@ void Resolver::feed(const adsbdec_b200_candidate_t *c, size_t count, uint64_t sc
 	in_n_ = in_i_ = 0;
 }
 
+void Resolver::feed_frames(const adsbdec_b200_frame_t *f, size_t count, uint64_t scanned_upto,
+                           uint64_t total_out, std::vector<adsbdec_b200_frame_t> &accepted)
+{
+	if (fhead_ == fpending_.size()) {
+		fpending_.clear();
+		fhead_ = 0;
+	}
+	fin_ = f;
+	fin_n_ = count;
+	fin_i_ = 0;
+	scanned_upto_ = std::max(scanned_upto_, scanned_upto);
+	total_out_ = std::max(total_out_, total_out);
+	run_calls(accepted);
+	if (fhead_ == fpending_.size()) {
+		fpending_.clear();
+		fhead_ = 0;
+	}
+	fpending_.insert(fpending_.end(), f + fin_i_, f + count);
+	fin_ = nullptr;
+	fin_n_ = fin_i_ = 0;
+}
+
 void Resolver::finish(std::vector<adsbdec_b200_frame_t> &accepted)
 {
 	run_calls(accepted);
@@ -101,6 +137,8 @@ void Resolver::finish(std::vector<adsbdec_b200_frame_t> &accepted)
 	}
 	pending_.clear();
 	head_ = 0;  // the reference drops whatever is left in ampbuff at EOF (air.c:243-244)
+	fpending_.clear();
+	fhead_ = 0;
 }
 
 }  // namespace adsb

@@ -7,7 +7,8 @@
 //   * the buffer schedule: deqframe runs whenever >= 40980 envelope samples are queued and
 //     leaves the last 1200 unscanned (air.c:94-99, demod.c:89), so the tail of a capture is
 //     never decoded.
-// All three are O(accepted frames) and are done here on the host.
+// All three are O(accepted frames).  The stream path does the first two on the GPU as well and
+// feeds stamped frames (feed_frames); the chunk path feeds raw candidates (feed).
 #pragma once
 #include <stdint.h>
 
@@ -24,6 +25,10 @@ public:
 	// Candidates in non-decreasing n, complete for all n < scanned_upto.
 	void feed(const adsbdec_b200_candidate_t *c, size_t count, uint64_t scanned_upto, uint64_t total_out,
 	          std::vector<adsbdec_b200_frame_t> &accepted);
+	// The same for frames the GPU has already put through the greedy rule and stamped (kernels_resolve.cu):
+	// only the deqframe call schedule is left, which decides how far the scan has come.
+	void feed_frames(const adsbdec_b200_frame_t *f, size_t count, uint64_t scanned_upto, uint64_t total_out,
+	                 std::vector<adsbdec_b200_frame_t> &accepted);
 	void finish(std::vector<adsbdec_b200_frame_t> &accepted);
 
 	// Offsets below this have been visited (or skipped) by the emulated scan.
@@ -45,6 +50,10 @@ private:
 	size_t head_ = 0;
 	const adsbdec_b200_candidate_t *in_ = nullptr;  // array being fed, consumed in place
 	size_t in_n_ = 0, in_i_ = 0;
+	std::vector<adsbdec_b200_frame_t> fpending_;    // stamped frames the call schedule has not reached
+	size_t fhead_ = 0;
+	const adsbdec_b200_frame_t *fin_ = nullptr;
+	size_t fin_n_ = 0, fin_i_ = 0;
 };
 
 }  // namespace adsb

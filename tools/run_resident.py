@@ -12,9 +12,15 @@ dev = torch.device("cuda", 0)
 cap, injected, _ = build_device_capture(torch, dev, seconds, 1234)
 torch.cuda.synchronize()
 dec = A.Decoder(accept_df18=True)
+import time
 for i in range(steps):
     dec.reset()
+    dec.host_time(reset=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
     dec.push_device(cap.data_ptr(), cap.numel())
     dec.finish()
+    wall = (time.perf_counter() - t0) * 1e3
+    print(f"   wall {wall:.3f} ms, kernels {dec.kernel_time(reset=True)[0]:.3f} ms, host {dec.host_time()}")
     ms, n, s = dec.fused_time(reset=True)
     print(f"step {i}: frames {dec.num_frames}, fused {ms:.3f} ms / {n} launches, {2*s/ms/1e6 if ms else 0:.1f} GB/s")
