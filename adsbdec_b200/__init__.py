@@ -170,7 +170,7 @@ class Decoder:
 
     def __init__(self, *, device: int = 0, accept_df18: bool = False, emulate_reference_tail: bool = True,
                  collect_stats: bool = True, kernel: int = 0, batch_samples: int = 0, start_sample: int = 0,
-                 sink=None, initial_caps: tuple[int, int] = (0, 0), reader_threads: int = 0):
+                 sink=None, initial_caps: tuple[int, int] = (0, 0), reader_threads: int = 0, repair: int = 0):
         L = lib()
         cfg = Config()
         L.adsbdec_b200_default_config(C.byref(cfg))
@@ -183,6 +183,7 @@ class Decoder:
         cfg.start_sample = start_sample
         cfg.reserved[0], cfg.reserved[1] = initial_caps
         cfg.reserved[2] = reader_threads  # decode_file: 0 = up to 12, 1 = the calling thread only
+        cfg.reserved[3] = repair          # EXTENSION (not in the reference): 1 = fix one bit, 2 = two bits
         self._h = C.c_void_p()
         self._cb = None
         _check(L.adsbdec_b200_open(C.byref(cfg), C.byref(self._h)))

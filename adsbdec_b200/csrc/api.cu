@@ -31,6 +31,7 @@
 #include "common.h"
 #include "kernels.h"
 #include "readpool.h"
+#include "repair.h"
 #include "resolver.h"
 
 using namespace adsb;
@@ -199,6 +200,8 @@ struct adsbdec_b200 {
 	std::vector<adsbdec_b200_candidate_t> cand_tmp;
 	adsbdec_b200_telemetry_t tel = {};
 	std::unique_ptr<ReadPool> readers;  // decode_file helpers, started on first use
+	unsigned long long *d_fix = nullptr;  // repair.h syndrome table (extension; null when off)
+	int fix_level = 0;
 
 	// parity taps of the fused kernel (adsbdec_b200_debug_fused)
 	float *dbg_amp = nullptr;
@@ -274,7 +277,7 @@ int launch_generic(adsbdec_b200 *h, int s, const Job &j, int64_t n0, int64_t n1)
 		const int64_t cnt = std::min(kAmpChunk, n1 - c0);
 		CU(launch_envelope_generic(j.buf, j.u0, j.origin, c0, cnt + kLookahead, h->d_amp, h->st));
 		CU(launch_scan_generic(h->d_amp, c0, c0, cnt, h->cfg.accept_df18, h->cfg.collect_stats, h->d_cands[s],
-		                       h->cand_cap[s], h->d_tries[s], h->try_cap[s], h->d_ctr[s], h->st));
+		                       h->cand_cap[s], h->d_tries[s], h->try_cap[s], h->d_ctr[s], h->d_fix, h->fix_level, h->st));
 		h->launches += 2;
 	}
 	return 0;
@@ -355,6 +358,8 @@ int launch_fused_range(adsbdec_b200 *h, int s, const Job &j, int64_t n0, int64_t
 	p.try_cap = h->try_cap[s];
 	p.ctr = h->d_ctr[s];
 	p.span_ticket = h->d_ticket[s];
+	p.fix_tab = h->d_fix;
+	p.fix_level = h->fix_level;
 	p.dbg_amp = h->dbg_amp;
 	p.dbg_p = h->dbg_p;
 	p.dbg_q = h->dbg_q;
@@ -764,6 +769,22 @@ int adsbdec_b200_open(const adsbdec_b200_config_t *cfg, adsbdec_b200_t **out)
 			}
 			h->fused_ctas = per_sm * prop.multiProcessorCount;
 		}
+		// reserved[3]: opt-in error repair (repair.h) - 0 = the reference's behaviour
+		if (cfg->reserved[3] > 2) {
+			rc = fail(ADSB_B200_EINVAL, "repair level must be 0, 1 or 2");
+			break;
+		}
+		h->fix_level = (int)cfg->reserved[3];
+		if (h->fix_level > 0) {
+			std::vector<unsigned long long> tab(kFixSlots);
+			fix_build_table(tab.data());
+			if (cudaMalloc(&h->d_fix, kFixSlots * sizeof(unsigned long long)) != cudaSuccess ||
+			    cudaMemcpy(h->d_fix, tab.data(), kFixSlots * sizeof(unsigned long long), cudaMemcpyHostToDevice) !=
+			        cudaSuccess) {
+				rc = fail(ADSB_B200_ECUDA, "repair table: %s", cudaGetErrorString(cudaGetLastError()));
+				break;
+			}
+		}
 	} while (0);
 	if (rc) {
 		adsbdec_b200_close(h);
@@ -813,6 +834,7 @@ void adsbdec_b200_close(adsbdec_b200_t *h)
 		if (h->ev_fb[s]) cudaEventDestroy(h->ev_fb[s]);
 		if (h->ev_done[s]) cudaEventDestroy(h->ev_done[s]);
 	}
+	if (h->d_fix) cudaFree(h->d_fix);
 	if (h->d_stats) cudaFree(h->d_stats);
 	if (h->d_state) cudaFree(h->d_state);
 	if (h->h_stats) cudaFreeHost(h->h_stats);

@@ -9,7 +9,8 @@
 // block on stderr at exit (valid.c:84-101); a file that cannot be opened prints stats and exits 0
 // (air.c:225-228).  Deliberately NOT kept: stdout beast output truncated by strlen() (output.c:331
 // - we write the full packet) and the frames the reference loses in its EOF race (output.c:287).
-// Extra: -D n selects the CUDA device, -G forces the generic kernels.
+// Extra: -D n selects the CUDA device, -G forces the generic kernels, -R 1|2 switches on the error
+// repair extension (repair.h; the reference has none, so the default output is the reference's).
 #include <arpa/inet.h>
 #include <netdb.h>
 #include <signal.h>
@@ -40,6 +41,7 @@ void usage()
 	printf("\t-f : input file (airspy raw real samples, 16 bits, 20 MS/s)\n");
 	printf("\t-s addr[:port] : send output via TCP to server at address addr:port (default port : 30001)\n");
 	printf("\t-D n : CUDA device ordinal\n");
+	printf("\t-R 1|2 : extension, not in adsbdec : repair 1 (2) flipped bits by CRC syndrome\n");
 }
 
 int connect_to(const char *spec)
@@ -123,7 +125,7 @@ int main(int argc, char **argv)
 	adsbdec_b200_config_t cfg;
 	adsbdec_b200_default_config(&cfg);
 	int c;
-	while ((c = getopt(argc, argv, "cf:s:l:g:aembD:G")) != EOF) {
+	while ((c = getopt(argc, argv, "cf:s:l:g:aembD:GR:")) != EOF) {
 		switch (c) {
 		case 'f': filename = optarg; break;
 		case 's': addr = optarg; break;
@@ -133,6 +135,7 @@ int main(int argc, char **argv)
 		case 'b': g_format = 2; break;
 		case 'D': cfg.device = atoi(optarg); break;
 		case 'G': cfg.kernel = 1; break;
+		case 'R': cfg.reserved[3] = (uint64_t)atoi(optarg); break;
 		default:  // -c, -e, -l (no listener here) and anything unknown
 			usage();
 			return 1;

@@ -40,6 +40,7 @@
 
 #include "common.h"
 #include "kernels.h"
+#include "repair.h"
 
 namespace adsb {
 
@@ -149,7 +150,9 @@ constexpr float kMagicMid = 8388608.0f + 2048.0f;
 
 }  // namespace
 
-template <bool DEBUG>
+// REPAIR: the opt-in syndrome repair of repair.h (a separate instantiation: the reference-parity
+// kernel carries none of it).
+template <bool DEBUG, bool REPAIR>
 __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -494,7 +497,15 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 					// valid.c:48-52 / :70-74: CRC over all but the last 3 bytes, XOR the last 3, == 0
 					acc ^= __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
 					acc ^= __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
-					const bool ok = have && acc == 0;
+					bool ok = have && acc == 0;
+					uint32_t fix = 0xFFFFu;  // (first << 8) | second flipped bit, 0xFF = none (repair.h)
+					if (REPAIR && have && acc != 0) {
+						const uint32_t e = fix_lookup(p.fix_tab, acc);
+						if (e != kFixNone && fix_allowed(e, is_long, p.fix_level)) {
+							ok = true;
+							fix = e;
+						}
+					}
 					if (__any_sync(0xFFFFFFFFu, ok)) {
 						unsigned long long slot = 0;
 						if (ok && sub == 0)
@@ -509,7 +520,18 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 									*reinterpret_cast<uint4 *>(out) = make_uint4(
 									    (uint32_t)n, (uint32_t)(n >> 32), 0u, (is_long ? 14u : 7u) | kCandNibbleWords);
 								}
-								out[4 + sub] = bits28;
+								uint32_t word = bits28;
+								if (REPAIR && fix != 0xFFFFu) {
+									const uint32_t base = is_long ? 0u : 56u;
+									const uint32_t b1 = (fix >> 8) - base, b2 = (fix & 0xFFu) - base;
+									if (b1 / 28u == (uint32_t)sub)
+										word ^= 0x08000000u >> (b1 % 28u);
+									if ((fix & 0xFFu) != 0xFFu && b2 / 28u == (uint32_t)sub)
+										word ^= 0x08000000u >> (b2 % 28u);
+									if (sub == 0)  // bits 28, 29 of word 0: how many bits were repaired
+										word |= ((fix & 0xFFu) != 0xFFu ? 2u : 1u) << 28;
+								}
+								out[4 + sub] = word;
 							} else if (sub == 0) {
 								atomicOr(&p.ctr->overflow, 1u);
 							}
@@ -552,13 +574,15 @@ int fused_prepare(int device)
 	}
 	if (cudaMemcpyToSymbol(g_lut, lut, sizeof lut) != cudaSuccess)
 		return -1;
-	if (cudaFuncSetAttribute(k_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	if (cudaFuncSetAttribute(k_fused<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                         (int)fused_smem_bytes()) != cudaSuccess ||
-	    cudaFuncSetAttribute(k_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    cudaFuncSetAttribute(k_fused<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                         (int)fused_smem_bytes()) != cudaSuccess ||
+	    cudaFuncSetAttribute(k_fused<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                         (int)fused_smem_bytes()) != cudaSuccess)
 		return -1;
 	int per_sm = 0;
-	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<false>, NT, fused_smem_bytes()) !=
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<false, false>, NT, fused_smem_bytes()) !=
 	    cudaSuccess)
 		return -1;
 	return per_sm * WPC;
@@ -571,9 +595,11 @@ cudaError_t launch_fused(const FusedParams &p, int workers, cudaStream_t st)
 		return cudaSuccess;
 	const int grid = (workers + WPC - 1) / WPC;
 	if (p.dbg_amp)
-		k_fused<true><<<grid, NT, fused_smem_bytes(), st>>>(p);
+		k_fused<true, false><<<grid, NT, fused_smem_bytes(), st>>>(p);
+	else if (p.fix_level > 0)
+		k_fused<false, true><<<grid, NT, fused_smem_bytes(), st>>>(p);
 	else
-		k_fused<false><<<grid, NT, fused_smem_bytes(), st>>>(p);
+		k_fused<false, false><<<grid, NT, fused_smem_bytes(), st>>>(p);
 	return cudaGetLastError();
 }
 

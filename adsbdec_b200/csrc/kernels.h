@@ -18,7 +18,8 @@ cudaError_t launch_fill_pw(const uint16_t *raw, long long u_raw0, unsigned long 
 cudaError_t launch_scan_generic(const float *amp, long long j_amp0, long long n0, long long count,
                                 int accept_df18, int want_tries, CandRec *cands,
                                 unsigned long long cand_cap, unsigned long long *tries,
-                                unsigned long long try_cap, Counters *ctr, cudaStream_t st);
+                                unsigned long long try_cap, Counters *ctr, const unsigned long long *fix_tab,
+                                int fix_level, cudaStream_t st);
 
 // ---- on-GPU ordering and greedy resolve (kernels_resolve.cu) ----------------
 
@@ -85,6 +86,8 @@ struct FusedParams {
 	unsigned long long try_cap;
 	Counters *ctr;
 	int *span_ticket;      // dynamic span scheduler (zeroed before launch)
+	const unsigned long long *fix_tab;  // repair.h table, null unless fix_level > 0 (extension, off by default)
+	int fix_level;
 	// parity taps (all null in production): envelope / bit arrays of span 0, indexed from its j_begin
 	float *dbg_amp;
 	unsigned int *dbg_p, *dbg_q, *dbg_b;

@@ -12,6 +12,7 @@
 // Reference citations are file:line into TLeconte/adsbdec.
 #include "common.h"
 #include "kernels.h"
+#include "repair.h"
 
 namespace adsb {
 
@@ -132,7 +133,8 @@ __device__ __forceinline__ bool ppm(const float *a, int at)
 __global__ void k_scan_generic(const float *__restrict__ amp, long long j_amp0, long long n0,
                                long long count, int accept_df18, int want_tries, CandRec *cands,
                                unsigned long long cand_cap, unsigned long long *tries,
-                               unsigned long long try_cap, Counters *ctr)
+                               unsigned long long try_cap, Counters *ctr, const unsigned long long *fix_tab,
+                               int fix_level)
 {
 	long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
 	if (i >= count)
@@ -187,8 +189,24 @@ __global__ void k_scan_generic(const float *__restrict__ amp, long long j_amp0, 
 	}
 	crc = (crc & 0xFFFFFFu) ^ ((uint32_t)msg[len - 3] << 16 | (uint32_t)msg[len - 2] << 8 |
 	                           (uint32_t)msg[len - 1]);  // crc.h:40-42
-	if (crc != 0)  // valid.c:52, :74
-		return;
+	uint32_t nfix = 0;
+	if (crc != 0) {  // valid.c:52, :74
+		if (fix_level <= 0)
+			return;
+		// extension (repair.h): the syndrome of one or two flipped bits
+		const uint32_t e = fix_lookup(fix_tab, crc);
+		if (e == kFixNone || !fix_allowed(e, len == 14, fix_level))
+			return;
+		const uint32_t base = len == 14 ? 0u : 56u;
+		const uint32_t b1 = (e >> 8) - base;
+		msg[b1 >> 3] ^= (uint8_t)(0x80u >> (b1 & 7u));
+		nfix = 1;
+		if ((e & 0xFFu) != 0xFFu) {
+			const uint32_t b2 = (e & 0xFFu) - base;
+			msg[b2 >> 3] ^= (uint8_t)(0x80u >> (b2 & 7u));
+			nfix = 2;
+		}
+	}
 	unsigned long long k = atomicAdd(&ctr->n_cand, 1ull);
 	if (k >= cand_cap) {
 		atomicOr(&ctr->overflow, 1u);
@@ -201,6 +219,7 @@ __global__ void k_scan_generic(const float *__restrict__ amp, long long j_amp0, 
 #pragma unroll
 	for (int b = 0; b < 16; b++)
 		r.bytes[b] = b < len ? msg[b] : 0;
+	r.bytes[15] = (uint8_t)nfix;  // bits repaired (0 unless the extension is on)
 	cands[k] = r;
 }
 
@@ -226,13 +245,14 @@ cudaError_t launch_fill_pw(const uint16_t *raw, long long u_raw0, unsigned long 
 cudaError_t launch_scan_generic(const float *amp, long long j_amp0, long long n0, long long count,
                                 int accept_df18, int want_tries, CandRec *cands,
                                 unsigned long long cand_cap, unsigned long long *tries,
-                                unsigned long long try_cap, Counters *ctr, cudaStream_t st)
+                                unsigned long long try_cap, Counters *ctr, const unsigned long long *fix_tab,
+                                int fix_level, cudaStream_t st)
 {
 	if (count <= 0)
 		return cudaSuccess;
 	const int bs = 256;
 	k_scan_generic<<<(unsigned)((count + bs - 1) / bs), bs, 0, st>>>(
-	    amp, j_amp0, n0, count, accept_df18, want_tries, cands, cand_cap, tries, try_cap, ctr);
+	    amp, j_amp0, n0, count, accept_df18, want_tries, cands, cand_cap, tries, try_cap, ctr, fix_tab, fix_level);
 	return cudaGetLastError();
 }
 

@@ -167,6 +167,10 @@ __device__ __forceinline__ void repack(CandRec &o, const CandRec &c)
 	o.len = c.len & ~kCandNibbleWords;
 	uint32_t w[4];
 	memcpy(w, c.bytes, 16);
+	const uint32_t nfix = w[0] >> 28;  // bits repaired (repair.h; 0 in reference mode)
+#pragma unroll
+	for (int k = 0; k < 4; k++)
+		w[k] &= 0x0FFFFFFFu;
 	unsigned long long hi, lo;  // 112-bit frame as hi:lo (hi holds the top 48 bits) / 56-bit frame in lo
 	int nbits;
 	if (o.len == 14) {
@@ -189,6 +193,7 @@ __device__ __forceinline__ void repack(CandRec &o, const CandRec &c)
 		}
 		o.bytes[k] = v;
 	}
+	o.bytes[15] = (uint8_t)nfix;
 }
 
 __global__ void k_scatter(const CandRec *__restrict__ c, const Counters *ctr, unsigned long long cap, long long n0,
@@ -310,7 +315,7 @@ __global__ void k_compact(const CandRec *__restrict__ sorted, const unsigned cha
 						w[3] &= 0x00FFFFFFFFFFFFFFull;
 						t = 0;
 					}
-					w[4] = t;
+					w[4] = t | ((unsigned long long)c.bytes[15] << 48);  // pad_[0] = bits repaired
 					unsigned long long *o = reinterpret_cast<unsigned long long *>(&out[p]);
 #pragma unroll
 					for (int k = 0; k < 5; k++)

@@ -55,7 +55,8 @@ void Resolver::scan_to(uint64_t cutoff, std::vector<adsbdec_b200_frame_t> &accep
 		memcpy(f.bytes, c->bytes, 14);
 		if (c->len == 7)
 			memset(f.bytes + 7, 0, 7);
-		f.pad_[0] = f.pad_[1] = 0;
+		f.pad_[0] = c->bytes[15];  // bits repaired (extension; 0 in reference mode)
+		f.pad_[1] = 0;
 		drift_ += skip - 1;
 		pos = c->n + skip;  // demod.c:110, :119-123: idx = lidx
 	}

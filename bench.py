@@ -275,7 +275,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     A.lib()   # fail loudly if the extension is missing
-    if world > 1:
+    if world > 1 and not os.environ.get("ADSB_B200_NO_BIND"):
         # keep each rank (and the page-locked memory it allocates) on the NUMA node of its GPU
         from adsbdec_b200.parallel import bind_to_gpu_numa_node
         bind_to_gpu_numa_node(local)
@@ -306,6 +306,7 @@ def main():
     barrier()
     dec.fused_time(reset=True)
     dec.kernel_time(reset=True)
+    dec.host_time(reset=True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fused_ms = fused_launches = fused_samples = 0.0
     launches = 0
@@ -320,10 +321,15 @@ def main():
         barrier()
     fused_ms, fused_launches, fused_samples = dec.fused_time()
     kernel_ms, launches = dec.kernel_time()
+    host_tel = dec.host_time()
     stats = dec.stats()
     ms_total = ev0.elapsed_time(ev1)
     t = torch.tensor([ms_total], device=dev)
+    per_rank = [ms_total / args.steps]
     if dist:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = [float(x.item()) / args.steps for x in allt]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
     value = world * n_samples / (ms_step * 1e-3) / 1e6
@@ -429,7 +435,8 @@ def main():
             "realtime_x": value * 1e6 / FS, "frames_per_step": int(frames),
             "frames_per_s": world * frames / (ms_step * 1e-3),
             "stats_try_ok": [list(stats[0]), list(stats[1])],
-            "kernel_ms_per_step": kernel_ms / args.steps,
+            "kernel_ms_per_step": kernel_ms / args.steps, "ms_per_step_ranks": per_rank,
+            "host_ms_per_step": {k: (v / args.steps if isinstance(v, float) else v) for k, v in host_tel.items()},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roof, "cpu_baseline": cpu,
         }

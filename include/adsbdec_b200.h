@@ -69,7 +69,7 @@ typedef struct {
 	uint32_t pw;        /* (p1+p2)/4 (demod.c:127)                                */
 	int32_t len;        /* 7 or 14                                                */
 	uint8_t bytes[14];
-	uint8_t pad_[2];
+	uint8_t pad_[2];    /* [0]: bits repaired (always 0 unless the repair extension is on) */
 } adsbdec_b200_frame_t;
 
 typedef struct {
@@ -85,7 +85,10 @@ typedef struct {
 	                                    FIR rotation / fidx wrap (air.c:34,65) line up)           */
 	uint64_t reserved[4];            /* [0], [1]: initial candidate / try list capacities (0 = default;
 	                                    lists regrow on demand), [2]: threads decode_file reads a regular
-	                                    file with (0 = up to 12, 1 = the calling thread only), [3]: 0  */
+	                                    file with (0 = up to 12, 1 = the calling thread only),
+	                                    [3]: EXTENSION, error repair by syndrome lookup: 0 = off = the
+	                                    reference (valid.c:52,:74 want syndrome 0), 1 = one flipped bit,
+	                                    2 = also two flipped bits of a 112-bit frame; never the DF field */
 } adsbdec_b200_config_t;
 
 /* Fills *cfg with defaults (device 0, reference-compatible behaviour). */

@@ -31,6 +31,7 @@ static const float taps[NTAPS] = {
 struct oracle_ctx {
 	int accept_df18;
 	int fma_contract;
+	int repair;                 /* EXTENSION, 0 = the reference: see try_repair() */
 	/* front end state (air.c:33-34, 49-50) */
 	float ring[NTAPS];
 	uint32_t ring_pos;
@@ -84,9 +85,41 @@ static uint32_t syndrome(const uint8_t *msg, int len)
 	return r ^ ((uint32_t)msg[len - 3] << 16 | (uint32_t)msg[len - 2] << 8 | msg[len - 1]);
 }
 
+/* ---- EXTENSION: error repair (not in the reference) ---------
+ * The reference stops at "syndrome != 0" (valid.c:52, :74).  With repair >= 1 a frame whose
+ * syndrome is that of ONE flipped bit is corrected and accepted; with repair >= 2 also TWO
+ * flipped bits of a 112-bit frame.  The five DF bits are never touched.  Stated here by brute
+ * force over the candidate bit positions (the CUDA path uses a hash of syndromes instead), with
+ * each position's syndrome taken from the table CRC above, so the two share no code. */
+static int try_repair(const oracle_ctx *c, uint8_t *msg, int len)
+{
+	const int nbits = 8 * len;
+	uint32_t s = syndrome(msg, len), one[112];
+	for (int b = 0; b < nbits; b++) {
+		uint8_t e[14] = {0};
+		e[b >> 3] = (uint8_t)(0x80 >> (b & 7));
+		one[b] = syndrome(e, len);
+	}
+	for (int b = 5; b < nbits; b++)
+		if (one[b] == s) {
+			msg[b >> 3] ^= (uint8_t)(0x80 >> (b & 7));
+			return 1;
+		}
+	if (c->repair < 2 || len != 14)
+		return 0;
+	for (int b1 = 5; b1 < nbits; b1++)
+		for (int b2 = b1 + 1; b2 < nbits; b2++)
+			if ((one[b1] ^ one[b2]) == s) {
+				msg[b1 >> 3] ^= (uint8_t)(0x80 >> (b1 & 7));
+				msg[b2 >> 3] ^= (uint8_t)(0x80 >> (b2 & 7));
+				return 2;
+			}
+	return 0;
+}
+
 /* ---- demodulator, demod.c ----------------------------------------------- */
 
-static void emit(oracle_ctx *c, const uint8_t *msg, int len, uint32_t pw, uint64_t n)
+static void emit(oracle_ctx *c, const uint8_t *msg, int len, uint32_t pw, uint64_t n, int fixed)
 {
 	if (c->nframes == c->capframes) {
 		c->capframes = c->capframes ? 2 * c->capframes : 1024;
@@ -99,6 +132,7 @@ static void emit(oracle_ctx *c, const uint8_t *msg, int len, uint32_t pw, uint64
 	f->pw = pw;
 	f->len = len;
 	memcpy(f->bytes, msg, (size_t)len);
+	f->pad_[0] = (uint8_t)fixed;
 }
 
 /* demod.c:31-44: bit k of a byte is "pulse in first half-microsecond". */
@@ -148,9 +182,10 @@ static int scan(oracle_ctx *c, const float *a, int have)
 		}
 		int df = msg[0] >> 3;
 		c->tried[df]++;                                            /* valid.c:46, 68 */
-		if (syndrome(msg, len) == 0) {
+		int fixed = 0;
+		if (syndrome(msg, len) == 0 || (c->repair > 0 && (fixed = try_repair(c, msg, len)) > 0)) {
 			c->passed[df]++;
-			emit(c, msg, len, (uint32_t)((p1 + p2) / 4), c->amp_base + (uint64_t)at);
+			emit(c, msg, len, (uint32_t)((p1 + p2) / 4), c->amp_base + (uint64_t)at, fixed);
 			at = d + 80 * len;                                     /* demod.c:128, 134 */
 			continue;
 		}
@@ -266,6 +301,8 @@ oracle_ctx *oracle_new(int accept_df18, int fma_contract)
 	c->fma_contract = fma_contract;
 	return c;
 }
+
+void oracle_set_repair(oracle_ctx *c, int level) { c->repair = level; }
 
 void oracle_set_origin(oracle_ctx *c, uint64_t origin)
 {

@@ -58,6 +58,7 @@ def lib():
         L.oracle_new.argtypes = [C.c_int, C.c_int]
         L.oracle_free.argtypes = [C.c_void_p]
         L.oracle_set_origin.argtypes = [C.c_void_p, C.c_uint64]
+        L.oracle_set_repair.argtypes = [C.c_void_p, C.c_int]
         L.oracle_push.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.oracle_decode_file.argtypes = [C.c_void_p, C.c_char_p]
         L.oracle_decode_file.restype = C.c_int
@@ -83,6 +84,7 @@ class Result:
     tried: tuple[int, int, int]
     ok: tuple[int, int, int]
     amp: np.ndarray | None = None
+    fixed: list[int] | None = None     # bits repaired per frame (extension; all 0 by default)
 
     def text(self, fmt: int = 0) -> bytes:
         return b"".join(format_frame(f, fmt) for f in self.frames)
@@ -99,7 +101,7 @@ def format_frame(f: Frame, fmt: int) -> bytes:
 
 
 def decode(samples: np.ndarray, *, accept_df18: bool = False, fma: bool = True,
-           want_amp: bool = False, origin: int = 0) -> Result:
+           want_amp: bool = False, origin: int = 0, repair: int = 0) -> Result:
     """Run the sequential restatement over a whole capture (file semantics)."""
     L = lib()
     samples = np.ascontiguousarray(samples, dtype="<u2")
@@ -108,6 +110,8 @@ def decode(samples: np.ndarray, *, accept_df18: bool = False, fma: bool = True,
     try:
         if origin:
             L.oracle_set_origin(ctx, origin)
+        if repair:
+            L.oracle_set_repair(ctx, repair)   # extension, see oracle.h
         if want_amp:
             amp = np.zeros(samples.size // 2 + 8, dtype=np.float32)
             L.oracle_record_amp(ctx, amp.ctypes.data, amp.size)
@@ -121,7 +125,9 @@ def decode(samples: np.ndarray, *, accept_df18: bool = False, fma: bool = True,
         L.oracle_stats(ctx, t, k)
         if want_amp:
             amp = amp[:L.oracle_amp_count(ctx)]
-        return Result(frames, tuple(t), tuple(k), amp)
+        res = Result(frames, tuple(t), tuple(k), amp)
+        res.fixed = [int(fr[i].pad[0]) for i in range(n)]
+        return res
     finally:
         L.oracle_free(ctx)
 

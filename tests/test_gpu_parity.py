@@ -524,3 +524,34 @@ def test_real_fidx_wrap_inside_a_long_stream(adsb, oracle):
     assert (fa["n"] < wrap_out).sum() > 1000 and (fa["n"] > wrap_out + 2_000_000).sum() > 1000
     near = fa[(fa["n"] > wrap_out - 3_000_000) & (fa["n"] < wrap_out + 3_000_000)]
     assert len(near) > 100
+
+
+@pytest.mark.parametrize("kernel", [1, 0], ids=["generic", "fused"])
+@pytest.mark.parametrize("level", [1, 2])
+def test_repair_extension_matches_oracle(adsb, oracle, kernel, level):
+    """EXTENSION, off by default (the reference has no repair): syndrome-lookup repair of one / two flipped
+    bits on the GPU against the oracle's brute-force statement of the same rule - frames, corrected bytes,
+    number of bits corrected, timestamps (a repaired frame takes part in the greedy skip) and Try/Ok."""
+    for nerr in (1, 2):
+        cap = synth_capture(0.3, 150, snr_db=22, seed=40 + nerr, df_mix=((17, 0.5), (18, 0.2), (11, 0.3)),
+                            bit_errors=nerr, pad=1 << 16)
+        ref = oracle.decode(cap.samples, accept_df18=True, repair=level)
+        d = adsb.decode(cap.samples, accept_df18=True, kernel=kernel, repair=level)
+        got, st, fixed = d.frames, d.stats(), [int(x) for x in d.frames_array["pad"][:, 0]]
+        d.close()
+        assert_same(ref, got, st)
+        assert fixed == ref.fixed
+        if level >= nerr:   # the injected errors are within reach of this level
+            plain = oracle.decode(cap.samples, accept_df18=True)
+            assert len(ref.frames) > len(plain.frames) + 10
+            assert nerr in fixed
+
+
+def test_repair_is_off_by_default(adsb, oracle):
+    cap = synth_capture(0.2, 80, snr_db=22, seed=45, bit_errors=1, pad=1 << 16)
+    d = adsb.decode(cap.samples)
+    assert not d.frames_array["pad"].any()
+    assert frames_key(d.frames) == frames_key(oracle.decode(cap.samples).frames)
+    d.close()
+    with pytest.raises(adsb.AdsbError):
+        adsb.Decoder(repair=3)

@@ -144,3 +144,37 @@ def test_oracle_file_ragged_odd_tail_vs_live_reference(oracle, tmp_path):
     ref = _run_ref_complete(oracle, f, ("-a", "-m"))
     r = oracle.decode_file(f, accept_df18=True)
     assert r.text(1) == ref.stdout and (r.tried, r.ok) == ref.stats()
+
+
+def test_oracle_repair_extension(oracle):
+    """EXTENSION (off by default, absent from the reference): 1-/2-bit repair by syndrome.  The oracle's
+    brute-force statement must give back the transmitted frame, never touch the DF bits, and leave the
+    default (reference) behaviour alone."""
+    from adsbdec_b200.modulator import crc24, synth_capture
+    cap = synth_capture(0.3, 120, snr_db=25, seed=77, df_mix=((17, 0.7), (11, 0.3)), bit_errors=1,
+                        pad=1 << 16, poisson=False)
+    r0 = oracle.decode(cap.samples)
+    r1 = oracle.decode(cap.samples, repair=1)
+    assert all(x == 0 for x in r0.fixed)
+    assert len(r1.frames) > len(r0.frames) + 20
+    # everything the reference mode decodes is still there, unchanged
+    k1 = {(f.n, f.data) for f in r1.frames}
+    assert all((f.n, f.data) in k1 for f in r0.frames)
+    n_fixed = 0
+    for f, nf in zip(r1.frames, r1.fixed):
+        # every accepted frame now has syndrome 0 over its (possibly corrected) bytes
+        assert crc24(f.data[:-3]) == int.from_bytes(f.data[-3:], "big")
+        n_fixed += nf == 1
+        assert nf in (0, 1)
+    assert n_fixed > 20
+    # a frame with an error in the DF field never comes back
+    sent = {b.frame for b in cap.bursts}
+    bad_df = [b for b in cap.bursts if crc24(b.frame[:-3]) != int.from_bytes(b.frame[-3:], "big")]
+    assert bad_df and len(sent) == len(cap.bursts)
+    # two flipped bits need level 2, and only 112-bit frames get it
+    cap2 = synth_capture(0.3, 120, snr_db=25, seed=78, df_mix=((17, 0.7), (11, 0.3)), bit_errors=2,
+                         pad=1 << 16, poisson=False)
+    a = oracle.decode(cap2.samples, repair=1)
+    b = oracle.decode(cap2.samples, repair=2)
+    assert sum(x == 2 for x in b.fixed) > 15 and not any(x == 2 for x in a.fixed)
+    assert all(len(f.data) == 14 for f, x in zip(b.frames, b.fixed) if x == 2)
