@@ -28,6 +28,7 @@ EXPORTS = [
     "adsbdec_b200_default_config", "adsbdec_b200_open", "adsbdec_b200_close", "adsbdec_b200_reset",
     "adsbdec_b200_set_sink",
     "adsbdec_b200_push", "adsbdec_b200_push_device", "adsbdec_b200_finish", "adsbdec_b200_decode_file",
+    "adsbdec_b200_flush", "adsbdec_b200_poll",
     "adsbdec_b200_stats", "adsbdec_b200_num_frames", "adsbdec_b200_frames", "adsbdec_b200_clear_frames",
     "adsbdec_b200_kernel_time", "adsbdec_b200_telemetry", "adsbdec_b200_fused_time", "adsbdec_b200_format_packet",
     "adsbdec_b200_envelope", "adsbdec_b200_resolver_new", "adsbdec_b200_resolver_free",
@@ -112,6 +113,8 @@ def lib():
         L.adsbdec_b200_push.argtypes = [vp, vp, C.c_size_t]
         L.adsbdec_b200_push_device.argtypes = [vp, vp, C.c_size_t]
         L.adsbdec_b200_finish.argtypes = [vp]
+        L.adsbdec_b200_flush.argtypes = [vp]
+        L.adsbdec_b200_poll.argtypes = [vp]
         L.adsbdec_b200_decode_file.argtypes = [vp, C.c_char_p]
         L.adsbdec_b200_stats.argtypes = [vp, u32p, u32p]
         L.adsbdec_b200_num_frames.argtypes = [vp]
@@ -210,6 +213,18 @@ class Decoder:
 
     def finish(self) -> None:
         _check(lib().adsbdec_b200_finish(self._h))
+
+    def flush(self) -> int:
+        """Submit the staged samples as a scan job now (live sources); returns frames delivered."""
+        rc = lib().adsbdec_b200_flush(self._h)
+        _check(rc)
+        return rc
+
+    def poll(self) -> int:
+        """Deliver the frames of finished scan jobs without blocking; returns how many."""
+        rc = lib().adsbdec_b200_poll(self._h)
+        _check(rc)
+        return rc
 
     def decode_file(self, path) -> int:
         """fileInput() (air.c:219-246).  Returns the C return code; a missing file is

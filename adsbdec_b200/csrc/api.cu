@@ -1005,6 +1005,40 @@ int adsbdec_b200_push_device(adsbdec_b200_t *h, const void *dev_samples, size_t 
 	return 0;
 }
 
+int adsbdec_b200_flush(adsbdec_b200_t *h)
+{
+	if (!h)
+		return fail(ADSB_B200_EINVAL, "null handle");
+	if (h->finished)
+		return fail(ADSB_B200_ESTATE, "flush after finish");
+	CU(cudaSetDevice(h->device));
+	const size_t before = h->emitted;
+	// only samples that arrived since the last scan justify a job (the carried tail alone does not)
+	if (h->dev[0] && 2 * h->own_next + 2 * kLookahead < h->pushed)
+		RC(flush_batch(h));
+	return (int)std::min<size_t>(h->emitted - before, 0x7FFFFFFF);
+}
+
+int adsbdec_b200_poll(adsbdec_b200_t *h)
+{
+	if (!h)
+		return fail(ADSB_B200_EINVAL, "null handle");
+	CU(cudaSetDevice(h->device));
+	const size_t before = h->emitted;
+	for (int k = 0; k < kSlots; k++) {
+		const int s = (h->next_slot + k) % kSlots;  // oldest first: frames leave in stream order
+		if (!h->job[s].active)
+			continue;
+		const cudaError_t e = cudaEventQuery(h->ev_done[s]);
+		if (e == cudaErrorNotReady)
+			break;
+		if (e != cudaSuccess)
+			return fail(ADSB_B200_ECUDA, "poll: %s", cudaGetErrorString(e));
+		RC(complete_job(h, s));
+	}
+	return (int)std::min<size_t>(h->emitted - before, 0x7FFFFFFF);
+}
+
 int adsbdec_b200_finish(adsbdec_b200_t *h)
 {
 	if (!h)

@@ -1,7 +1,7 @@
 // cli.cpp - command line with the option letters and observable behaviour of the reference's
 // main.c:54-106 / output.c:264-344 for the `-f FILE` path, on top of the C ABI.
 //
-//   adsbdec_b200 [-a] [-m] [-b] [-g N] -f FILE [-s addr[:port]]
+//   adsbdec_b200 [-a] [-m] [-b] [-g N] -f FILE [-s addr[:port]] [-l addr[:port]]
 //
 // Kept from the reference: getopt string "cf:s:l:g:aemb" with -c / -e / unknown -> usage, exit 1
 // (main.c:60, :85-87); -m / -b last one wins (main.c:79-84); -g parsed and ignored with -f; frames
@@ -32,7 +32,7 @@ int g_sock = -1;
 void usage()
 {
 	printf("adsbdec_b200 - B200-native ADS-B decoder, drop-in for `adsbdec -f`\n\n");
-	printf("usage : adsbdec_b200 [-a] [-m] [-b] [-g 0-21] -f filename [-s addr[:port]]\n\n");
+	printf("usage : adsbdec_b200 [-a] [-m] [-b] [-g 0-21] -f filename [-s addr[:port]] [-l addr[:port]]\n\n");
 	printf("Options :\n");
 	printf("\t-a : decode DF18 too\n");
 	printf("\t-m : output avrmlat format (ie : with 12Mhz timestamp)\n");
@@ -40,14 +40,17 @@ void usage()
 	printf("\t-g 0-21 : accepted for compatibility, ignored with -f\n");
 	printf("\t-f : input file (airspy raw real samples, 16 bits, 20 MS/s)\n");
 	printf("\t-s addr[:port] : send output via TCP to server at address addr:port (default port : 30001)\n");
+	printf("\t-l addr[:port] : listen on addr:port and send output via TCP to the first client (default port : 30002)\n");
 	printf("\t-D n : CUDA device ordinal\n");
 	printf("\t-R 1|2 : extension, not in adsbdec : repair 1 (2) flipped bits by CRC syndrome\n");
 }
 
-int connect_to(const char *spec)
+// -s: connect to a server; -l: bind, wait for ONE client ("listening" / "connected" on stderr), then
+// write to it exactly like -s (output.c:59-157; default ports 30001 / 30002).
+int open_socket(const char *spec, bool listener)
 {
-	// "addr[:port]" or "[v6addr]:port", default port 30001 (output.c:59-157)
-	std::string host(spec), port("30001");
+	// "addr[:port]" or "[v6addr]:port"
+	std::string host(spec), port(listener ? "30002" : "30001");
 	if (!host.empty() && host[0] == '[') {
 		size_t e = host.find(']');
 		if (e != std::string::npos) {
@@ -71,8 +74,22 @@ int connect_to(const char *spec)
 		fd = socket(p->ai_family, p->ai_socktype, p->ai_protocol);
 		if (fd < 0)
 			continue;
-		if (connect(fd, p->ai_addr, p->ai_addrlen) == 0)
-			break;
+		if (!listener) {
+			if (connect(fd, p->ai_addr, p->ai_addrlen) == 0)
+				break;
+		} else {
+			int one = 1;
+			setsockopt(fd, SOL_SOCKET, SO_REUSEADDR, &one, sizeof one);
+			if (bind(fd, p->ai_addr, p->ai_addrlen) == 0 && listen(fd, 1) == 0) {
+				fprintf(stderr, "listening\n");
+				const int client = accept(fd, nullptr, nullptr);
+				close(fd);
+				fd = client;
+				if (fd >= 0)
+					break;
+				continue;
+			}
+		}
 		close(fd);
 		fd = -1;
 	}
@@ -122,13 +139,15 @@ void print_stats(adsbdec_b200_t *h)
 int main(int argc, char **argv)
 {
 	const char *filename = nullptr, *addr = nullptr;
+	bool listener = false;
 	adsbdec_b200_config_t cfg;
 	adsbdec_b200_default_config(&cfg);
 	int c;
 	while ((c = getopt(argc, argv, "cf:s:l:g:aembD:GR:")) != EOF) {
 		switch (c) {
 		case 'f': filename = optarg; break;
-		case 's': addr = optarg; break;
+		case 's': addr = optarg; listener = false; break;  // main.c: outmode 1
+		case 'l': addr = optarg; listener = true; break;   // main.c: outmode 2
 		case 'g': (void)atoi(optarg); break;
 		case 'a': cfg.accept_df18 = 1; break;
 		case 'm': g_format = 1; break;
@@ -136,7 +155,7 @@ int main(int argc, char **argv)
 		case 'D': cfg.device = atoi(optarg); break;
 		case 'G': cfg.kernel = 1; break;
 		case 'R': cfg.reserved[3] = (uint64_t)atoi(optarg); break;
-		default:  // -c, -e, -l (no listener here) and anything unknown
+		default:  // -c, -e and anything unknown
 			usage();
 			return 1;
 		}
@@ -148,9 +167,9 @@ int main(int argc, char **argv)
 		return 1;
 	}
 	if (addr) {
-		g_sock = connect_to(addr);
+		g_sock = open_socket(addr, listener);
 		if (g_sock < 0) {
-			fprintf(stderr, "adsbdec_b200: cannot connect to %s\n", addr);
+			fprintf(stderr, "adsbdec_b200: cannot %s %s\n", listener ? "listen on" : "connect to", addr);
 			return 255;
 		}
 		fprintf(stderr, "connected\n");

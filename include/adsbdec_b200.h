@@ -16,6 +16,7 @@
  *                              getdf/getabyte (demod.c:31-81), validShort/validLong
  *                              (demod.c:28-29, valid.c:39-82)
  *   adsbdec_b200_finish        end of fileInput's read loop -> handlerExit(0)                  air.c:243-244
+ *   adsbdec_b200_flush / _poll bounded latency for a live rx_callback -> decodeiq source          air.c:173-177
  *   adsbdec_b200_sink_fn       void netout(const uint8_t *frame, const int len,
  *                                          const uint64_t ts, const uint32_t pw)                output.c:159
  *   adsbdec_b200_stats         stat_try / stat_ok read by print_stats()                         valid.c:30-31, 84-101
@@ -112,6 +113,16 @@ int adsbdec_b200_push(adsbdec_b200_t *h, const uint16_t *samples, size_t n);
 /* Same, with the samples already in DEVICE memory of cfg->device.  The pointer
  * must stay valid until the call returns. */
 int adsbdec_b200_push_device(adsbdec_b200_t *h, const void *dev_samples, size_t n);
+
+/* Live sources (the airspy callback, air.c:173-177, hands decodeiq 64 Ki..1 Mi samples at a time and
+ * the reference decodes them before it returns).  push() only scans once a batch is full and hands
+ * frames out two batches later; these two bound the latency instead:
+ *   flush: submit whatever is staged as a scan job now (no-op if nothing is staged);
+ *   poll:  deliver the frames of every scan job that has finished, without blocking.
+ * Both return the number of frames delivered to the sink / frame list by the call, or < 0.
+ * The decoded output does not depend on when, or whether, they are called. */
+int adsbdec_b200_flush(adsbdec_b200_t *h);
+int adsbdec_b200_poll(adsbdec_b200_t *h);
 
 /* End of input: flushes staged samples, resolves and emits the remaining frames. */
 int adsbdec_b200_finish(adsbdec_b200_t *h);

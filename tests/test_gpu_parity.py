@@ -113,6 +113,38 @@ def test_push_in_pieces(adsb, oracle, kernel):
     assert d.stats() == (ref.tried, ref.ok)
 
 
+@pytest.mark.parametrize("kernel", [1, 0], ids=["generic", "fused"])
+def test_live_source_flush_and_poll(adsb, oracle, kernel):
+    """A live source (rx_callback -> decodeiq, air.c:173-177) pushes small buffers and wants its frames
+    soon: flush() scans what is staged, poll() hands out finished jobs.  Neither changes the output."""
+    import time
+    cap = capture_basic(seed=71, seconds=0.4, n_frames=150)
+    ref = oracle.decode(cap.samples)
+    rng = np.random.default_rng(8)
+    seen = []
+    d = adsb.Decoder(kernel=kernel, sink=lambda fr, ts, pw: seen.append((ts, pw, fr)))
+    pos, early = 0, 0
+    while pos < cap.samples.size:
+        n = int(rng.integers(1, 60000)) * 4
+        d.push(cap.samples[pos:pos + n])
+        pos += n
+        early += d.flush()
+        if rng.integers(0, 3) == 0:
+            time.sleep(0.002)
+        early += d.poll()
+    before_finish = len(seen)
+    d.finish()
+    assert frames_key(d.frames) == frames_key(ref.frames)
+    assert seen == [(f.ts, f.pw, f.data) for f in ref.frames]
+    assert d.stats() == (ref.tried, ref.ok)
+    # most frames left long before the end of the stream (default batch = 32 Mi samples > this capture)
+    assert early == before_finish and before_finish > 0.8 * len(ref.frames)
+    assert d.poll() == 0
+    with pytest.raises(adsb.AdsbError):
+        d.flush()
+    d.close()
+
+
 def test_push_rejects_ragged_length(adsb):
     d = adsb.Decoder()
     with pytest.raises(adsb.AdsbError):
@@ -271,6 +303,43 @@ def test_cli_beast_over_tcp_and_missing_file(adsb, tmp_path):
     # air.c:225-228: a file that cannot be opened -> no frames, stats, exit 0
     r = subprocess.run([str(adsb.CLI_PATH), "-f", str(tmp_path / "nope.bin")], capture_output=True)
     assert r.returncode == 0 and r.stdout == b"" and b"Try :" in r.stderr
+
+
+def test_cli_listener_serves_the_first_client(adsb, tmp_path):
+    """-l addr:port (main.c:69-72, output.c:130-146): bind, print "listening", accept one client, then
+    write to it like -s.  Same bytes as the reference's beast output over TCP."""
+    import socket
+    import time
+    g = _load_golden(GOLDEN[0])
+    f = tmp_path / "cap.bin"
+    g["samples"].astype("<u2").tofile(f)
+    probe = socket.socket()
+    probe.bind(("127.0.0.1", 0))
+    port = probe.getsockname()[1]
+    probe.close()
+    p = subprocess.Popen([str(adsb.CLI_PATH), "-a", "-b", "-l", f"127.0.0.1:{port}", "-f", str(f)],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    try:
+        assert p.stderr.readline().strip() == b"listening"
+        got = b""
+        for _ in range(50):
+            try:
+                c = socket.create_connection(("127.0.0.1", port), timeout=5)
+                break
+            except OSError:
+                time.sleep(0.1)
+        with c:
+            while True:
+                b = c.recv(65536)
+                if not b:
+                    break
+                got += b
+        out, err = p.communicate(timeout=60)
+    finally:
+        if p.poll() is None:
+            p.kill()
+    assert p.returncode == 0 and out == b"" and got == g["beast_a"]
+    assert err.startswith(b"connected") and b"Try :" in err
 
 
 def test_cli_vs_live_reference_binary(adsb, oracle, tmp_path):
