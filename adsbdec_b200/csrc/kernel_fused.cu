@@ -68,7 +68,7 @@ constexpr int WR = 128;             // bit-array ring, in 32-bit words
 constexpr int WPB = S / 32;         // bit words per sub-block (28)
 constexpr int CAND_CAP = 96;        // survivors of the DF gate one sub-block may add
 constexpr int LIST_CAP = 192;       // survivor list of a warp: doubles as its try buffer between flushes
-constexpr int MIRROR = 8;           // words 0..7 of the bit rings are mirrored behind the end
+constexpr int MIRROR = 12;          // words 0..11 of the bit rings are mirrored behind the end
 
 static_assert(LAG3 % 32 == 0 && LAG3 >= kLookahead + LAG2 * R + 32 + 8, "stage-3 lag");
 static_assert(WR >= WPB + LAG3 / 32 + 8, "bit ring too small");
@@ -479,16 +479,24 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 					// frame bit b sits at n + 80 + 10 b; nibble g starts at bit 4g
 					const uint32_t pb0 = n_rel + 80u + 280u * (uint32_t)sub;
 					const char *lutp = reinterpret_cast<const char *>(sm.lut) + (7 * sub + (is_long ? 0 : 14)) * 64;
-					const char *bbp = reinterpret_cast<const char *>(ws.bbits);
 					uint32_t acc = 0, bits28 = 0;
 					if (active) {
+						// The lane's 28 frame bits sit 10 apart in 271 consecutive B bits: fetch the ten
+						// words once (mirrored past the end of the ring) and shift them so that the
+						// lane's first bit is bit 31 of W[0] - every later position is then a constant.
+						const uint32_t *bb = &ws.bbits[(pb0 >> 5) & (WR - 1)];
+						const uint32_t sh = pb0 & 31u;
+						uint32_t r[10], W[9];
+#pragma unroll
+						for (int i = 0; i < 10; i++)
+							r[i] = bb[i];
+#pragma unroll
+						for (int i = 0; i < 9; i++)
+							W[i] = __funnelshift_l(r[i + 1], r[i], sh);
 #pragma unroll
 						for (int s_ = 0; s_ < 7; s_++) {
-							const uint32_t pb = pb0 + 40u * s_;
-							const uint32_t wa = (pb >> 3) & ((WR - 1) << 2);  // byte offset of the word in the ring
-							const uint32_t w0 = *reinterpret_cast<const uint32_t *>(bbp + wa);
-							const uint32_t w1 = *reinterpret_cast<const uint32_t *>(bbp + wa + 4);  // mirrored past the end
-							const uint32_t x = __funnelshift_l(w1, w0, pb & 31u);  // bits 31, 21, 11, 1
+							const int k = 40 * s_, i = k >> 5, o = k & 31;
+							const uint32_t x = o ? __funnelshift_l(W[i + 1], W[i], o) : W[i];  // bits 31, 21, 11, 1
 							const uint32_t nib = ((x & 0x80200802u) * 0x08040201u) >> 28;
 							acc ^= *reinterpret_cast<const uint32_t *>(lutp + 64 * s_ + 4u * nib);
 							bits28 = bits28 * 16u + nib;
