@@ -405,11 +405,12 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 					}
 				}
 			}
+			// survivors of earlier sub-blocks still listed: the length was last written before the previous
+			// barrier, and every lane reads it before the next one, behind which stage 3 appends
+			const int list0 = p.want_tries ? ws.ncand : 0;
 			__syncwarp();  // bit arrays of sub-block k visible to the warp
 
 			// ================= stage 3: preamble AND + DF gate ===============
-			const int list0 = p.want_tries ? ws.ncand : 0;  // survivors of earlier sub-blocks still listed
-			__syncwarp();  // every lane has read the list length before any lane appends to it
 			if (lane < WPB) {
 				const int wd = k * WPB + lane - LAG3 / 32;
 				if (wd >= 0) {
@@ -546,12 +547,13 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 						}
 					}
 				}
-				__syncwarp();
 				// keep the entries as tries until the list runs short of room for another sub-block
+				// (flush_list only reads the list until its own barrier)
 				if (!p.want_tries || list1 > LIST_CAP - CAND_CAP)
 					flush_list();
 			}
-			__syncwarp();
+			// no barrier here: the next one every lane meets is behind the mbarrier wait of sub-block
+			// k+1, and nothing shared is written before it except the raw stage, which is free
 			q_fir += 32;
 			if (q_fir >= RUNS) q_fir -= RUNS;
 		}
