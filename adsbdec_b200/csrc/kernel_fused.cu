@@ -72,6 +72,7 @@ constexpr int MIRROR = 12;          // words 0..11 of the bit rings are mirrored
 
 static_assert(LAG3 % 32 == 0 && LAG3 >= kLookahead + LAG2 * R + 32 + 8, "stage-3 lag");
 static_assert(WR >= WPB + LAG3 / 32 + 8, "bit ring too small");
+static_assert(LAG3 / 32 > WPB + 3 + (LAG2 * R + 31) / 32, "stage 3 of a sub-block must not need its stage 2");
 static_assert((WR & (WR - 1)) == 0, "bit ring must be a power of two");
 
 struct WarpSmem {
@@ -248,20 +249,26 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 		int q_fir = lane;  // ring run of this lane's FIR output, (k*32 + lane) % RUNS
 
 		for (int k = 0; k < nb; k++) {
+			// survivors of earlier sub-blocks still listed: the length was last written before the previous
+			// barrier, and every lane reads it here, in front of the barriers of stage 1
+			const int list0 = p.want_tries ? ws.ncand : 0;
+
 			// ================= stage 1: envelope ============================
 			{
 				const int start = k * S;
 				// words the window does not hold read as mid-scale: before the stream start the
 				// reference's ring is zero (air.c:33), past the end they are never used
 				const int va = max(start, vlo) - start, vb = min(start + STAGE_WORDS, vhi) - start;
-				if (va > 0 || vb < STAGE_WORDS) {
+				const bool partial = va > 0 || vb < STAGE_WORDS;  // warp-uniform
+				if (partial) {
 					for (int i = lane; i < STAGE_WORDS; i += 32)
 						if (i < va || i >= vb)
 							ws.raw[i] = 0x08000800u;
 				}
 				mbar_wait(&ws.full, phase);
 				phase ^= 1u;
-				__syncwarp();
+				if (partial)
+					__syncwarp();  // the fill above was written by other lanes
 
 				uint32_t w[36];
 				const uint4 *src = reinterpret_cast<const uint4 *>(&ws.raw[R * lane]);
@@ -324,6 +331,55 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 							const long long at = (long long)k * S + R * lane + (r_ - 3);
 							if (at + 4 <= p.dbg_n)
 								*reinterpret_cast<float4 *>(&p.dbg_amp[at]) = make_float4(o[0], o[1], o[2], o[3]);
+						}
+					}
+				}
+			}
+
+			// ================= stage 3: preamble AND + DF gate ===============
+			// Runs BEFORE stage 2 of this sub-block: it looks at words 28k-46 .. 28k-15 of the bit arrays,
+			// all written by stage 2 of earlier sub-blocks (stage 2 of this one writes 28k-7 .. 28k+20), so
+			// no barrier is needed in front of it and its list is complete at the barrier stage 4 needs anyway.
+			if (lane < WPB) {
+				const int wd = k * WPB + lane - LAG3 / 32;
+				if (wd >= 0) {
+					const int wb = wd & (WR - 1);  // wb .. wb+4 are readable thanks to the mirror
+					const uint32_t p0 = ws.pbits[wb];
+					const uint32_t q0 = ws.qbits[wb], q1 = ws.qbits[wb + 1];
+					// demod.c:107: p1 > 2*s1 at n, p2 > 2*s2 at n+30
+					uint32_t pre = p0 & __funnelshift_l(q1, q0, 30);
+					// ownership: only offsets in [own_lo, own_hi) (relative to j_begin) are emitted here
+					const uint32_t o0 = (uint32_t)wd * 32u;
+					if (o0 < own_lo || o0 + 32u > own_hi) {
+						const uint32_t lo = own_lo > o0 ? own_lo - o0 : 0u;            // first owned bit index
+						const uint32_t hi = own_hi > o0 ? min(own_hi - o0, 32u) : 0u;  // one past the last
+						const uint32_t m_lo = lo >= 32u ? 0u : 0xFFFFFFFFu >> lo;
+						const uint32_t m_hi = hi >= 32u ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> hi);
+						pre &= m_lo & m_hi;
+					}
+					if (pre) {
+						const uint32_t b2 = ws.bbits[wb + 2], b3 = ws.bbits[wb + 3], b4 = ws.bbits[wb + 4];
+						// first five data bits sit at n+80, +90, +100, +110, +120 (demod.c:110, :46-81)
+						const uint32_t x7 = __funnelshift_l(b3, b2, 16);  // 80  = 64 + 16
+						const uint32_t x6 = __funnelshift_l(b3, b2, 26);  // 90  = 64 + 26
+						const uint32_t x5 = __funnelshift_l(b4, b3, 4);   // 100 = 96 + 4
+						const uint32_t x4 = __funnelshift_l(b4, b3, 14);  // 110 = 96 + 14
+						const uint32_t x3 = __funnelshift_l(b4, b3, 24);  // 120 = 96 + 24
+						const uint32_t m17 = pre & x7 & ~x6 & ~x5 & ~x4 & x3;                         // 10001
+						const uint32_t m18 = p.accept_df18 ? (pre & x7 & ~x6 & ~x5 & x4 & ~x3) : 0u;  // 10010
+						const uint32_t m11 = pre & ~x7 & x6 & ~x5 & x4 & x3;                          // 01011
+						uint32_t any = m17 | m18 | m11;
+						if (any) {
+							int slot = atomicAdd(&ws.ncand, __popc(any));
+							do {
+								const int i = __clz(any);
+								const uint32_t bit = 0x80000000u >> i;
+								any &= ~bit;
+								const uint32_t cls = (m17 & bit) ? kClsDF17 : (m11 & bit) ? kClsDF11 : kClsDF18;
+								if (slot < LIST_CAP)
+									ws.cand[slot] = (o0 + (uint32_t)i) | (cls << 30);
+								slot++;
+							} while (any);
 						}
 					}
 				}
@@ -405,57 +461,7 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 					}
 				}
 			}
-			// survivors of earlier sub-blocks still listed: the length was last written before the previous
-			// barrier, and every lane reads it before the next one, behind which stage 3 appends
-			const int list0 = p.want_tries ? ws.ncand : 0;
-			__syncwarp();  // bit arrays of sub-block k visible to the warp
-
-			// ================= stage 3: preamble AND + DF gate ===============
-			if (lane < WPB) {
-				const int wd = k * WPB + lane - LAG3 / 32;
-				if (wd >= 0) {
-					const int wb = wd & (WR - 1);  // wb .. wb+4 are readable thanks to the mirror
-					const uint32_t p0 = ws.pbits[wb];
-					const uint32_t q0 = ws.qbits[wb], q1 = ws.qbits[wb + 1];
-					// demod.c:107: p1 > 2*s1 at n, p2 > 2*s2 at n+30
-					uint32_t pre = p0 & __funnelshift_l(q1, q0, 30);
-					// ownership: only offsets in [own_lo, own_hi) (relative to j_begin) are emitted here
-					const uint32_t o0 = (uint32_t)wd * 32u;
-					if (o0 < own_lo || o0 + 32u > own_hi) {
-						const uint32_t lo = own_lo > o0 ? own_lo - o0 : 0u;            // first owned bit index
-						const uint32_t hi = own_hi > o0 ? min(own_hi - o0, 32u) : 0u;  // one past the last
-						const uint32_t m_lo = lo >= 32u ? 0u : 0xFFFFFFFFu >> lo;
-						const uint32_t m_hi = hi >= 32u ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> hi);
-						pre &= m_lo & m_hi;
-					}
-					if (pre) {
-						const uint32_t b2 = ws.bbits[wb + 2], b3 = ws.bbits[wb + 3], b4 = ws.bbits[wb + 4];
-						// first five data bits sit at n+80, +90, +100, +110, +120 (demod.c:110, :46-81)
-						const uint32_t x7 = __funnelshift_l(b3, b2, 16);  // 80  = 64 + 16
-						const uint32_t x6 = __funnelshift_l(b3, b2, 26);  // 90  = 64 + 26
-						const uint32_t x5 = __funnelshift_l(b4, b3, 4);   // 100 = 96 + 4
-						const uint32_t x4 = __funnelshift_l(b4, b3, 14);  // 110 = 96 + 14
-						const uint32_t x3 = __funnelshift_l(b4, b3, 24);  // 120 = 96 + 24
-						const uint32_t m17 = pre & x7 & ~x6 & ~x5 & ~x4 & x3;                         // 10001
-						const uint32_t m18 = p.accept_df18 ? (pre & x7 & ~x6 & ~x5 & x4 & ~x3) : 0u;  // 10010
-						const uint32_t m11 = pre & ~x7 & x6 & ~x5 & x4 & x3;                          // 01011
-						uint32_t any = m17 | m18 | m11;
-						if (any) {
-							int slot = atomicAdd(&ws.ncand, __popc(any));
-							do {
-								const int i = __clz(any);
-								const uint32_t bit = 0x80000000u >> i;
-								any &= ~bit;
-								const uint32_t cls = (m17 & bit) ? kClsDF17 : (m11 & bit) ? kClsDF11 : kClsDF18;
-								if (slot < LIST_CAP)
-									ws.cand[slot] = (o0 + (uint32_t)i) | (cls << 30);
-								slot++;
-							} while (any);
-						}
-					}
-				}
-			}
-			__syncwarp();  // survivor list complete
+			__syncwarp();  // bit arrays of sub-block k and the survivor list visible to the warp
 
 			// ================= stage 4: slice + CRC, four lanes per survivor ==
 			const int n_all = ws.ncand;
