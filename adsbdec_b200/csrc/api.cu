@@ -72,7 +72,7 @@ constexpr int64_t kAmpChunk = 8ll << 20;   // generic path: offsets per envelope
 constexpr int64_t kMinFused = 1 << 16;     // ranges smaller than this use the generic kernels
 constexpr int64_t kStageSlice = 4ll << 20; // pageable pushes are staged and uploaded in slices
 constexpr int64_t kBulkRead = 16ll << 20;  // decode_file: samples fetched per parallel read
-constexpr unsigned long long kSpecCands = 1ull << 15;  // candidates copied back speculatively
+constexpr unsigned long long kSpecCands = 1ull << 15;  // results copied back speculatively, at least
 constexpr unsigned long long kPendCap = 1ull << 18;
 constexpr int kSlots = 2;
 
@@ -135,6 +135,7 @@ struct adsbdec_b200 {
 	int device = 0;
 	cudaStream_t st = nullptr;       // kernels + result copies
 	cudaStream_t st_copy = nullptr;  // uploads of sample batches
+	cudaStream_t st_d2h = nullptr;   // the rest of a job's results when the speculative copy fell short
 	unsigned long long origin = 0;   // absolute index of local sample 0 (FIR phase / fidx wrap)
 
 	// stream position (local sample / offset indices, 0 = first sample ever pushed)
@@ -163,6 +164,8 @@ struct adsbdec_b200 {
 	CandRec *d_cands[kSlots] = {nullptr, nullptr};
 	unsigned char *h_cands[kSlots] = {nullptr, nullptr};  // accepted frames (FrameRec) or sorted candidates (CandRec)
 	unsigned long long cand_cap[kSlots] = {0, 0};
+	unsigned long long spec_n[kSlots] = {0, 0};  // records the job's speculative result copy covered
+	unsigned long long spec_want = kSpecCands;   // sized from what the last jobs returned
 	unsigned long long *d_tries[kSlots] = {nullptr, nullptr};
 	unsigned long long try_cap[kSlots] = {0, 0};
 	// on-GPU ordering + greedy resolve (kernels_resolve.cu)
@@ -435,8 +438,11 @@ int enqueue_job(adsbdec_b200 *h, int s, bool force_generic)
 	CU(cudaMemcpyAsync(h->h_ctr[s], h->d_ctr[s], sizeof(Counters), cudaMemcpyDeviceToHost, h->st));
 	if (j.resolve)
 		CU(cudaMemcpyAsync(h->h_slot[s], h->d_slot[s], sizeof(SlotResolve), cudaMemcpyDeviceToHost, h->st));
-	CU(cudaMemcpyAsync(h->h_cands[s], result, std::min(kSpecCands, h->cand_cap[s]) * rec, cudaMemcpyDeviceToHost,
-	                   h->st));
+	// The result count is only known on the device: copy what recent jobs needed plus a margin now, in
+	// stream order; complete_job fetches any remainder on a stream of its own (a copy queued on THIS
+	// stream would sit behind the next job and stall the host for a whole scan).
+	h->spec_n[s] = std::min(h->spec_want, h->cand_cap[s]);
+	CU(cudaMemcpyAsync(h->h_cands[s], result, h->spec_n[s] * rec, cudaMemcpyDeviceToHost, h->st));
 	CU(cudaEventRecord(h->ev_done[s], h->st));
 	return 0;
 }
@@ -525,14 +531,17 @@ int complete_job(adsbdec_b200 *h, int s)
 		h->tel.candidates += h->h_ctr[s]->n_cand;
 		h->tel.tries += h->cfg.collect_stats ? h->h_ctr[s]->n_try : 0;
 		n_res = j.resolve ? (size_t)h->h_slot[s]->n_accept : (size_t)std::min<unsigned long long>(h->h_ctr[s]->n_cand, h->cand_cap[s]);
-		if (n_res > kSpecCands) {
+		if (n_res > h->spec_n[s]) {
 			const size_t rec = j.resolve ? sizeof(FrameRec) : sizeof(CandRec);
 			const unsigned char *src = j.resolve ? reinterpret_cast<const unsigned char *>(h->d_acc[s])
 			                                     : reinterpret_cast<const unsigned char *>(h->rb[s].sorted);
-			CU(cudaMemcpyAsync(h->h_cands[s] + kSpecCands * rec, src + kSpecCands * rec, (n_res - kSpecCands) * rec,
-			                   cudaMemcpyDeviceToHost, h->st));
-			CU(cudaStreamSynchronize(h->st));
+			const size_t done = (size_t)h->spec_n[s];
+			CU(cudaMemcpyAsync(h->h_cands[s] + done * rec, src + done * rec, (n_res - done) * rec,
+			                   cudaMemcpyDeviceToHost, h->st_d2h));  // the job is done: no dependency to wait for
+			CU(cudaStreamSynchronize(h->st_d2h));
 		}
+		// next time copy 1.25 x what this job returned up front (never less than the floor)
+		h->spec_want = std::max<unsigned long long>(kSpecCands, (unsigned long long)n_res + n_res / 4 + 1024);
 	} else {
 		CU(cudaEventSynchronize(h->ev_done[s]));
 	}
@@ -723,6 +732,7 @@ int adsbdec_b200_open(const adsbdec_b200_config_t *cfg, adsbdec_b200_t **out)
 	do {
 		bool ok = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) == cudaSuccess &&
 		          cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking) == cudaSuccess &&
+		          cudaStreamCreateWithFlags(&h->st_d2h, cudaStreamNonBlocking) == cudaSuccess &&
 		          cudaEventCreateWithFlags(&h->ev_h2d, cudaEventDisableTiming) == cudaSuccess &&
 		          cudaMalloc(&h->d_stats, sizeof(StreamStats)) == cudaSuccess &&
 		          cudaMalloc(&h->d_state, sizeof(ResolveState)) == cudaSuccess &&
@@ -842,6 +852,7 @@ void adsbdec_b200_close(adsbdec_b200_t *h)
 	if (h->ev_h2d) cudaEventDestroy(h->ev_h2d);
 	if (h->st) cudaStreamDestroy(h->st);
 	if (h->st_copy) cudaStreamDestroy(h->st_copy);
+	if (h->st_d2h) cudaStreamDestroy(h->st_d2h);
 	delete h->res;
 	delete h;
 }
