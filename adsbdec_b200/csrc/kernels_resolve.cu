@@ -43,118 +43,107 @@ __global__ void k_hist(const CandRec *__restrict__ c, const Counters *ctr, unsig
 		atomicAdd(&cnt[(unsigned long long)((long long)c[i].n - n0) >> kBShift], 1u);
 }
 
-// Exclusive scan of `in` (nb entries) into `out` (nb+1 entries), single block: tiles of 4096
-// entries (one uint4 per thread, coalesced), warp-shuffle scans inside the tile, running carry.
-__global__ void k_scan_buckets(const unsigned int *__restrict__ in, unsigned int *__restrict__ out, int nb)
+// Exclusive scan of bucket counts (nb entries in, nb+1 out), single block, three block barriers per
+// 36 Ki entries: every warp scans its 128-entry slice of each 4 Ki tile with shuffles and leaves the
+// slice totals in shared memory; nine warps scan those; every thread then reloads its four entries per
+// tile (coalesced 16-byte accesses, L2-resident) and writes them with the offsets added.  DUAL scans
+// two arrays at once (accepted frames and their timestamp drift per bucket) packed into one 64-bit
+// value: both totals stay below 2^32 (a job holds < 2^28 offsets).
+constexpr int kScanTile = 4 * kScanThreads;
+constexpr int kScanTiles = 9;  // per pass: a full-size job has 32 Ki + 2 buckets
+
+template <bool DUAL>
+__device__ __forceinline__ void scan_load4(const unsigned int *__restrict__ in_a, const unsigned int *__restrict__ in_b,
+                                           int i0, int nb, unsigned long long v[4])
 {
-	__shared__ unsigned int warp_sum[kScanThreads / 32];
-	__shared__ unsigned int carry_s;
-	const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-	if (t == 0)
-		carry_s = 0;
-	__syncthreads();
-	for (int base = 0; base < nb; base += 4 * kScanThreads) {
-		const int i0 = base + 4 * t;
-		unsigned int v[4];
+	typedef unsigned long long T;
+	if (i0 + 4 <= nb) {
+		const uint4 a = *reinterpret_cast<const uint4 *>(in_a + i0);
+		v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+		if (DUAL) {
+			const uint4 b = *reinterpret_cast<const uint4 *>(in_b + i0);
+			v[0] |= (T)b.x << 32; v[1] |= (T)b.y << 32; v[2] |= (T)b.z << 32; v[3] |= (T)b.w << 32;
+		}
+	} else {
 #pragma unroll
 		for (int k = 0; k < 4; k++)
-			v[k] = i0 + k < nb ? in[i0 + k] : 0u;
-		const unsigned int mine = v[0] + v[1] + v[2] + v[3];
-		unsigned int x = mine;  // inclusive scan across the warp
-#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
-			const unsigned int y = __shfl_up_sync(0xFFFFFFFFu, x, d);
-			if (lane >= d)
-				x += y;
-		}
-		if (lane == 31)
-			warp_sum[w] = x;
-		__syncthreads();
-		if (w == 0) {
-			unsigned int s = warp_sum[lane];
-#pragma unroll
-			for (int d = 1; d < 32; d <<= 1) {
-				const unsigned int y = __shfl_up_sync(0xFFFFFFFFu, s, d);
-				if (lane >= d)
-					s += y;
-			}
-			warp_sum[lane] = s;  // inclusive over warps
-		}
-		__syncthreads();
-		const unsigned int carry = carry_s;
-		unsigned int pre = carry + (w ? warp_sum[w - 1] : 0u) + (x - mine);  // exclusive prefix of this thread
-#pragma unroll
-		for (int k = 0; k < 4; k++) {
-			if (i0 + k < nb)
-				out[i0 + k] = pre;
-			pre += v[k];
-		}
-		__syncthreads();
-		if (t == kScanThreads - 1)
-			carry_s = carry + warp_sum[31];
-		__syncthreads();
+			v[k] = i0 + k < nb ? (T)in_a[i0 + k] | (DUAL ? (T)in_b[i0 + k] << 32 : 0ull) : 0ull;
 	}
-	if (t == 0)
-		out[nb] = carry_s;
 }
 
-// The same scan over two arrays at once (accepted frames and their timestamp drift per bucket),
-// packed into one 64-bit value per entry: both totals stay below 2^32 (a job holds < 2^28 offsets).
-__global__ void k_scan_buckets2(const unsigned int *__restrict__ in_a, const unsigned int *__restrict__ in_b,
-                                unsigned int *__restrict__ out_a, unsigned int *__restrict__ out_b, int nb)
+template <bool DUAL>
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_buckets_t(const unsigned int *__restrict__ in_a, const unsigned int *__restrict__ in_b,
+                 unsigned int *__restrict__ out_a, unsigned int *__restrict__ out_b, int nb)
 {
-	__shared__ unsigned long long warp_sum[kScanThreads / 32];
-	__shared__ unsigned long long carry_s;
+	typedef unsigned long long T;
+	__shared__ T wsum[kScanTiles][32];
 	const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-	if (t == 0)
-		carry_s = 0;
-	__syncthreads();
-	for (int base = 0; base < nb; base += 4 * kScanThreads) {
-		const int i0 = base + 4 * t;
-		unsigned long long v[4];
+	T carry = 0;  // identical in every thread
+	for (int base = 0; base < nb; base += kScanTiles * kScanTile) {
+		T ex[kScanTiles];  // sum of the entries of this tile in front of this thread's, inside its warp
 #pragma unroll
-		for (int k = 0; k < 4; k++)
-			v[k] = i0 + k < nb ? ((unsigned long long)in_b[i0 + k] << 32) | in_a[i0 + k] : 0ull;
-		const unsigned long long mine = v[0] + v[1] + v[2] + v[3];
-		unsigned long long x = mine;
-#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
-			const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, d);
-			if (lane >= d)
-				x += y;
-		}
-		if (lane == 31)
-			warp_sum[w] = x;
-		__syncthreads();
-		if (w == 0) {
-			unsigned long long s = warp_sum[lane];
+		for (int tl = 0; tl < kScanTiles; tl++) {
+			T v[4];
+			scan_load4<DUAL>(in_a, in_b, base + tl * kScanTile + 4 * t, nb, v);
+			const T mine = v[0] + v[1] + v[2] + v[3];
+			T x = mine;
 #pragma unroll
 			for (int d = 1; d < 32; d <<= 1) {
-				const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, s, d);
+				const T y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+				if (lane >= d)
+					x += y;
+			}
+			ex[tl] = x - mine;
+			if (lane == 31)
+				wsum[tl][w] = x;
+		}
+		__syncthreads();
+		if (w < kScanTiles) {  // warp w: inclusive scan of tile w's 32 slice totals
+			T s = wsum[w][lane];
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const T y = __shfl_up_sync(0xFFFFFFFFu, s, d);
 				if (lane >= d)
 					s += y;
 			}
-			warp_sum[lane] = s;
+			wsum[w][lane] = s;
 		}
 		__syncthreads();
-		const unsigned long long carry = carry_s;
-		unsigned long long pre = carry + (w ? warp_sum[w - 1] : 0ull) + (x - mine);
 #pragma unroll
-		for (int k = 0; k < 4; k++) {
-			if (i0 + k < nb) {
-				out_a[i0 + k] = (unsigned int)pre;
-				out_b[i0 + k] = (unsigned int)(pre >> 32);
+		for (int tl = 0; tl < kScanTiles; tl++) {
+			const int i0 = base + tl * kScanTile + 4 * t;
+			T v[4];
+			scan_load4<DUAL>(in_a, in_b, i0, nb, v);
+			T pre = carry + (w ? wsum[tl][w - 1] : 0ull) + ex[tl];
+			unsigned int oa[4], ob[4];
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				oa[k] = (unsigned int)pre;
+				ob[k] = (unsigned int)(pre >> 32);
+				pre += v[k];
 			}
-			pre += v[k];
+			if (i0 + 4 <= nb) {
+				*reinterpret_cast<uint4 *>(out_a + i0) = make_uint4(oa[0], oa[1], oa[2], oa[3]);
+				if (DUAL)
+					*reinterpret_cast<uint4 *>(out_b + i0) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+			} else {
+#pragma unroll
+				for (int k = 0; k < 4; k++)
+					if (i0 + k < nb) {
+						out_a[i0 + k] = oa[k];
+						if (DUAL)
+							out_b[i0 + k] = ob[k];
+					}
+			}
+			carry += wsum[tl][31];
 		}
-		__syncthreads();
-		if (t == kScanThreads - 1)
-			carry_s = carry + warp_sum[31];
-		__syncthreads();
+		__syncthreads();  // wsum is reused by the next pass
 	}
 	if (t == 0) {
-		out_a[nb] = (unsigned int)carry_s;
-		out_b[nb] = (unsigned int)(carry_s >> 32);
+		out_a[nb] = (unsigned int)carry;
+		if (DUAL)
+			out_b[nb] = (unsigned int)(carry >> 32);
 	}
 }
 
@@ -410,7 +399,7 @@ cudaError_t launch_sort(const ResolveBuffers &rb, const CandRec *cands, const Co
 	e = cudaMemsetAsync(rb.cur, 0, (size_t)(nb + 1) * sizeof(unsigned int), st);
 	if (e != cudaSuccess) return e;
 	k_hist<<<296, 256, 0, st>>>(cands, ctr, cap, n0, rb.cnt);
-	k_scan_buckets<<<1, kScanThreads, 0, st>>>(rb.cnt, rb.off, nb);
+	k_scan_buckets_t<false><<<1, kScanThreads, 0, st>>>(rb.cnt, nullptr, rb.off, nullptr, nb);
 	k_scatter<<<296, 256, 0, st>>>(cands, ctr, cap, n0, rb.off, rb.cur, rb.sorted);
 	k_bucket_sort<<<(nb + 127) / 128, 128, 0, st>>>(rb.sorted, rb.off, nb);
 	return cudaGetLastError();
@@ -427,7 +416,7 @@ cudaError_t launch_resolve(const ResolveBuffers &rb, const CandRec *cands, const
 	k_snapshot<<<1, 1, 0, st>>>(state, slot);
 	k_greedy<<<296, 256, 0, st>>>(rb.sorted, rb.off, nb, rb.accept, state, slot);
 	k_bucket_stats<<<(nb + 127) / 128, 128, 0, st>>>(rb.sorted, rb.accept, rb.off, nb, rb.bacc, rb.bdrift);
-	k_scan_buckets2<<<1, kScanThreads, 0, st>>>(rb.bacc, rb.bdrift, rb.bacc_x, rb.bdrift_x, nb);
+	k_scan_buckets_t<true><<<1, kScanThreads, 0, st>>>(rb.bacc, rb.bdrift, rb.bacc_x, rb.bdrift_x, nb);
 	k_compact<<<(nb + 127) / 128, 128, 0, st>>>(rb.sorted, rb.accept, rb.off, nb, rb.bacc_x, rb.bdrift_x, out, out_cap,
 	                                             state, slot);
 	return cudaGetLastError();
