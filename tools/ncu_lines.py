@@ -28,6 +28,7 @@ for f, lines in files.items():
         marks = [("helpers+setup", 1), ("span fetch", find("fetch a span")), ("stage 1", find("stage 1: envelope")),
                  ("stage 2", find("stage 2: decision bits")), ("stage 3", find("stage 3: preamble AND")),
                  ("stage 4", find("stage 4: slice + CRC")), ("tail", find("q_fir += 32"))]
+        marks.sort(key=lambda m: m[1])   # stage 3 sits in front of stage 2 in the source
         for (name, lo), (_, hi) in zip(marks, marks[1:] + [("", 10 ** 9)]):
             a = sum(v[0] for l, v in lines.items() if lo <= l < hi)
             b = sum(v[1] for l, v in lines.items() if lo <= l < hi)
