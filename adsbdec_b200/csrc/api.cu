@@ -193,6 +193,7 @@ struct adsbdec_b200 {
 	Resolver *res = nullptr;
 	std::vector<adsbdec_b200_frame_t> frames;
 	size_t emitted = 0;
+	size_t counted = 0;      // frames[0 .. counted) are in stat_ok already (the resolver counts while it copies)
 	uint32_t stat_ok[3] = {0, 0, 0};
 	adsbdec_b200_sink_fn sink = nullptr;
 	void *sink_user = nullptr;
@@ -449,10 +450,17 @@ int enqueue_job(adsbdec_b200 *h, int s, bool force_generic)
 
 void emit_new_frames(adsbdec_b200 *h)
 {
+	if (!h->sink && h->counted == h->frames.size()) {
+		h->emitted = h->frames.size();  // nothing to call, nothing to count
+		return;
+	}
 	for (; h->emitted < h->frames.size(); h->emitted++) {
 		const adsbdec_b200_frame_t &f = h->frames[h->emitted];
-		const int df = f.bytes[0] >> 3;
-		h->stat_ok[df == 11 ? 0 : df == 17 ? 1 : 2]++;  // valid.c:53, :75
+		if (h->emitted >= h->counted) {
+			const int df = f.bytes[0] >> 3;
+			h->stat_ok[df == 11 ? 0 : df == 17 ? 1 : 2]++;  // valid.c:53, :75
+			h->counted = h->emitted + 1;
+		}
 		if (h->sink)
 			h->sink(f.bytes, f.len, f.ts, f.pw, h->sink_user);
 	}
@@ -557,7 +565,8 @@ int complete_job(adsbdec_b200 *h, int s)
 	// is left is the deqframe call schedule (air.c:94-99), which decides how far the scan has come.
 	const double t2 = now_ms();
 	h->res->feed_frames(reinterpret_cast<const adsbdec_b200_frame_t *>(h->h_cands[s]), n_res,
-	                    (uint64_t)std::max<int64_t>(j.n1, 0), (uint64_t)j.total_out, h->frames);
+	                    (uint64_t)std::max<int64_t>(j.n1, 0), (uint64_t)j.total_out, h->frames, h->stat_ok);
+	h->counted = h->frames.size();
 	const double t3 = now_ms();
 	if (scanned) {
 		RC(stats_pass(h, s, true));
@@ -885,6 +894,7 @@ int adsbdec_b200_reset(adsbdec_b200_t *h, uint64_t start_sample)
 	h->res = new Resolver(h->cfg.emulate_reference_tail != 0);
 	h->frames.clear();  // keeps its capacity
 	h->emitted = 0;
+	h->counted = 0;
 	for (int i = 0; i < 3; i++)
 		h->stat_ok[i] = 0;
 	CU(cudaMemset(h->d_stats, 0, sizeof(StreamStats)));
@@ -1060,7 +1070,8 @@ int adsbdec_b200_finish(adsbdec_b200_t *h)
 	if (h->dev[0] && (h->pin_fill > 0 || h->dev_fill > 0))
 		RC(flush_batch(h));
 	RC(complete_all(h));
-	h->res->finish(h->frames);
+	h->res->finish(h->frames);  // the stream path only ever feeds stamped frames: counted as they are accepted
+	h->counted = h->frames.size();
 	RC(stats_pass(h, h->last_slot, false));  // pending tries against the final scan end
 	emit_new_frames(h);
 	CU(cudaStreamSynchronize(h->st));
@@ -1205,6 +1216,7 @@ void adsbdec_b200_clear_frames(adsbdec_b200_t *h)
 	if (h->emitted == h->frames.size() && h->frames.size() > 1) {
 		h->frames.erase(h->frames.begin(), h->frames.end() - 1);
 		h->emitted = h->frames.size();
+		h->counted = h->frames.size();
 	}
 }
 

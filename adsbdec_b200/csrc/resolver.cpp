@@ -20,8 +20,13 @@ void Resolver::scan_to(uint64_t cutoff, std::vector<adsbdec_b200_frame_t> &accep
 		const adsbdec_b200_frame_t *f = src == 0 ? fpending_.data() : fin_;
 		size_t &i = src == 0 ? fhead_ : fin_i_;
 		const size_t n = src == 0 ? fpending_.size() : fin_n_, i0 = i;
-		while (i < n && f[i].n < cutoff)
+		while (i < n && f[i].n < cutoff) {
+			if (ok_) {
+				const int df = f[i].bytes[0] >> 3;
+				ok_[df == 11 ? 0 : df == 17 ? 1 : 2]++;
+			}
 			i++;
+		}
 		if (i > i0) {
 			accepted.insert(accepted.end(), f + i0, f + i);
 			pos = f[i - 1].n + (f[i - 1].len == 7 ? kSkipShort : kSkipLong);
@@ -104,8 +109,9 @@ void Resolver::feed(const adsbdec_b200_candidate_t *c, size_t count, uint64_t sc
 }
 
 void Resolver::feed_frames(const adsbdec_b200_frame_t *f, size_t count, uint64_t scanned_upto,
-                           uint64_t total_out, std::vector<adsbdec_b200_frame_t> &accepted)
+                           uint64_t total_out, std::vector<adsbdec_b200_frame_t> &accepted, uint32_t ok[3])
 {
+	ok_ = ok;
 	if (fhead_ == fpending_.size()) {
 		fpending_.clear();
 		fhead_ = 0;

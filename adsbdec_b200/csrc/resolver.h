@@ -27,8 +27,9 @@ public:
 	          std::vector<adsbdec_b200_frame_t> &accepted);
 	// The same for frames the GPU has already put through the greedy rule and stamped (kernels_resolve.cu):
 	// only the deqframe call schedule is left, which decides how far the scan has come.
+	// ok[0..2] += accepted DF11 / DF17 / DF18 frames (valid.c:53, :75), counted while they are copied.
 	void feed_frames(const adsbdec_b200_frame_t *f, size_t count, uint64_t scanned_upto, uint64_t total_out,
-	                 std::vector<adsbdec_b200_frame_t> &accepted);
+	                 std::vector<adsbdec_b200_frame_t> &accepted, uint32_t ok[3]);
 	void finish(std::vector<adsbdec_b200_frame_t> &accepted);
 
 	// Offsets below this have been visited (or skipped) by the emulated scan.
@@ -54,6 +55,7 @@ private:
 	size_t fhead_ = 0;
 	const adsbdec_b200_frame_t *fin_ = nullptr;
 	size_t fin_n_ = 0, fin_i_ = 0;
+	uint32_t *ok_ = nullptr;  // where scan_to counts the stamped frames it accepts
 };
 
 }  // namespace adsb
