@@ -31,10 +31,17 @@
 //                B[n] = a[n] > a[n+5]      (PPM bit decision)
 //              transposed inside 8-lane groups (8 runs of 28 = 7 words of 32) into bit arrays;
 //   * stage 3 (gate): word-parallel: preamble = P[n] & Q[n+30]; DF gate = five bits of B at stride
-//              10; survivors go to a small list;
-//   * stage 4 (slice+CRC): four lanes per survivor; a lane pulls its 7 nibbles of the frame out of B
-//              (one funnel shift + one multiply each), looks their syndromes up in a 28x16 table and
-//              the four lanes XOR-reduce; syndrome 0 -> the frame bits go to the candidate list.
+//              10; survivors go to a small list.  It lags 1472 offsets behind the FIR front, so in
+//              the code it runs in FRONT of stage 2 of the same sub-block (its words are one
+//              sub-block old) and needs no barrier of its own;
+//   * stage 4 (slice+CRC): four lanes per survivor; a lane loads the ten B words that hold its 28
+//              frame bits once, shifts them so that its first bit leads, pulls 7 nibbles out at
+//              constant positions (funnel shift + multiply-gather), looks their syndromes up in a
+//              28x16 table and the four lanes XOR-reduce; syndrome 0 -> the frame bits go to the
+//              candidate list.  (REPAIR instantiation only: a non-zero syndrome is looked up in
+//              repair.h's table - an extension, off by default.)
+// Three __syncwarp per sub-block: before the raw stage is refilled, after the envelope, after the
+// bit arrays.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
