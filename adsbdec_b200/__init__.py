@@ -28,7 +28,7 @@ EXPORTS = [
     "adsbdec_b200_default_config", "adsbdec_b200_open", "adsbdec_b200_close", "adsbdec_b200_reset",
     "adsbdec_b200_set_sink",
     "adsbdec_b200_push", "adsbdec_b200_push_device", "adsbdec_b200_finish", "adsbdec_b200_decode_file",
-    "adsbdec_b200_flush", "adsbdec_b200_poll",
+    "adsbdec_b200_flush", "adsbdec_b200_poll", "adsbdec_b200_push_packed12",
     "adsbdec_b200_stats", "adsbdec_b200_num_frames", "adsbdec_b200_frames", "adsbdec_b200_clear_frames",
     "adsbdec_b200_kernel_time", "adsbdec_b200_telemetry", "adsbdec_b200_fused_time", "adsbdec_b200_format_packet",
     "adsbdec_b200_envelope", "adsbdec_b200_resolver_new", "adsbdec_b200_resolver_free",
@@ -114,6 +114,7 @@ def lib():
         L.adsbdec_b200_push_device.argtypes = [vp, vp, C.c_size_t]
         L.adsbdec_b200_finish.argtypes = [vp]
         L.adsbdec_b200_flush.argtypes = [vp]
+        L.adsbdec_b200_push_packed12.argtypes = [vp, vp, C.c_size_t]
         L.adsbdec_b200_poll.argtypes = [vp]
         L.adsbdec_b200_decode_file.argtypes = [vp, C.c_char_p]
         L.adsbdec_b200_stats.argtypes = [vp, u32p, u32p]
@@ -207,6 +208,12 @@ class Decoder:
     def push(self, samples: np.ndarray) -> None:
         a = np.ascontiguousarray(samples, dtype="<u2")
         _check(lib().adsbdec_b200_push(self._h, a.ctypes.data, a.size))
+
+    def push_packed12(self, packed: np.ndarray, n_samples: int | None = None) -> None:
+        """Samples packed 8 to 12 bytes (see pack12); a quarter less PCIe traffic than push()."""
+        a = np.ascontiguousarray(packed).view(np.uint8)
+        n = a.size // 3 * 2 if n_samples is None else n_samples
+        _check(lib().adsbdec_b200_push_packed12(self._h, a.ctypes.data, n))
 
     def push_device(self, dev_ptr: int, n_samples: int) -> None:
         _check(lib().adsbdec_b200_push_device(self._h, C.c_void_p(dev_ptr), n_samples))
@@ -322,6 +329,35 @@ class Decoder:
             self.close()
         except Exception:
             pass
+
+
+def pack12(samples: np.ndarray) -> np.ndarray:
+    """12-bit samples (u16, < 4096, a multiple of 8 of them) packed the way the airspy does with packing on
+    (libairspy unpack_samples): the 96 bits of three little-endian 32-bit words, most significant first, are
+    eight samples.  Returns the words as a uint32 array."""
+    s = np.ascontiguousarray(samples, dtype="<u2").astype(np.uint32).reshape(-1, 8)
+    if (s > 0xFFF).any():
+        raise ValueError("samples do not fit 12 bits")
+    w = np.empty((s.shape[0], 3), dtype="<u4")
+    w[:, 0] = (s[:, 0] << 20) | (s[:, 1] << 8) | (s[:, 2] >> 4)
+    w[:, 1] = ((s[:, 2] & 0xF) << 28) | (s[:, 3] << 16) | (s[:, 4] << 4) | (s[:, 5] >> 8)
+    w[:, 2] = ((s[:, 5] & 0xFF) << 24) | (s[:, 6] << 12) | s[:, 7]
+    return w.reshape(-1)
+
+
+def unpack12(words: np.ndarray) -> np.ndarray:
+    """Inverse of pack12 on the host (tests)."""
+    w = np.ascontiguousarray(words, dtype="<u4").reshape(-1, 3)
+    s = np.empty((w.shape[0], 8), dtype="<u2")
+    s[:, 0] = w[:, 0] >> 20
+    s[:, 1] = (w[:, 0] >> 8) & 0xFFF
+    s[:, 2] = ((w[:, 0] & 0xFF) << 4) | (w[:, 1] >> 28)
+    s[:, 3] = (w[:, 1] >> 16) & 0xFFF
+    s[:, 4] = (w[:, 1] >> 4) & 0xFFF
+    s[:, 5] = ((w[:, 1] & 0xF) << 8) | (w[:, 2] >> 24)
+    s[:, 6] = (w[:, 2] >> 12) & 0xFFF
+    s[:, 7] = w[:, 2] & 0xFFF
+    return s.reshape(-1)
 
 
 def decode(samples: np.ndarray, **kw) -> "Decoder":

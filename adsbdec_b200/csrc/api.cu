@@ -72,6 +72,7 @@ constexpr int64_t kAmpChunk = 8ll << 20;   // generic path: offsets per envelope
 constexpr int64_t kMinFused = 1 << 16;     // ranges smaller than this use the generic kernels
 constexpr int64_t kStageSlice = 4ll << 20; // pageable pushes are staged and uploaded in slices
 constexpr int64_t kBulkRead = 16ll << 20;  // decode_file: samples fetched per parallel read
+constexpr int64_t kPackSlice = 32ll << 20; // push_packed12: samples uploaded and unpacked per step
 constexpr unsigned long long kSpecCands = 1ull << 15;  // results copied back speculatively, at least
 constexpr unsigned long long kPendCap = 1ull << 18;
 constexpr int kSlots = 2;
@@ -205,6 +206,10 @@ struct adsbdec_b200 {
 	adsbdec_b200_telemetry_t tel = {};
 	std::unique_ptr<ReadPool> readers;  // decode_file helpers, started on first use
 	unsigned long long *d_fix = nullptr;  // repair.h syndrome table (extension; null when off)
+	// packed 12-bit input: device scratch for one slice, two pinned staging buffers for pageable callers
+	unsigned char *d_pk = nullptr, *h_pk[2] = {nullptr, nullptr};
+	cudaEvent_t ev_pk[2] = {nullptr, nullptr};
+	int pk_i = 0;
 	int fix_level = 0;
 
 	// parity taps of the fused kernel (adsbdec_b200_debug_fused)
@@ -854,6 +859,11 @@ void adsbdec_b200_close(adsbdec_b200_t *h)
 		if (h->ev_done[s]) cudaEventDestroy(h->ev_done[s]);
 	}
 	if (h->d_fix) cudaFree(h->d_fix);
+	if (h->d_pk) cudaFree(h->d_pk);
+	for (int i = 0; i < 2; i++) {
+		if (h->h_pk[i]) cudaFreeHost(h->h_pk[i]);
+		if (h->ev_pk[i]) cudaEventDestroy(h->ev_pk[i]);
+	}
 	if (h->d_stats) cudaFree(h->d_stats);
 	if (h->d_state) cudaFree(h->d_state);
 	if (h->h_stats) cudaFreeHost(h->h_stats);
@@ -952,6 +962,69 @@ int adsbdec_b200_push(adsbdec_b200_t *h, const uint16_t *samples, size_t n)
 			if (h->pin_fill >= kStageSlice)
 				RC(drain_pinned(h));
 		}
+		h->pushed += (int64_t)take;
+		done += take;
+	}
+	if (direct) {
+		const double t0 = now_ms();
+		CU(cudaStreamSynchronize(h->st_copy));  // the caller may reuse its buffer on return
+		h->tel.wait_upload_ms += now_ms() - t0;
+	}
+	return 0;
+}
+
+int adsbdec_b200_push_packed12(adsbdec_b200_t *h, const void *packed, size_t n)
+{
+	if (!h || (!packed && n))
+		return fail(ADSB_B200_EINVAL, "null argument");
+	if (n % 8)
+		return fail(ADSB_B200_EINVAL, "packed pushes come in groups of 8 samples (12 bytes)");
+	if (((uintptr_t)packed) % 4)
+		return fail(ADSB_B200_EINVAL, "packed samples must be 4-byte aligned");
+	if (h->finished)
+		return fail(ADSB_B200_ESTATE, "push after finish");
+	if (n == 0)
+		return 0;
+	CU(cudaSetDevice(h->device));
+	const bool direct = is_pinned_host(packed);
+	RC(ensure_batch_buffers(h, false));
+	const int64_t slice = std::min<int64_t>(kPackSlice, align_down(h->batch, 8));
+	if (!h->d_pk)
+		CU(cudaMalloc(&h->d_pk, (size_t)slice / 2 * 3));
+	for (int i = 0; i < 2 && !direct; i++) {
+		if (!h->h_pk[i])
+			CU(cudaMallocHost(&h->h_pk[i], (size_t)slice / 2 * 3));
+		if (!h->ev_pk[i])
+			CU(cudaEventCreateWithFlags(&h->ev_pk[i], cudaEventDisableTiming));
+	}
+	const unsigned char *src = static_cast<const unsigned char *>(packed);
+	size_t done = 0;
+	while (done < n) {
+		const int64_t room = align_down(batch_room(h), 8);
+		if (room <= 0) {
+			RC(flush_batch(h));
+			continue;
+		}
+		RC(drain_pinned(h));  // earlier 16-bit pushes of this window go first
+		const size_t take = (size_t)std::min<int64_t>(std::min<int64_t>(room, slice), (int64_t)(n - done));
+		const size_t bytes = take / 2 * 3;
+		const void *from = src + done / 2 * 3;
+		if (!direct) {
+			const int i = h->pk_i;
+			CU(cudaEventSynchronize(h->ev_pk[i]));  // the upload that last used this staging buffer
+			memcpy(h->h_pk[i], from, bytes);
+			from = h->h_pk[i];
+		}
+		// copy and unpack on the upload stream, in order: the scratch buffer is free again when the next
+		// slice's copy starts, and the scan waits for this stream anyway
+		CU(cudaMemcpyAsync(h->d_pk, from, bytes, cudaMemcpyHostToDevice, h->st_copy));
+		if (!direct) {
+			CU(cudaEventRecord(h->ev_pk[h->pk_i], h->st_copy));
+			h->pk_i ^= 1;
+		}
+		CU(launch_unpack12(h->d_pk, h->dev[h->cur] + h->win_off + h->dev_fill, (long long)take, h->st_copy));
+		h->launches += 1;
+		h->dev_fill += (int64_t)take;
 		h->pushed += (int64_t)take;
 		done += take;
 	}

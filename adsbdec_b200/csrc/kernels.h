@@ -21,6 +21,10 @@ cudaError_t launch_scan_generic(const float *amp, long long j_amp0, long long n0
                                 unsigned long long try_cap, Counters *ctr, const unsigned long long *fix_tab,
                                 int fix_level, cudaStream_t st);
 
+// Packed 12-bit samples (libairspy layout, 8 samples per 12 bytes) -> u16 samples.  n_samples % 8 == 0,
+// `packed` 4-byte and `out` 8-byte aligned.
+cudaError_t launch_unpack12(const void *packed, uint16_t *out, long long n_samples, cudaStream_t st);
+
 // ---- on-GPU ordering and greedy resolve (kernels_resolve.cu) ----------------
 
 struct ResolveState {        // per stream: where the sequential scan stands (demod.c:128, :134)

@@ -223,6 +223,25 @@ __global__ void k_scan_generic(const float *__restrict__ amp, long long j_amp0, 
 	cands[k] = r;
 }
 
+// ---- packed 12-bit input -------------------------------------
+// The airspy can deliver its 12-bit samples packed (the reference leaves that off, air.c:128-152):
+// three 32-bit little-endian words hold eight samples, most significant bits first - the layout of
+// libairspy's unpack_samples (airspy.c; not vendored in the reference).  One thread per group:
+// 12 bytes in, 16 bytes out, straight into the sample window the scan kernels read.
+__global__ void k_unpack12(const uint32_t *__restrict__ in, uint16_t *__restrict__ out, long long groups)
+{
+	for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < groups;
+	     g += (long long)gridDim.x * blockDim.x) {
+		const uint32_t w0 = in[3 * g], w1 = in[3 * g + 1], w2 = in[3 * g + 2];
+		const uint32_t s0 = w0 >> 20, s1 = (w0 >> 8) & 0xFFFu, s2 = ((w0 & 0xFFu) << 4) | (w1 >> 28);
+		const uint32_t s3 = (w1 >> 16) & 0xFFFu, s4 = (w1 >> 4) & 0xFFFu, s5 = ((w1 & 0xFu) << 8) | (w2 >> 24);
+		const uint32_t s6 = (w2 >> 12) & 0xFFFu, s7 = w2 & 0xFFFu;
+		uint2 *o = reinterpret_cast<uint2 *>(out + 8 * g);  // the window keeps pushes 8-byte aligned
+		o[0] = make_uint2(s0 | (s1 << 16), s2 | (s3 << 16));
+		o[1] = make_uint2(s4 | (s5 << 16), s6 | (s7 << 16));
+	}
+}
+
 // ---- launch wrappers -----------------------------------------------------
 
 cudaError_t launch_envelope_generic(const uint16_t *raw, long long u_raw0, unsigned long long origin,
@@ -253,6 +272,18 @@ cudaError_t launch_scan_generic(const float *amp, long long j_amp0, long long n0
 	const int bs = 256;
 	k_scan_generic<<<(unsigned)((count + bs - 1) / bs), bs, 0, st>>>(
 	    amp, j_amp0, n0, count, accept_df18, want_tries, cands, cand_cap, tries, try_cap, ctr, fix_tab, fix_level);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_unpack12(const void *packed, uint16_t *out, long long n_samples, cudaStream_t st)
+{
+	const long long groups = n_samples / 8;
+	if (groups <= 0)
+		return cudaSuccess;
+	const int bs = 256;
+	const long long want = (groups + bs - 1) / bs;
+	k_unpack12<<<(unsigned)(want < 148 * 16 ? want : 148 * 16), bs, 0, st>>>(
+	    static_cast<const uint32_t *>(packed), out, groups);
 	return cudaGetLastError();
 }
 

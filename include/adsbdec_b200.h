@@ -110,6 +110,14 @@ int adsbdec_b200_set_sink(adsbdec_b200_t *h, adsbdec_b200_sink_fn fn, void *user
  * four and over-reads otherwise, air.c:59-82; decode_file emulates that case). */
 int adsbdec_b200_push(adsbdec_b200_t *h, const uint16_t *samples, size_t n);
 
+/* Same stream, other wire format: 12-bit samples packed eight to twelve bytes, the way the
+ * airspy delivers them with packing on (the reference leaves it off, air.c:128-152; layout of libairspy's
+ * unpack_samples: three little-endian 32-bit words, most significant bits first).  A quarter less to move
+ * over PCIe; unpacked on the GPU into the same sample window, so everything behind it is unchanged.
+ * `packed` is HOST memory, 4-byte aligned; n counts SAMPLES and must be a multiple of 8.  May be mixed
+ * with adsbdec_b200_push() on one stream. */
+int adsbdec_b200_push_packed12(adsbdec_b200_t *h, const void *packed, size_t n);
+
 /* Same, with the samples already in DEVICE memory of cfg->device.  The pointer
  * must stay valid until the call returns. */
 int adsbdec_b200_push_device(adsbdec_b200_t *h, const void *dev_samples, size_t n);

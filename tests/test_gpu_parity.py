@@ -145,6 +145,38 @@ def test_live_source_flush_and_poll(adsb, oracle, kernel):
     d.close()
 
 
+@pytest.mark.parametrize("kernel", [1, 0], ids=["generic", "fused"])
+def test_packed12_input_is_the_same_stream(adsb, oracle, kernel):
+    """the airspy's packed 12-bit wire format (8 samples in 12 bytes), unpacked on the GPU into
+    the same sample window.  Whole capture, pieces, and mixed with 16-bit pushes: always the oracle's output."""
+    cap = capture_basic(seed=72, seconds=0.4, n_frames=150)
+    ref = oracle.decode(cap.samples)
+    n = cap.samples.size - cap.samples.size % 8
+    words = adsb.pack12(cap.samples[:n])
+    d = adsb.Decoder(kernel=kernel, batch_samples=1 << 20)
+    d.push_packed12(words)
+    d.push(cap.samples[n:])
+    d.finish()
+    assert frames_key(d.frames) == frames_key(ref.frames) and d.stats() == (ref.tried, ref.ok)
+    rng = np.random.default_rng(9)
+    d.reset()
+    pos = 0
+    while pos < n:
+        k = min(int(rng.integers(1, 100000)) * 8, n - pos)
+        if rng.integers(0, 2):
+            d.push_packed12(words[pos // 8 * 3:(pos + k) // 8 * 3])
+        else:
+            d.push(cap.samples[pos:pos + k])
+        pos += k
+    d.push(cap.samples[n:])
+    d.finish()
+    assert frames_key(d.frames) == frames_key(ref.frames) and d.stats() == (ref.tried, ref.ok)
+    with pytest.raises(adsb.AdsbError):
+        d.reset()
+        d.push_packed12(words[:3], 4)
+    d.close()
+
+
 def test_push_rejects_ragged_length(adsb):
     d = adsb.Decoder()
     with pytest.raises(adsb.AdsbError):

@@ -221,3 +221,16 @@ def test_two_rank_gloo_chunk_merge(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)],
                        capture_output=True, text=True, env=env, timeout=300)
     assert "RESULT True" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_pack12_layout_and_roundtrip(adsb):
+    """The packed wire format of adsbdec_b200_push_packed12: 96 bits of three little-endian words, most
+    significant first, are eight 12-bit samples (libairspy's unpack_samples)."""
+    s = np.array([0xABC, 0x123, 0xFED, 0x001, 0x800, 0x7FF, 0x000, 0xFFF], dtype="<u2")
+    w = adsb.pack12(s)
+    assert w.dtype == np.dtype("<u4") and w.tolist() == [0xABC123FE, 0xD0018007, 0xFF000FFF]
+    rng = np.random.default_rng(3)
+    t = rng.integers(0, 4096, 8 * 1000).astype("<u2")
+    assert np.array_equal(adsb.unpack12(adsb.pack12(t)), t)
+    with pytest.raises(ValueError):
+        adsb.pack12(np.full(8, 4096, dtype="<u2"))
