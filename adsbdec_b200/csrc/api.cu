@@ -249,6 +249,19 @@ int alloc_slot_outputs(adsbdec_b200 *h, int s, unsigned long long cand_cap, unsi
 	return 0;
 }
 
+// Lists of an idle slot sized up front for a job of `offsets` offsets (dense traffic: ~0.1 % of the offsets
+// are CRC-valid candidates, ~2.6 % pass the gate), so that a big job does not start with a redo or two.
+int presize_lists(adsbdec_b200 *h, int s, int64_t offsets)
+{
+	const unsigned long long cc = std::max<unsigned long long>(h->cand_cap[s], (unsigned long long)offsets / 256);
+	const unsigned long long tc =
+	    h->cfg.collect_stats ? std::max<unsigned long long>(h->try_cap[s], (unsigned long long)offsets / 24) : h->try_cap[s];
+	if (cc == h->cand_cap[s] && tc == h->try_cap[s])
+		return 0;
+	CU(cudaStreamSynchronize(h->st));
+	return alloc_slot_outputs(h, s, cc, tc);
+}
+
 int ensure_buckets(adsbdec_b200 *h, int s, int nb)
 {
 	if (nb + 1 <= h->nb_cap[s])
@@ -1096,6 +1109,9 @@ int adsbdec_b200_push_device(adsbdec_b200_t *h, const void *dev_samples, size_t 
 	if (n_jobs < 2 && total >= 2 * std::max(h->batch, kDeviceJobMin))
 		n_jobs = 2;
 	const int64_t per = align_down((total + n_jobs - 1) / n_jobs + 7, 8);
+	if (piece_u0 == 0 && !h->job[0].active && !h->job[1].active)  // a fresh stream: nothing refers to the lists yet
+		for (int s = 0; s < kSlots; s++)
+			RC(presize_lists(h, s, per / 2));
 	for (int64_t end = piece_u0; end < piece_u1;) {
 		end = std::min(piece_u1, end + per);
 		// window: from the FIR history of the next owned offset to `end`, inside the caller's memory
@@ -1395,6 +1411,7 @@ int64_t adsbdec_b200_chunk_candidates(adsbdec_b200_t *h, const void *dev_samples
 	j.origin = start_sample;
 	j.resolve = false;
 	j.active = true;
+	RC(presize_lists(h, s, j.n1 - j.n0));
 	RC(enqueue_job(h, s, false));
 	RC(complete_job(h, s));
 	if (h->cand_tmp.size() > cap)
