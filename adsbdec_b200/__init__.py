@@ -28,7 +28,7 @@ EXPORTS = [
     "adsbdec_b200_default_config", "adsbdec_b200_open", "adsbdec_b200_close", "adsbdec_b200_reset",
     "adsbdec_b200_set_sink",
     "adsbdec_b200_push", "adsbdec_b200_push_device", "adsbdec_b200_finish", "adsbdec_b200_decode_file",
-    "adsbdec_b200_flush", "adsbdec_b200_poll", "adsbdec_b200_push_packed12",
+    "adsbdec_b200_flush", "adsbdec_b200_poll", "adsbdec_b200_push_packed12", "adsbdec_b200_repair_lookup",
     "adsbdec_b200_stats", "adsbdec_b200_num_frames", "adsbdec_b200_frames", "adsbdec_b200_clear_frames",
     "adsbdec_b200_kernel_time", "adsbdec_b200_telemetry", "adsbdec_b200_fused_time", "adsbdec_b200_format_packet",
     "adsbdec_b200_envelope", "adsbdec_b200_resolver_new", "adsbdec_b200_resolver_free",
@@ -114,6 +114,8 @@ def lib():
         L.adsbdec_b200_push_device.argtypes = [vp, vp, C.c_size_t]
         L.adsbdec_b200_finish.argtypes = [vp]
         L.adsbdec_b200_flush.argtypes = [vp]
+        L.adsbdec_b200_repair_lookup.argtypes = [C.c_uint32]
+        L.adsbdec_b200_repair_lookup.restype = C.c_int
         L.adsbdec_b200_push_packed12.argtypes = [vp, vp, C.c_size_t]
         L.adsbdec_b200_poll.argtypes = [vp]
         L.adsbdec_b200_decode_file.argtypes = [vp, C.c_char_p]
@@ -329,6 +331,11 @@ class Decoder:
             self.close()
         except Exception:
             pass
+
+
+def repair_lookup(syndrome: int) -> int:
+    """Bits the repair extension flips for this CRC syndrome: (first << 8) | second, 0xFF = none; -1 if unknown."""
+    return int(lib().adsbdec_b200_repair_lookup(syndrome))
 
 
 def pack12(samples: np.ndarray) -> np.ndarray:

@@ -1125,6 +1125,17 @@ int adsbdec_b200_push_device(adsbdec_b200_t *h, const void *dev_samples, size_t 
 	return 0;
 }
 
+int adsbdec_b200_repair_lookup(uint32_t syndrome)
+{
+	static std::vector<unsigned long long> tab;
+	if (tab.empty()) {
+		tab.resize(kFixSlots);
+		fix_build_table(tab.data());
+	}
+	const uint32_t e = fix_lookup(tab.data(), syndrome & 0xFFFFFFu);
+	return e == kFixNone ? -1 : (int)e;
+}
+
 int adsbdec_b200_flush(adsbdec_b200_t *h)
 {
 	if (!h)

@@ -234,6 +234,12 @@ int64_t adsbdec_b200_chunk_candidates(adsbdec_b200_t *h, const void *dev_samples
                                       adsbdec_b200_candidate_t *out, size_t cap,
                                       uint32_t tries_out[3]);
 
+/* EXTENSION (see reserved[3]): which bits does the repair table flip for this 24-bit CRC syndrome?
+ * Returns (first << 8) | second with positions counted from the first bit of a 112-bit frame (a 56-bit
+ * frame is positions 56..111), second = 0xFF for a single bit, or -1 if no pattern of <= 2 bits has this
+ * syndrome.  Host-only (no GPU needed): lets the table be checked against brute force. */
+int adsbdec_b200_repair_lookup(uint32_t syndrome);
+
 const char *adsbdec_b200_last_error(void);
 const char *adsbdec_b200_version(void);
 

@@ -234,3 +234,33 @@ def test_pack12_layout_and_roundtrip(adsb):
     assert np.array_equal(adsb.unpack12(adsb.pack12(t)), t)
     with pytest.raises(ValueError):
         adsb.pack12(np.full(8, 4096, dtype="<u2"))
+
+
+def test_repair_table_against_brute_force(adsb, oracle):
+    """EXTENSION: every pattern of one or two flipped bits in 112 has its own syndrome, and the library's hash
+    table (host-built, the same one the kernels probe) returns exactly that pattern - checked with the
+    modulator's bitwise CRC, which shares no code with it."""
+    from adsbdec_b200.modulator import crc24
+
+    def syn(bits):
+        m = bytearray(14)
+        for b in bits:
+            m[b >> 3] ^= 0x80 >> (b & 7)
+        return crc24(bytes(m[:11])) ^ int.from_bytes(m[11:], "big")
+    one = [syn([b]) for b in range(112)]
+    seen = {}
+    for a in range(112):
+        assert adsb.repair_lookup(one[a]) == (a << 8) | 0xFF
+        seen[one[a]] = (a,)
+        for b in range(a + 1, 112):
+            s = one[a] ^ one[b]
+            assert s not in seen, "two patterns share a syndrome"
+            seen[s] = (a, b)
+            assert adsb.repair_lookup(s) == (a << 8) | b
+    assert len(seen) == 112 + 112 * 111 // 2
+    assert syn([3, 77]) == one[3] ^ one[77]          # linearity, as the table assumes
+    assert adsb.repair_lookup(0) == -1
+    rng = np.random.default_rng(5)
+    for s in rng.integers(1, 1 << 24, 2000):
+        if int(s) not in seen:
+            assert adsb.repair_lookup(int(s)) == -1
