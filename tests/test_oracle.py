@@ -178,3 +178,23 @@ def test_oracle_repair_extension(oracle):
     b = oracle.decode(cap2.samples, repair=2)
     assert sum(x == 2 for x in b.fixed) > 15 and not any(x == 2 for x in a.fixed)
     assert all(len(f.data) == 14 for f, x in zip(b.frames, b.fixed) if x == 2)
+
+
+def test_oracle_empty_and_tiny_inputs(oracle, tmp_path):
+    """air.c:233-244: an empty file ends the read loop at once; anything shorter than one deqframe flush
+    (40 980 envelope samples, air.c:94) is never scanned at all."""
+    import numpy as np
+    assert oracle.decode(np.zeros(0, dtype="<u2")).frames == []
+    f = tmp_path / "empty.bin"
+    f.write_bytes(b"")
+    r = oracle.decode_file(f)
+    assert r.frames == [] and r.tried == (0, 0, 0) and r.ok == (0, 0, 0)
+    from adsbdec_b200.modulator import synth_capture
+    cap = synth_capture(0.004, 8, snr_db=25, seed=5, pad=0, poisson=False)   # 80 000 samples = 40 000 outputs
+    assert cap.samples.size // 2 < 40980
+    assert oracle.decode(cap.samples).frames == []
+    binary = oracle.ref_binary()
+    if binary is not None:
+        g = tmp_path / "tiny.bin"
+        cap.tofile(g)
+        assert oracle.run_ref(g, binary=binary).stdout == b""
