@@ -1127,11 +1127,11 @@ int adsbdec_b200_push_device(adsbdec_b200_t *h, const void *dev_samples, size_t 
 
 int adsbdec_b200_repair_lookup(uint32_t syndrome)
 {
-	static std::vector<unsigned long long> tab;
-	if (tab.empty()) {
-		tab.resize(kFixSlots);
-		fix_build_table(tab.data());
-	}
+	static const std::vector<unsigned long long> tab = [] {  // built once, thread-safe (C++11 static init)
+		std::vector<unsigned long long> t(kFixSlots);
+		fix_build_table(t.data());
+		return t;
+	}();
 	const uint32_t e = fix_lookup(tab.data(), syndrome & 0xFFFFFFu);
 	return e == kFixNone ? -1 : (int)e;
 }
