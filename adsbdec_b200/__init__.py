@@ -32,7 +32,8 @@ EXPORTS = [
     "adsbdec_b200_stats", "adsbdec_b200_num_frames", "adsbdec_b200_frames", "adsbdec_b200_clear_frames",
     "adsbdec_b200_kernel_time", "adsbdec_b200_telemetry", "adsbdec_b200_fused_time", "adsbdec_b200_format_packet",
     "adsbdec_b200_envelope", "adsbdec_b200_resolver_new", "adsbdec_b200_resolver_free",
-    "adsbdec_b200_resolver_feed", "adsbdec_b200_resolver_finish", "adsbdec_b200_resolver_scan_end",
+    "adsbdec_b200_resolver_feed", "adsbdec_b200_resolver_feed_frames", "adsbdec_b200_resolver_finish",
+    "adsbdec_b200_resolver_scan_end",
     "adsbdec_b200_chunk_candidates", "adsbdec_b200_debug_fused", "adsbdec_b200_last_error",
     "adsbdec_b200_version",
 ]
@@ -136,6 +137,7 @@ def lib():
         L.adsbdec_b200_resolver_free.argtypes = [vp]
         L.adsbdec_b200_resolver_free.restype = None
         L.adsbdec_b200_resolver_feed.argtypes = [vp, vp, C.c_size_t, u64, u64, SINK_FN, vp]
+        L.adsbdec_b200_resolver_feed_frames.argtypes = [vp, vp, C.c_size_t, u64, u64, u32p, SINK_FN, vp]
         L.adsbdec_b200_resolver_finish.argtypes = [vp, SINK_FN, vp]
         L.adsbdec_b200_resolver_scan_end.argtypes = [vp]
         L.adsbdec_b200_resolver_scan_end.restype = u64
@@ -399,6 +401,15 @@ class Resolver:
         c = np.ascontiguousarray(cands, dtype=CAND_DTYPE)
         _check(lib().adsbdec_b200_resolver_feed(self._r, c.ctypes.data, c.size, scanned_upto, total_out,
                                                 self._cb, None))
+
+    def feed_frames(self, frames: np.ndarray, scanned_upto: int, total_out: int):
+        """Frames that already carry the greedy decision and their ts (FRAME_DTYPE): only the deqframe call
+        schedule is applied.  Returns the Ok counts (DF11, DF17, DF18) of what was accepted by this call."""
+        f = np.ascontiguousarray(frames, dtype=FRAME_DTYPE)
+        ok = (C.c_uint32 * 3)()
+        _check(lib().adsbdec_b200_resolver_feed_frames(self._r, f.ctypes.data, f.size, scanned_upto, total_out,
+                                                       ok, self._cb, None))
+        return tuple(ok)
 
     def finish(self) -> None:
         _check(lib().adsbdec_b200_resolver_finish(self._r, self._cb, None))

@@ -1180,7 +1180,7 @@ int adsbdec_b200_finish(adsbdec_b200_t *h)
 	if (h->dev[0] && (h->pin_fill > 0 || h->dev_fill > 0))
 		RC(flush_batch(h));
 	RC(complete_all(h));
-	h->res->finish(h->frames);  // the stream path only ever feeds stamped frames: counted as they are accepted
+	h->res->finish(h->frames, h->stat_ok);  // the stream path only ever feeds stamped frames: counted as they are accepted
 	h->counted = h->frames.size();
 	RC(stats_pass(h, h->last_slot, false));  // pending tries against the final scan end
 	emit_new_frames(h);
@@ -1531,6 +1531,17 @@ int adsbdec_b200_resolver_feed(adsbdec_b200_resolver_t *r, const adsbdec_b200_ca
 	if (!r || (!c && count))
 		return fail(ADSB_B200_EINVAL, "null argument");
 	r->r.feed(c, count, scanned_upto, total_out, r->out);
+	resolver_emit(r, fn, user);
+	return 0;
+}
+
+int adsbdec_b200_resolver_feed_frames(adsbdec_b200_resolver_t *r, const adsbdec_b200_frame_t *f, size_t count,
+                                      uint64_t scanned_upto, uint64_t total_out, uint32_t ok[3],
+                                      adsbdec_b200_sink_fn fn, void *user)
+{
+	if (!r || (!f && count))
+		return fail(ADSB_B200_EINVAL, "null argument");
+	r->r.feed_frames(f, count, scanned_upto, total_out, r->out, ok);
 	resolver_emit(r, fn, user);
 	return 0;
 }

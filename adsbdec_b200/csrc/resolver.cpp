@@ -129,10 +129,12 @@ void Resolver::feed_frames(const adsbdec_b200_frame_t *f, size_t count, uint64_t
 	fpending_.insert(fpending_.end(), f + fin_i_, f + count);
 	fin_ = nullptr;
 	fin_n_ = fin_i_ = 0;
+	ok_ = nullptr;  // the caller's counters are only borrowed for the call
 }
 
-void Resolver::finish(std::vector<adsbdec_b200_frame_t> &accepted)
+void Resolver::finish(std::vector<adsbdec_b200_frame_t> &accepted, uint32_t ok[3])
 {
+	ok_ = ok;
 	run_calls(accepted);
 	if (!emulate_tail_) {
 		// Non-reference mode: scan every offset that has a complete look-ahead.
@@ -146,6 +148,7 @@ void Resolver::finish(std::vector<adsbdec_b200_frame_t> &accepted)
 	head_ = 0;  // the reference drops whatever is left in ampbuff at EOF (air.c:243-244)
 	fpending_.clear();
 	fhead_ = 0;
+	ok_ = nullptr;
 }
 
 }  // namespace adsb

@@ -30,7 +30,8 @@ public:
 	// ok[0..2] += accepted DF11 / DF17 / DF18 frames (valid.c:53, :75), counted while they are copied.
 	void feed_frames(const adsbdec_b200_frame_t *f, size_t count, uint64_t scanned_upto, uint64_t total_out,
 	                 std::vector<adsbdec_b200_frame_t> &accepted, uint32_t ok[3]);
-	void finish(std::vector<adsbdec_b200_frame_t> &accepted);
+	// ok (may be null): counters for the stamped frames still accepted here.
+	void finish(std::vector<adsbdec_b200_frame_t> &accepted, uint32_t ok[3] = nullptr);
 
 	// Offsets below this have been visited (or skipped) by the emulated scan.
 	uint64_t scan_end() const { return scan_end_; }

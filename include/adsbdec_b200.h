@@ -215,6 +215,13 @@ void adsbdec_b200_resolver_free(adsbdec_b200_resolver_t *r);
 int adsbdec_b200_resolver_feed(adsbdec_b200_resolver_t *r, const adsbdec_b200_candidate_t *c,
                                size_t count, uint64_t scanned_upto, uint64_t total_out,
                                adsbdec_b200_sink_fn fn, void *user);
+/* The same schedule over frames that already went through the greedy rule and carry their timestamps -
+ * what the stream decoder feeds itself from kernels_resolve.cu; only the deqframe call schedule (which frames
+ * the reference's scan ever reaches, air.c:94-99) is applied.  ok[0..2] (may be NULL) += accepted DF11 /
+ * DF17 / DF18 frames.  A resolver takes candidates or stamped frames, not both. */
+int adsbdec_b200_resolver_feed_frames(adsbdec_b200_resolver_t *r, const adsbdec_b200_frame_t *f, size_t count,
+                                      uint64_t scanned_upto, uint64_t total_out, uint32_t ok[3],
+                                      adsbdec_b200_sink_fn fn, void *user);
 int adsbdec_b200_resolver_finish(adsbdec_b200_resolver_t *r, adsbdec_b200_sink_fn fn, void *user);
 /* Number of spans accepted so far / copy them ([start, start+skip) pairs). */
 uint64_t adsbdec_b200_resolver_scan_end(const adsbdec_b200_resolver_t *r);

@@ -136,6 +136,46 @@ def test_resolver_reproduces_sequential_scan(adsb, oracle, df18, cut):
     assert tuple(vis) == ref.tried
 
 
+@pytest.mark.parametrize("cut", [0, 40_000, 81_236])
+def test_resolver_stamped_frames_path(adsb, oracle, cut):
+    """What the stream decoder does in production: the GPU applies the greedy rule and the timestamps
+    (kernels_resolve.cu; stated here in a few lines of Python over the all-offsets candidates) and the host
+    resolver only runs the deqframe call schedule over the stamped frames.  Result == the oracle's sequential
+    scan, tail cut-off and Ok counters included, fed whole or in pieces."""
+    cap = capture_basic(seed=33, seconds=0.05, n_frames=70, pad=0)
+    s = cap.samples[:cap.samples.size - cut]
+    ref = oracle.decode(s, accept_df18=True, want_amp=True)
+    cands, _ = all_offset_candidates(ref.amp, True)
+    total_out = ref.amp.size
+    stamped = np.zeros(len(cands), dtype=adsb.FRAME_DTYPE)
+    k, pos, drift = 0, 0, 0
+    for c in cands:                       # demod.c:99, :128, :134 over the sparse list
+        if c["n"] < pos or c["n"] >= total_out - 1200:
+            continue
+        skip = 640 if c["len"] == 7 else 1200
+        stamped[k] = (int(c["n"]) + 1 - drift, int(c["n"]), int(c["pw"]), int(c["len"]), c["bytes"][:14], (0, 0))
+        k, pos, drift = k + 1, int(c["n"]) + skip, drift + skip - 1
+    stamped = stamped[:k]
+    want = [(f.ts, f.pw, f.data) for f in ref.frames]
+    r = adsb.Resolver(True)
+    ok = r.feed_frames(stamped, max(0, total_out - 1200), total_out)
+    r.finish()
+    assert [(f.ts, f.pw, f.data) for f in r.out] == want and len(want) > 15
+    r2 = adsb.Resolver(True)
+    ok2 = np.zeros(3, dtype=np.int64)
+    step = 30_000
+    for upto in range(step, total_out + step, step):
+        upto = min(upto, total_out)
+        scanned = max(0, upto - 1200)
+        part = stamped[(stamped["n"] < scanned) & (stamped["n"] >= max(0, upto - step - 1200))]
+        ok2 += r2.feed_frames(part, scanned, upto)
+    r2.finish()
+    assert [(f.ts, f.pw, f.data) for f in r2.out] == want
+    assert len(stamped) >= len(want)      # the frames behind the last deqframe call were dropped
+    if cut == 0:
+        assert tuple(ok) == ref.ok == tuple(int(x) for x in ok2)
+
+
 def test_resolver_non_emulated_tail_scans_everything(adsb, oracle):
     cap = capture_basic(seed=32, seconds=0.03, n_frames=40, pad=0)
     ref = oracle.decode(cap.samples, want_amp=True)
