@@ -340,17 +340,18 @@ int launch_fused_range(adsbdec_b200 *h, int s, const Job &j, int64_t n0, int64_t
 	if (r < 0)
 		return fail(ADSB_B200_EINVAL, "internal: no FIR phase for shift %d", shift);
 	const int64_t total = n1 - n0;
-	// Span length: a whole number of sub-blocks INCLUDING the look-back tail, so that the last
-	// sub-block of a span is not mostly wasted: per = k*S - (lookback + alignment slack).
-	// A worker is one warp of the fused kernel.  Big ranges get 4 spans per worker (the dynamic
-	// scheduler evens out the tail); small ones at most one span per worker - never "a few more
-	// spans than workers".
+	// A worker is one warp of the fused kernel, and every worker gets exactly ONE span: a span pays
+	// `lookback` offsets of envelope past its end (the look-ahead of its last frames), so long spans
+	// keep that redundancy small (60 s capture in three jobs: 67 k offsets per span, 2 %), and the
+	// work per offset is uniform enough that equal spans finish together (a dynamic scheduler over
+	// four spans per worker cost 9 % in re-computed look-ahead).  Small ranges: spans of at least
+	// 16 sub-blocks on fewer workers.
 	const int64_t tail = lookback + 64;
-	const int want = total >= (int64_t)h->fused_ctas * 4 * 16 * S ? h->fused_ctas * 4 : h->fused_ctas;
-	int64_t nbk = ((total + want - 1) / want + tail + S - 1) / S;
-	nbk = std::max<int64_t>(nbk, 16);  // keep the per-span look-back overhead below ~12 %
-	nbk = std::min<int64_t>(nbk, (1ll << 29) / S);
-	const int64_t per = nbk * S - tail;
+	const int want = h->fused_ctas;
+	int64_t per = (total + want - 1) / want;
+	per = std::max<int64_t>(per, 16 * (int64_t)S - tail);  // keep the per-span look-back overhead below ~12 %
+	per = std::min<int64_t>(per, (1ll << 29) - tail);
+	per = (per + 31) & ~31ll;
 	const int n_sp = (int)((total + per - 1) / per);
 	if (n_sp > h->fspan_cap[s]) {
 		CU(cudaStreamSynchronize(h->st));
