@@ -30,7 +30,8 @@ EXPORTS = [
     "adsbdec_b200_push", "adsbdec_b200_push_device", "adsbdec_b200_finish", "adsbdec_b200_decode_file",
     "adsbdec_b200_flush", "adsbdec_b200_poll", "adsbdec_b200_push_packed12", "adsbdec_b200_repair_lookup",
     "adsbdec_b200_stats", "adsbdec_b200_num_frames", "adsbdec_b200_frames", "adsbdec_b200_clear_frames",
-    "adsbdec_b200_kernel_time", "adsbdec_b200_telemetry", "adsbdec_b200_fused_time", "adsbdec_b200_format_packet",
+    "adsbdec_b200_kernel_time", "adsbdec_b200_telemetry", "adsbdec_b200_fused_time", "adsbdec_b200_gate_time",
+    "adsbdec_b200_format_packet",
     "adsbdec_b200_envelope", "adsbdec_b200_resolver_new", "adsbdec_b200_resolver_free",
     "adsbdec_b200_resolver_feed", "adsbdec_b200_resolver_feed_frames", "adsbdec_b200_resolver_finish",
     "adsbdec_b200_resolver_scan_end",
@@ -130,6 +131,7 @@ def lib():
         L.adsbdec_b200_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64), C.c_int]
         L.adsbdec_b200_telemetry.argtypes = [vp, C.POINTER(Telemetry), C.c_int]
         L.adsbdec_b200_fused_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64), C.POINTER(u64), C.c_int]
+        L.adsbdec_b200_gate_time.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
         L.adsbdec_b200_format_packet.argtypes = [C.c_int, C.c_char_p, C.c_int, u64, C.c_uint32, C.c_char_p]
         L.adsbdec_b200_envelope.argtypes = [C.c_int, vp, C.c_size_t, C.c_int, u64, vp, C.c_size_t]
         L.adsbdec_b200_resolver_new.argtypes = [C.c_int]
@@ -313,6 +315,11 @@ class Decoder:
         s = C.c_uint64()
         _check(lib().adsbdec_b200_fused_time(self._h, C.byref(ms), C.byref(n), C.byref(s), int(reset)))
         return ms.value, n.value, s.value
+
+    def gate_time(self, reset: bool = False) -> float:
+        ms = C.c_double()
+        _check(lib().adsbdec_b200_gate_time(self._h, C.byref(ms), int(reset)))
+        return ms.value
 
     def text(self, fmt: int = 0) -> bytes:
         return b"".join(format_packet(fmt, f.data, f.ts, f.pw) for f in self.frames)

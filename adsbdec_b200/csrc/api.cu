@@ -84,30 +84,34 @@ __global__ void k_reset_counters(Counters *c)
 	c->n_try = 0;
 	c->overflow = 0;
 	c->wide = 0;
+	c->try_mark = 0;
 }
 
 __global__ void k_zero_u64(unsigned long long *p) { *p = 0; }
 
-// Builds the span table of one fused launch on the device.
-__global__ void k_make_spans(FusedSpan *sp, int *ticket, int n_sp, long long n0, long long n1, long long per,
-                             int r, unsigned long long raw_w0, long long w_lo, long long w_hi, int S, int lookback)
+// Builds the span table of one fused launch on the device and marks where its tries will begin.
+// Span i covers envelope samples [j0 + i*per, j0 + (i+1)*per) = bit words [i*per/32, (i+1)*per/32), cut off at
+// `words` (per is a multiple of 224: FIR phase 0 and a bit-word boundary at every span start).
+__global__ void k_make_spans(FusedSpan *sp, int *ticket, Counters *ctr, int n_sp, long long j0, long long per,
+                             long long words, unsigned long long raw_w0, long long w_lo, long long w_hi)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i == 0)
+	if (i == 0) {
 		*ticket = 0;
+		ctr->try_mark = ctr->n_try;
+	}
 	if (i >= n_sp)
 		return;
 	FusedSpan s;
-	s.own_begin = n0 + (long long)i * per;
-	s.own_end = min(n1, s.own_begin + per);
-	long long q = s.own_begin - r;
-	q -= ((q % 28) + 28) % 28;
-	s.j_begin = q + r;  // at or before own_begin, == r (mod 28)
+	s.j_begin = j0 + (long long)i * per;
+	s.word_base = (long long)i * (per / 32);
+	const long long nw = min(per / 32, words - s.word_base);
+	s.n_words = (int)nw;
+	// stage 2 of sub-block k stores words 28k-7 .. 28k+20
+	s.n_blocks = (int)((nw + 7 + 27) / 28);
 	s.raw_w0 = raw_w0;
 	s.w_lo = w_lo;
 	s.w_hi = w_hi;
-	s.n_blocks = (int)((s.own_end + lookback - s.j_begin + S - 1) / S);
-	s.pad_ = 0;
 	sp[i] = s;
 }
 
@@ -177,12 +181,15 @@ struct adsbdec_b200 {
 	FrameRec *d_acc[kSlots] = {nullptr, nullptr};  // accepted frames of the job, in order, stamped
 	ResolveState *d_state = nullptr;
 	int last_slot = 0;
+	unsigned int *d_bits[kSlots] = {nullptr, nullptr};  // P | Q | B bit arrays of the slot's fused range
+	long long bits_cap[kSlots] = {0, 0};                // words per array
 	FusedSpan *d_fspans[kSlots] = {nullptr, nullptr};
 	int fspan_cap[kSlots] = {0, 0};
 	int *d_ticket[kSlots] = {nullptr, nullptr};
 	cudaEvent_t ev_done[kSlots] = {nullptr, nullptr};
 	cudaEvent_t ev_a[kSlots] = {nullptr, nullptr}, ev_b[kSlots] = {nullptr, nullptr};
 	cudaEvent_t ev_fa[kSlots] = {nullptr, nullptr}, ev_fb[kSlots] = {nullptr, nullptr};
+	cudaEvent_t ev_fc[kSlots] = {nullptr, nullptr};     // behind k_gate + k_slice of the slot's last fused range
 
 	// statistics
 	StreamStats *d_stats = nullptr, *h_stats = nullptr;
@@ -200,7 +207,7 @@ struct adsbdec_b200 {
 	adsbdec_b200_sink_fn sink = nullptr;
 	void *sink_user = nullptr;
 
-	double kernel_ms = 0, fused_ms = 0;
+	double kernel_ms = 0, fused_ms = 0, gate_ms = 0;
 	uint64_t launches = 0, fused_launches = 0, fused_samples = 0;
 
 	std::vector<adsbdec_b200_candidate_t> cand_tmp;
@@ -215,8 +222,8 @@ struct adsbdec_b200 {
 
 	// parity taps of the fused kernel (adsbdec_b200_debug_fused)
 	float *dbg_amp = nullptr;
-	unsigned int *dbg_p = nullptr, *dbg_q = nullptr, *dbg_b = nullptr;
 	long long dbg_n = 0, dbg_jb = 0;
+	int dbg_slot = 0;
 };
 
 namespace {
@@ -233,6 +240,7 @@ int alloc_slot_outputs(adsbdec_b200 *h, int s, unsigned long long cand_cap, unsi
 		h->h_cands[s] = nullptr;
 		h->d_acc[s] = nullptr;
 		h->rb[s].accept = nullptr;
+		h->cand_cap[s] = 0;  // a failed allocation below must not leave the old capacity behind
 		CU(cudaMalloc(&h->d_cands[s], cand_cap * sizeof(CandRec)));
 		CU(cudaMalloc(&h->d_acc[s], cand_cap * sizeof(FrameRec)));
 		CU(cudaMalloc(&h->rb[s].sorted, cand_cap * sizeof(CandRec)));
@@ -243,6 +251,7 @@ int alloc_slot_outputs(adsbdec_b200 *h, int s, unsigned long long cand_cap, unsi
 	if (try_cap != h->try_cap[s]) {
 		if (h->d_tries[s]) cudaFree(h->d_tries[s]);
 		h->d_tries[s] = nullptr;
+		h->try_cap[s] = 0;
 		CU(cudaMalloc(&h->d_tries[s], try_cap * sizeof(unsigned long long)));
 		h->try_cap[s] = try_cap;
 	}
@@ -254,8 +263,8 @@ int alloc_slot_outputs(adsbdec_b200 *h, int s, unsigned long long cand_cap, unsi
 int presize_lists(adsbdec_b200 *h, int s, int64_t offsets)
 {
 	const unsigned long long cc = std::max<unsigned long long>(h->cand_cap[s], (unsigned long long)offsets / 256);
-	const unsigned long long tc =
-	    h->cfg.collect_stats ? std::max<unsigned long long>(h->try_cap[s], (unsigned long long)offsets / 24) : h->try_cap[s];
+	// (the try list is also the fused path's survivor list: needed with or without statistics)
+	const unsigned long long tc = std::max<unsigned long long>(h->try_cap[s], (unsigned long long)offsets / 24);
 	if (cc == h->cand_cap[s] && tc == h->try_cap[s])
 		return 0;
 	CU(cudaStreamSynchronize(h->st));
@@ -319,11 +328,12 @@ bool wrap_in_range(unsigned long long org, int64_t j0, int64_t j1, int64_t *wrap
 	return true;
 }
 
-// Cuts [n0, n1) into spans for the fused kernel and launches it.  Requires no fidx wrap in range.
+// Runs the fused path over [n0, n1): k_fused (samples -> bit arrays), k_gate (-> tries), k_slice (-> candidates).
+// Requires no fidx wrap in range.
 int launch_fused_range(adsbdec_b200 *h, int s, const Job &j, int64_t n0, int64_t n1)
 {
 	const int S = fused_block_outputs();
-	const int lookback = fused_lookback();
+	const int64_t Q = fused_span_quantum();
 	// FIR phase.  Within one 2^32 epoch of the reference's fidx, slot(u) = (u + shift) % 14 with
 	// shift = (origin - epoch_base) mod 14.  A span must start on an output j with
 	// (2j + shift) % 14 == 0 (summation order becomes a compile-time constant per thread) and
@@ -339,64 +349,95 @@ int launch_fused_range(adsbdec_b200 *h, int s, const Job &j, int64_t n0, int64_t
 		}
 	if (r < 0)
 		return fail(ADSB_B200_EINVAL, "internal: no FIR phase for shift %d", shift);
-	const int64_t total = n1 - n0;
-	// A worker is one warp of the fused kernel, and every worker gets exactly ONE span: a span pays
-	// `lookback` offsets of envelope past its end (the look-ahead of its last frames), so long spans
-	// keep that redundancy small (60 s capture in three jobs: 67 k offsets per span, 2 %), and the
-	// work per offset is uniform enough that equal spans finish together (a dynamic scheduler over
-	// four spans per worker cost 9 % in re-computed look-ahead).  Small ranges: spans of at least
-	// 16 sub-blocks on fewer workers.
-	const int64_t tail = lookback + 64;
-	const int want = h->fused_ctas;
-	int64_t per = (total + want - 1) / want;
-	per = std::max<int64_t>(per, 16 * (int64_t)S - tail);  // keep the per-span look-back overhead below ~12 %
-	per = std::min<int64_t>(per, (1ll << 29) - tail);
-	per = (per + 31) & ~31ll;
+	// Bit arrays: word 0 starts at offset j0 <= n0 (FIR phase 0); the slicer reads the B bits of the last
+	// owned offset up to n1 - 1 + 1190, the gate up to n1 - 1 + 120.
+	const int64_t j0 = align_down(n0 - r, 28) + r;
+	const int64_t words = (n1 + kLookahead + 31 - j0) / 32 + 1;
+	// A worker is one warp of k_fused, and every worker gets exactly ONE span: a span computes up to one
+	// sub-block of envelope past its end (the 15 samples of look-ahead of its last bits), so long spans keep
+	// that redundancy small (60 s capture in three jobs: 67 k offsets per span, < 1 %), and the work per
+	// offset is uniform, so equal spans finish together.  Small ranges: spans of at least 16 sub-blocks on
+	// fewer workers.
+	const int64_t total = words * 32;
+	int64_t per = (total + h->fused_ctas - 1) / h->fused_ctas;
+	per = std::max<int64_t>(per, 16 * (int64_t)S);
+	per = std::min<int64_t>(per, 1ll << 29);
+	per = (per + Q - 1) / Q * Q;
 	const int n_sp = (int)((total + per - 1) / per);
 	if (n_sp > h->fspan_cap[s]) {
 		CU(cudaStreamSynchronize(h->st));
 		if (h->d_fspans[s]) cudaFree(h->d_fspans[s]);
+		h->d_fspans[s] = nullptr;
+		h->fspan_cap[s] = 0;
+		CU(cudaMalloc(&h->d_fspans[s], (size_t)(n_sp + 64) * sizeof(FusedSpan)));
 		h->fspan_cap[s] = n_sp + 64;
-		CU(cudaMalloc(&h->d_fspans[s], h->fspan_cap[s] * sizeof(FusedSpan)));
+	}
+	const int64_t words_alloc = words + 16;  // the slicer fetches ten words per lane whatever it uses of them
+	if (words_alloc > h->bits_cap[s]) {
+		CU(cudaStreamSynchronize(h->st));
+		if (h->d_bits[s]) cudaFree(h->d_bits[s]);
+		h->d_bits[s] = nullptr;
+		h->bits_cap[s] = 0;
+		const int64_t cap = words_alloc + words_alloc / 8;
+		CU(cudaMalloc(&h->d_bits[s], (size_t)cap * 3 * sizeof(unsigned int)));
+		h->bits_cap[s] = cap;
 	}
 	if (!h->d_ticket[s])
 		CU(cudaMalloc(&h->d_ticket[s], sizeof(int)));
 	if (j.u0 % 8 || ((uintptr_t)j.buf % 16))
 		return fail(ADSB_B200_EINVAL, "internal: fused window not 16-byte aligned");
 	const int64_t w_lo = j.u0 / 2, w_hi = align_down(j.u1 / 2, 4);
-	const int64_t jb0 = align_down(n0 - r, 28) + r;
-	if (jb0 - 8 < w_lo && j.u0 != 0)
+	if (j0 - 8 < w_lo && j.u0 != 0)
 		return fail(ADSB_B200_EINVAL, "internal: window lacks FIR history");
 	k_make_spans<<<(n_sp + 127) / 128, 128, 0, h->st>>>(
-	    h->d_fspans[s], h->d_ticket[s], n_sp, n0, n1, per, r,
-	    (unsigned long long)(uintptr_t)j.buf - 2ull * (unsigned long long)j.u0, w_lo, w_hi, S, lookback);
+	    h->d_fspans[s], h->d_ticket[s], h->d_ctr[s], n_sp, j0, per, words,
+	    (unsigned long long)(uintptr_t)j.buf - 2ull * (unsigned long long)j.u0, w_lo, w_hi);
 	CU(cudaGetLastError());
+	unsigned int *bp = h->d_bits[s], *bq = bp + h->bits_cap[s], *bb = bq + h->bits_cap[s];
 	FusedParams p;
 	p.spans = h->d_fspans[s];
 	p.n_spans = n_sp;
-	p.accept_df18 = h->cfg.accept_df18;
-	p.want_tries = h->cfg.collect_stats;
-	p.cands = h->d_cands[s];
-	p.cand_cap = h->cand_cap[s];
-	p.tries = h->d_tries[s];
-	p.try_cap = h->try_cap[s];
-	p.ctr = h->d_ctr[s];
 	p.span_ticket = h->d_ticket[s];
-	p.fix_tab = h->d_fix;
-	p.fix_level = h->fix_level;
+	p.ctr = h->d_ctr[s];
+	p.bits_p = bp;
+	p.bits_q = bq;
+	p.bits_b = bb;
 	p.dbg_amp = h->dbg_amp;
-	p.dbg_p = h->dbg_p;
-	p.dbg_q = h->dbg_q;
-	p.dbg_b = h->dbg_b;
 	p.dbg_n = h->dbg_n;
-	if (h->dbg_amp)
-		h->dbg_jb = jb0;
+	if (h->dbg_amp) {
+		h->dbg_jb = j0;
+		h->dbg_slot = s;
+	}
 	CU(cudaEventRecord(h->ev_fa[s], h->st));
 	CU(launch_fused(p, std::min(h->fused_ctas, n_sp), h->st));
 	CU(cudaEventRecord(h->ev_fb[s], h->st));
-	h->launches += 1;
+	GateParams g;
+	g.bits_p = bp;
+	g.bits_q = bq;
+	g.bits_b = bb;
+	g.j0 = j0;
+	g.n0 = n0;
+	g.n1 = n1;
+	g.accept_df18 = h->cfg.accept_df18;
+	g.tries = h->d_tries[s];
+	g.try_cap = h->try_cap[s];
+	g.ctr = h->d_ctr[s];
+	CU(launch_gate(g, h->st));
+	SliceParams sl;
+	sl.bits_b = bb;
+	sl.j0 = j0;
+	sl.tries = h->d_tries[s];
+	sl.try_cap = h->try_cap[s];
+	sl.cands = h->d_cands[s];
+	sl.cand_cap = h->cand_cap[s];
+	sl.ctr = h->d_ctr[s];
+	sl.fix_tab = h->d_fix;
+	sl.fix_level = h->fix_level;
+	CU(launch_slice(sl, h->st));
+	CU(cudaEventRecord(h->ev_fc[s], h->st));
+	h->launches += 4;
 	h->fused_launches += 1;
-	h->fused_samples += (uint64_t)(2 * total);
+	h->fused_samples += (uint64_t)(2 * (n1 - n0));
 	return 0;
 }
 
@@ -532,16 +573,18 @@ int complete_job(adsbdec_b200 *h, int s)
 			if (j.used_fused) {
 				cudaEventElapsedTime(&ms, h->ev_fa[s], h->ev_fb[s]);
 				h->fused_ms += ms;
+				cudaEventElapsedTime(&ms, h->ev_fb[s], h->ev_fc[s]);
+				h->gate_ms += ms;
 			}
 			const Counters &c = *h->h_ctr[s];
-			if (attempt >= 8)
-				return fail(ADSB_B200_ERANGE, "candidate lists keep overflowing");
-			if (j.used_fused && (c.wide || (c.overflow & 4u))) {
-				// samples beyond 12 bits (or an absurd survivor density): exact generic kernels
+			if (j.used_fused && c.wide) {
+				// samples beyond 12 bits: exact generic kernels
 				force_generic = true;
 			} else if (!(c.overflow & 3u)) {
 				break;
 			}
+			if (attempt >= 8)
+				return fail(ADSB_B200_ERANGE, "candidate lists keep overflowing");
 			// Redo.  Everything issued since this job started ran on a truncated list: drain the GPU,
 			// put the scan position back to where it was before this job, grow the lists and re-issue
 			// this job and the (newer) one in the other slot.
@@ -776,6 +819,7 @@ int adsbdec_b200_open(const adsbdec_b200_config_t *cfg, adsbdec_b200_t **out)
 		for (int s = 0; ok && s < kSlots; s++) {
 			ok = cudaEventCreate(&h->ev_a[s]) == cudaSuccess && cudaEventCreate(&h->ev_b[s]) == cudaSuccess &&
 			     cudaEventCreate(&h->ev_fa[s]) == cudaSuccess && cudaEventCreate(&h->ev_fb[s]) == cudaSuccess &&
+			     cudaEventCreate(&h->ev_fc[s]) == cudaSuccess &&
 			     cudaEventCreateWithFlags(&h->ev_done[s], cudaEventDisableTiming) == cudaSuccess &&
 			     cudaMalloc(&h->d_ctr[s], sizeof(Counters)) == cudaSuccess &&
 			     cudaMalloc(&h->d_slot[s], sizeof(SlotResolve)) == cudaSuccess &&
@@ -871,6 +915,8 @@ void adsbdec_b200_close(adsbdec_b200_t *h)
 		if (h->ev_b[s]) cudaEventDestroy(h->ev_b[s]);
 		if (h->ev_fa[s]) cudaEventDestroy(h->ev_fa[s]);
 		if (h->ev_fb[s]) cudaEventDestroy(h->ev_fb[s]);
+		if (h->ev_fc[s]) cudaEventDestroy(h->ev_fc[s]);
+		if (h->d_bits[s]) cudaFree(h->d_bits[s]);
 		if (h->ev_done[s]) cudaEventDestroy(h->ev_done[s]);
 	}
 	if (h->d_fix) cudaFree(h->d_fix);
@@ -1369,6 +1415,16 @@ int adsbdec_b200_fused_time(adsbdec_b200_t *h, double *ms, uint64_t *launches, u
 	return 0;
 }
 
+int adsbdec_b200_gate_time(adsbdec_b200_t *h, double *ms, int reset)
+{
+	if (!h)
+		return fail(ADSB_B200_EINVAL, "null handle");
+	if (ms) *ms = h->gate_ms;
+	if (reset)
+		h->gate_ms = 0;
+	return 0;
+}
+
 int adsbdec_b200_envelope(int device, const void *samples, size_t n_samples, int is_device,
                           uint64_t start_sample, float *amp_out, size_t count)
 {
@@ -1461,13 +1517,7 @@ int adsbdec_b200_debug_fused(adsbdec_b200_t *h, const uint16_t *samples, size_t 
 	CU(cudaMalloc(&d_raw, (n_samples + 64) * sizeof(uint16_t)));
 	CU(cudaMemcpy(d_raw, samples, n_samples * sizeof(uint16_t), cudaMemcpyHostToDevice));
 	CU(cudaMalloc(&h->dbg_amp, count * sizeof(float)));
-	CU(cudaMalloc(&h->dbg_p, count / 8));
-	CU(cudaMalloc(&h->dbg_q, count / 8));
-	CU(cudaMalloc(&h->dbg_b, count / 8));
 	CU(cudaMemset(h->dbg_amp, 0, count * sizeof(float)));
-	CU(cudaMemset(h->dbg_p, 0, count / 8));
-	CU(cudaMemset(h->dbg_q, 0, count / 8));
-	CU(cudaMemset(h->dbg_b, 0, count / 8));
 	h->dbg_n = (long long)count;
 	const int saved_ctas = h->fused_ctas;
 	h->fused_ctas = 1;  // one worker, so span 0 covers the head of the capture in order
@@ -1483,18 +1533,20 @@ int adsbdec_b200_debug_fused(adsbdec_b200_t *h, const uint16_t *samples, size_t 
 	cudaError_t e = cudaStreamSynchronize(h->st);
 	if (rc == 0 && e == cudaSuccess) {
 		cudaMemcpy(amp_out, h->dbg_amp, count * sizeof(float), cudaMemcpyDeviceToHost);
-		cudaMemcpy(p_out, h->dbg_p, count / 8, cudaMemcpyDeviceToHost);
-		cudaMemcpy(q_out, h->dbg_q, count / 8, cudaMemcpyDeviceToHost);
-		cudaMemcpy(b_out, h->dbg_b, count / 8, cudaMemcpyDeviceToHost);
+		// the bit arrays of the range, word 0 at the range's first span (j_begin_out)
+		const long long cap = h->bits_cap[h->dbg_slot];
+		const size_t nw = (size_t)std::min<long long>((long long)count / 32, cap);
+		memset(p_out, 0, count / 8);
+		memset(q_out, 0, count / 8);
+		memset(b_out, 0, count / 8);
+		cudaMemcpy(p_out, h->d_bits[h->dbg_slot], nw * 4, cudaMemcpyDeviceToHost);
+		cudaMemcpy(q_out, h->d_bits[h->dbg_slot] + cap, nw * 4, cudaMemcpyDeviceToHost);
+		cudaMemcpy(b_out, h->d_bits[h->dbg_slot] + 2 * cap, nw * 4, cudaMemcpyDeviceToHost);
 		if (j_begin_out) *j_begin_out = h->dbg_jb;
 	}
 	cudaFree(h->dbg_amp);
-	cudaFree(h->dbg_p);
-	cudaFree(h->dbg_q);
-	cudaFree(h->dbg_b);
 	cudaFree(d_raw);
 	h->dbg_amp = nullptr;
-	h->dbg_p = h->dbg_q = h->dbg_b = nullptr;
 	h->dbg_n = 0;
 	if (rc) return rc;
 	if (e != cudaSuccess)

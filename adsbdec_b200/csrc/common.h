@@ -48,9 +48,10 @@ constexpr uint64_t kTryMask = (1ull << kTryClsShift) - 1;
 struct Counters {
 	unsigned long long n_cand;      // entries in the job's candidate list
 	unsigned long long n_try;       // entries in the job's try list
-	unsigned int overflow;          // bit0: candidate list full, bit1: try list full, bit2: CTA survivor list full
+	unsigned int overflow;          // bit0: candidate list full, bit1: try list full
 	unsigned int wide;              // a sample outside 0..4095 was seen by the fused kernel
-	unsigned int pad_[10];
+	unsigned long long try_mark;    // n_try when the current fused range began: k_slice starts here
+	unsigned int pad_[8];
 };
 static_assert(sizeof(Counters) == 64, "Counters layout");
 

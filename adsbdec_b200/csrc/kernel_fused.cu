@@ -1,5 +1,5 @@
-// kernel_fused.cu - the B200 hot path: one persistent kernel that takes raw 16-bit samples from
-// HBM and emits CRC-valid Mode S candidates, with the envelope never leaving the SM.
+// kernel_fused.cu - the B200 hot path: raw 16-bit samples in HBM -> CRC-valid Mode S candidates, with the
+// envelope never leaving the SM.
 //
 // What it computes is exactly the per-offset part of the reference (TLeconte/adsbdec):
 //   air.c:59-92    envelope: fs/4 mixer, 14-tap FIR in ring-slot order, |.|^2, decimate by 2
@@ -11,14 +11,13 @@
 // the sparse output (kernels_resolve.cu + resolver.cpp), and pw (demod.c:127) is filled in for the
 // few CRC-valid candidates by a follow-up kernel (kernels_generic.cu: k_fill_pw).
 //
-// Organisation: every WARP is an autonomous worker.  It owns ONE long contiguous span of the capture
-// per launch (the host cuts a job into exactly as many spans as there are workers, so the ~1.4 k
-// offsets of look-ahead a span has to compute past its end are ~2 % of its work) and streams it
-// through its own slice of shared memory in sub-blocks of S = 28*32 = 896 envelope samples.  There
-// is no CTA barrier in the steady state - only __syncwarp and one mbarrier per warp for its TMA
-// loads - so the warps of an SM sit in different stages at any time and the FMA-heavy and ALU-heavy
-// stages overlap on the pipes.
+// Three kernels, split where the arithmetic density changes:
 //
+// k_fused (dominant; streams the samples once): every WARP is an autonomous worker.  It owns ONE long
+//   contiguous span of the capture per launch and streams it through its own slice of shared memory in
+//   sub-blocks of S = 28*32 = 896 envelope samples.  No CTA barrier in the steady state - only
+//   __syncwarp and one mbarrier per warp for its TMA loads - so the warps of an SM sit in different
+//   stages at any time and the FMA-heavy and ALU-heavy stages overlap on the pipes.
 //   * load:    raw samples of a sub-block arrive by a 1-D TMA bulk copy (cp.async.bulk + mbarrier,
 //              3.6 KB), issued by lane 0 as soon as the previous sub-block has been read;
 //   * stage 1 (FIR): each lane owns 28 consecutive outputs.  28 = lcm(4,7): the ring-slot rotation of
@@ -31,21 +30,21 @@
 //                P[n] = f[n] > 2*f[n+5]    (pulse pair at n, n+10 against the gap pair at n+5, n+15)
 //                Q[n] = f[n+5] > 2*f[n]    (the mirrored test; the preamble is P[n] & Q[n+30])
 //                B[n] = a[n] > a[n+5]      (PPM bit decision)
-//              transposed inside 8-lane groups (8 runs of 28 = 7 words of 32) into bit rings;
-//   * stage 3 (gate): word-parallel, one lane per 32 offsets: preamble = P[n] & Q[n+30]; DF gate =
-//              five bits of B at stride 10.  It only needs 120 offsets of look-ahead, so it runs
-//              right behind the bit front (on the words of the previous sub-block: no barrier of
-//              its own) and appends its survivors to a small ring with a ballot + popc rank;
-//   * stage 4 (slice+CRC): four lanes per survivor, EIGHT survivors per pass, and a pass only runs
-//              when eight are waiting (or the oldest is about to lose its bits), so its ~100
-//              instructions always work for 32 lanes.  A lane loads the ten B words that hold its
-//              28 frame bits once, shifts them so that its first bit leads, pulls 7 nibbles out at
-//              constant positions (funnel shift + multiply-gather), looks their syndromes up in a
-//              28x16 table and the four lanes XOR-reduce; syndrome 0 -> the frame bits go to the
-//              candidate list.  (REPAIR instantiation only: a non-zero syndrome is looked up in
-//              repair.h's table - an extension, off by default.)
-// Three __syncwarp per sub-block: before the raw stage is refilled, after the envelope (and the
-// gate), after the bit arrays.
+//              transposed inside 8-lane groups (8 runs of 28 = 7 words of 32) and stored to three bit
+//              arrays in HBM: 3 bits per offset against 32 bits of input, and they stay in the L2.
+//   The gate and the slicer used to live in this kernel; they are short dependent chains around
+//   shared-memory loads and atomics, and at the 20 warps per SM the FIR's registers allow they took
+//   half of the warps' time for a third of the instructions (profiles/r2a).
+//
+// k_gate (word-parallel, one lane per 32 offsets): preamble = P[n] & Q[n+30]; DF gate = five bits of B
+//   at stride 10; survivors ("tries", valid.c:46, :68) are compacted with a warp scan and one atomic
+//   per 1024 offsets into the try list.
+//
+// k_slice (four lanes per try): a lane loads the ten B words that hold its 28 frame bits once, shifts
+//   them so that its first bit leads, pulls 7 nibbles out at constant positions (funnel shift +
+//   multiply-gather), looks their syndromes up in a 28x16 table and the four lanes XOR-reduce;
+//   syndrome 0 -> the frame bits go to the candidate list.  (REPAIR instantiation only: a non-zero
+//   syndrome is looked up in repair.h's table - an extension, off by default.)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -65,9 +64,6 @@ namespace {
 #ifndef ADSB_MINB
 #define ADSB_MINB 1  // CTAs per SM
 #endif
-#ifndef ADSB_LIST_CAP
-#define ADSB_LIST_CAP 256  // survivor ring of a warp (tests build a tiny one to reach the overflow path)
-#endif
 
 constexpr int R = 28;               // outputs per lane per sub-block
 constexpr int WPC = ADSB_WPC;
@@ -78,41 +74,17 @@ constexpr int STAGE_WORDS = S + HIST;
 constexpr int LAG2 = 8;             // stage 2 works 8 runs behind the FIR front
 constexpr int RUNS = 32 + LAG2;     // envelope ring, in runs of 28 floats
 constexpr int WPB = S / 32;         // bit words per sub-block (28)
-constexpr int WPQ = 64;             // P and Q rings, in 32-bit words
-constexpr int WRB = 256;            // B ring: long enough for survivors to wait for a full slicer pass
-constexpr int MIRROR_Q = 4;         // words 0.. of a ring mirrored behind its end (readers never wrap)
-constexpr int MIRROR_B = 12;
-constexpr int LAG3W = 39;           // stage 3 of sub-block k handles words 28k-39 .. 28k-12
-constexpr int LIST_CAP = ADSB_LIST_CAP;
-constexpr int BATCH = 8;            // survivors per slicer pass (four lanes each)
-constexpr int FORCE_AGE = 6;        // a survivor older than this many sub-blocks is sliced at once
-constexpr int TRY_FLUSH = 64;       // tries go to the global list in pieces of at least this many
-// A span must run until the B bits of its last owned offset exist: stage 2 of sub-block k writes
-// words up to 28k+20, the last frame bit of offset n sits at n+1190.
-constexpr int LOOKBACK = 1440;
-
-static_assert(LAG3W - 4 >= WPB + 7, "stage 3 of a sub-block must only need words of earlier sub-blocks");
-static_assert(WPQ >= LAG3W + 21 + 1 && (WPQ & (WPQ - 1)) == 0, "P/Q ring too small");
-static_assert((WRB & (WRB - 1)) == 0 && (LIST_CAP & (LIST_CAP - 1)) == 0, "rings must be powers of two");
-static_assert(LOOKBACK % 32 == 0 && LOOKBACK >= 1190 + 32 * 7 + 1, "span look-back");
-// a survivor found in sub-block k' starts at word >= 28k'-39 and must be sliced before stage 2 of
-// sub-block k'+FORCE_AGE+1 overwrites the word behind its preamble (28k'-37 + WRB)
-static_assert(28 * (FORCE_AGE + 1) + 20 < WRB - 37, "B ring too short for the slicer's waiting time");
+constexpr int QUANTUM = 224;        // lcm(28, 32): spans start on FIR phase 0 AND on a bit-word boundary
 
 struct WarpSmem {
 	uint32_t raw[STAGE_WORDS];          // 3616 B
 	float amp[RUNS * R];                // 4480 B
-	uint32_t pbits[WPQ + MIRROR_Q];     // P[n]: first pulse pair beats its gap
-	uint32_t qbits[WPQ + MIRROR_Q];     // Q[n]: pulse at n+5.. beats the gap at n..
-	uint32_t bbits[WRB + MIRROR_B];     // B[n]: PPM decision
-	uint32_t cand[LIST_CAP];            // survivor ring (offset relative to the span, class in the top bits)
 	unsigned long long full;            // mbarrier of the raw stage
 	unsigned long long pad_;
 };
 static_assert(sizeof(WarpSmem) % 16 == 0, "per-warp shared memory must keep 16-byte alignment");
 
 struct Smem {
-	uint32_t lut[28 * 16];              // lut[g][v]: syndrome of nibble g of a 112-bit frame holding v
 	WarpSmem w[WPC];
 };
 
@@ -169,22 +141,16 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 	    : "memory");
 }
 
-__device__ __forceinline__ uint32_t lanemask_lt()
-{
-	uint32_t m;
-	asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
-	return m;
-}
-
 constexpr float kMagic = 8388608.0f;           // 2^23: float(0x4B000000 | x) == 2^23 + x
 constexpr float kMagicMid = 8388608.0f + 2048.0f;
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 
 }  // namespace
 
-// REPAIR: the opt-in syndrome repair of repair.h (a separate instantiation: the reference-parity
-// kernel carries none of it).
-template <bool DEBUG, bool REPAIR>
+// ============================================================================================
+// k_fused: samples -> P / Q / B bit arrays
+// ============================================================================================
+template <bool DEBUG>
 __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 {
 	//@region setup
@@ -194,14 +160,11 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 	const int lane = tid & 31;
 	WarpSmem &ws = sm.w[tid >> 5];
 
-	// ---- one-time setup (the only CTA barrier) ----------------------------
-	for (int e = tid; e < 28 * 16; e += NT)
-		sm.lut[e] = g_lut[e];
 	if (lane == 0) {
 		mbar_init(&ws.full, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
-	__syncthreads();
+	__syncwarp();
 	uint32_t phase = 0;  // mbarrier phase parity
 
 	// air.c:36-45 taps paired for a 32-bit word of age g (0 = newest): the even sample (I, low
@@ -213,13 +176,9 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 		const int ai = 2 * g + 1, aq = 2 * g;  // ages
 		tp[g] = make_float2(h[ai < 7 ? ai : 13 - ai], h[aq < 7 ? aq : 13 - aq]);
 	}
-	// lane constants of the 8-lane bit transposition and of the slicer
+	// lane constants of the 8-lane bit transposition
 	const int j8 = lane & 7;
 	const int wl = 7 * (lane >> 3) + j8 - 7;   // word written by this lane in sub-block k: 28k + wl
-	const int sub = lane & 3;                  // quarter of a frame this lane slices
-	const uint32_t lt = lanemask_lt();
-	const uint32_t lane_mask3 = lane < WPB ? 0xFFFFFFFFu : 0u;      // lanes that own a word in stage 3
-	const uint32_t df18_mask = p.accept_df18 ? 0xFFFFFFFFu : 0u;
 
 	for (;;) {
 		//@region span
@@ -233,9 +192,12 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 		const FusedSpan sp = p.spans[span_idx];
 		const long long jb = sp.j_begin;
 		const int nb = sp.n_blocks;
+		const uint32_t n_words = (uint32_t)sp.n_words;
+		unsigned int *const out_p = p.bits_p + sp.word_base;
+		unsigned int *const out_q = p.bits_q + sp.word_base;
+		unsigned int *const out_b = p.bits_b + sp.word_base;
 		// address of the first word of sub-block 0 (word jb - HIST); only valid words are touched
 		const char *raw_s0 = reinterpret_cast<const char *>(sp.raw_w0) + 4 * (jb - HIST);
-		const uint32_t own_lo = (uint32_t)(sp.own_begin - jb), own_hi = (uint32_t)(sp.own_end - jb);
 		// valid words of the window, relative to word jb - HIST (clamped to int range)
 		const long long lo64 = sp.w_lo - (jb - HIST), hi64 = sp.w_hi - (jb - HIST);
 		const int vlo = (int)(lo64 < 0 ? 0 : lo64);
@@ -268,114 +230,6 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 			}
 		}
 
-		// Survivor ring: entries [done, head) wait for the slicer, [flushed, head) for the global try
-		// list (valid.c:46, :68: every offset that reaches the CRC is a "try").  All warp-uniform.
-		uint32_t head = 0, done = 0, flushed = 0;
-
-		auto flush_tries = [&]() {
-			const uint32_t nt = head - flushed;
-			unsigned long long base = 0;
-			if (lane == 0)
-				base = atomicAdd(&p.ctr->n_try, (unsigned long long)nt);
-			base = __shfl_sync(FULL, base, 0);
-			for (uint32_t i = lane; i < nt; i += 32) {
-				const uint32_t ent = ws.cand[(flushed + i) & (LIST_CAP - 1)];
-				if (base + i < p.try_cap)
-					p.tries[base + i] = ((unsigned long long)(ent >> 30) << kTryClsShift) |
-					                    (unsigned long long)(jb + (long long)(ent & 0x3FFFFFFFu));
-				else
-					atomicOr(&p.ctr->overflow, 2u);
-			}
-			flushed = head;
-		};
-
-		// slice + CRC for ring entries [done, done + n) (n <= BATCH), four lanes per survivor
-		auto slice_pass = [&](uint32_t n) {
-			const uint32_t ci = lane >> 2;
-			const bool have = ci < n;
-			const uint32_t ent = ws.cand[(done + ci) & (LIST_CAP - 1)];
-			const uint32_t n_rel = ent & 0x3FFFFFFFu;
-			const bool is_long = (ent >> 30) != kClsDF11;
-			// short frames are the last 56 bits of the syndrome table and only use sub 0, 1
-			const bool active = have && (is_long || sub < 2);
-			// frame bit b sits at n + 80 + 10 b; nibble g starts at bit 4g
-			const uint32_t pb0 = n_rel + 80u + 280u * (uint32_t)sub;
-			const char *lutp = reinterpret_cast<const char *>(sm.lut) + (7 * sub + (is_long ? 0 : 14)) * 64;
-			uint32_t acc = 0, bits28 = 0;
-			if (active) {
-				// The lane's 28 frame bits sit 10 apart in 271 consecutive B bits: fetch the ten
-				// words once (mirrored past the end of the ring) and shift them so that the
-				// lane's first bit is bit 31 of W[0] - every later position is then a constant.
-				const uint32_t *bb = &ws.bbits[(pb0 >> 5) & (WRB - 1)];
-				const uint32_t sh = pb0 & 31u;
-				uint32_t r[10], W[9];
-#pragma unroll
-				for (int i = 0; i < 10; i++)
-					r[i] = bb[i];
-#pragma unroll
-				for (int i = 0; i < 9; i++)
-					W[i] = __funnelshift_l(r[i + 1], r[i], sh);
-#pragma unroll
-				for (int s_ = 0; s_ < 7; s_++) {
-					const int kk = 40 * s_, i = kk >> 5, o = kk & 31;
-					const uint32_t x = o ? __funnelshift_l(W[i + 1], W[i], o) : W[i];  // bits 31, 21, 11, 1
-					// the product's bits 27..22 are zero (no two partial products land there)
-					const uint32_t prod = (x & 0x80200802u) * 0x08040201u;
-					acc ^= *reinterpret_cast<const uint32_t *>(lutp + 64 * s_ + (prod >> 26));
-					bits28 = __funnelshift_l(prod, bits28, 4);
-				}
-			}
-			// valid.c:48-52 / :70-74: CRC over all but the last 3 bytes, XOR the last 3, == 0
-			acc ^= __shfl_xor_sync(FULL, acc, 1);
-			acc ^= __shfl_xor_sync(FULL, acc, 2);
-			bool ok = have && acc == 0;
-			uint32_t fix = 0xFFFFu;  // (first << 8) | second flipped bit, 0xFF = none (repair.h)
-			if (REPAIR && have && acc != 0) {
-				const uint32_t e = fix_lookup(p.fix_tab, acc);
-				if (e != kFixNone && fix_allowed(e, is_long, p.fix_level)) {
-					ok = true;
-					fix = e;
-				}
-			}
-			if (__any_sync(FULL, ok)) {
-				unsigned long long slot = 0;
-				if (ok && sub == 0)
-					slot = atomicAdd(&p.ctr->n_cand, 1ull);
-				slot = __shfl_sync(FULL, slot, lane & ~3);
-				if (ok) {
-					if (slot < p.cand_cap) {
-						uint32_t *out = reinterpret_cast<uint32_t *>(&p.cands[slot]);
-						if (sub == 0) {
-							const unsigned long long n = (unsigned long long)(jb + (long long)n_rel);
-							// pw is filled in by k_fill_pw (demod.c:127)
-							*reinterpret_cast<uint4 *>(out) = make_uint4(
-							    (uint32_t)n, (uint32_t)(n >> 32), 0u, (is_long ? 14u : 7u) | kCandNibbleWords);
-						}
-						uint32_t word = bits28;
-						if (REPAIR && fix != 0xFFFFu) {
-							const uint32_t base = is_long ? 0u : 56u;
-							const uint32_t b1 = (fix >> 8) - base, b2 = (fix & 0xFFu) - base;
-							if (b1 / 28u == (uint32_t)sub)
-								word ^= 0x08000000u >> (b1 % 28u);
-							if ((fix & 0xFFu) != 0xFFu && b2 / 28u == (uint32_t)sub)
-								word ^= 0x08000000u >> (b2 % 28u);
-							if (sub == 0)  // bits 28, 29 of word 0: how many bits were repaired
-								word |= ((fix & 0xFFu) != 0xFFu ? 2u : 1u) << 28;
-						}
-						out[4 + sub] = word;
-					} else if (sub == 0) {
-						atomicOr(&p.ctr->overflow, 1u);
-					}
-				}
-			}
-			done += n;
-		};
-
-		// stage 3: word handled by this lane in sub-block k (28k - 39 + lane), fully owned words
-		int wd3 = lane - LAG3W;
-		const bool ow_any = (own_hi >> 5) > ((own_lo + 31u) >> 5);
-		const int ow_lo = ow_any ? (int)((own_lo + 31u) >> 5) : 0x40000000;  // none: every word takes the masked path
-		const uint32_t ow_n = ow_any ? (own_hi >> 5) - 1u - (uint32_t)ow_lo : 0u;
 		int q_fir = lane;          // ring run of this lane's FIR output, (k*32 + lane) % RUNS
 		int wbase = wl;            // 28k + wl
 		const char *src_next = raw_s0 + 4ll * S;  // global address of sub-block k+1
@@ -471,76 +325,13 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 				}
 			}
 
-			//@region stage3
-			// ================= stage 3: preamble AND + DF gate ===============
-			// Runs BEFORE stage 2 of this sub-block: it looks at words 28k-39 .. 28k-8 of the bit rings,
-			// all written by stage 2 of earlier sub-blocks (stage 2 of this one writes 28k-7 .. 28k+20), so
-			// no barrier is needed in front of it.  Entries appended here are sliced from the next
-			// sub-block on, when stage 2 has produced the last of their 1190 look-ahead bits.
-			const uint32_t ready = head;
-			{
-				// every lane works (lanes 28..31 and words in front of the span are masked, not branched
-				// around): the ring reads of a negative word index land on valid, unused words
-				const uint32_t o0 = (uint32_t)wd3 * 32u;
-				const int wq = wd3 & (WPQ - 1);  // wq+1 is readable thanks to the mirror
-				// demod.c:107: p1 > 2*s1 at n, p2 > 2*s2 at n+30
-				uint32_t pre = ws.pbits[wq] & __funnelshift_l(ws.qbits[wq + 1], ws.qbits[wq], 30) & lane_mask3;
-				// ownership: only offsets in [own_lo, own_hi) (relative to j_begin) are emitted here; words
-				// ow_lo .. ow_lo + ow_n lie entirely inside
-				if ((uint32_t)(wd3 - ow_lo) > ow_n) {
-					const int o0s = wd3 * 32;
-					const int lo = max((int)own_lo - o0s, 0);           // first owned bit index
-					const int hi = min((int)own_hi - o0s, 32);          // one past the last
-					const uint32_t m_lo = lo >= 32 ? 0u : 0xFFFFFFFFu >> lo;
-					const uint32_t m_hi = hi >= 32 ? 0xFFFFFFFFu : hi <= 0 ? 0u : ~(0xFFFFFFFFu >> hi);
-					pre &= m_lo & m_hi;
-				}
-				const uint32_t *bw = &ws.bbits[wd3 & (WRB - 1)];  // +2 .. +4 readable thanks to the mirror
-				const uint32_t b2 = bw[2], b3 = bw[3], b4 = bw[4];
-				// first five data bits sit at n+80, +90, +100, +110, +120 (demod.c:110, :46-81)
-				const uint32_t x7 = __funnelshift_l(b3, b2, 16);  // 80  = 64 + 16
-				const uint32_t x6 = __funnelshift_l(b3, b2, 26);  // 90  = 64 + 26
-				const uint32_t x5 = __funnelshift_l(b4, b3, 4);   // 100 = 96 + 4
-				const uint32_t x4 = __funnelshift_l(b4, b3, 14);  // 110 = 96 + 14
-				const uint32_t x3 = __funnelshift_l(b4, b3, 24);  // 120 = 96 + 24
-				const uint32_t c0 = pre & ~x5;
-				const uint32_t m17 = c0 & x7 & ~x6 & ~x4 & x3;                   // 10001
-				const uint32_t m18 = c0 & x7 & ~x6 & x4 & ~x3 & df18_mask;       // 10010 (only with -a, demod.c:59)
-				const uint32_t m11 = c0 & ~x7 & x6 & x4 & x3;                    // 01011
-				uint32_t any = m17 | m18 | m11;
-				// warp-cooperative append: one bit per lane and round, ranked by ballot + popc
-				uint32_t bal = __ballot_sync(FULL, any != 0u);
-				if (bal) {
-					const uint32_t floor_ = p.want_tries ? min(done, flushed) : done;
-					do {
-						if (any) {
-							const int i = __clz(any);
-							const uint32_t bit = 0x80000000u >> i;
-							any &= ~bit;
-							// class in the top two bits: DF11 = 0, DF17 = 1, DF18 = 2
-							const uint32_t cls = ((m17 << i) >> 1 & 0x40000000u) | ((m18 << i) & 0x80000000u);
-							const uint32_t idx = head + __popc(bal & lt);
-							if (idx - floor_ < (uint32_t)LIST_CAP)
-								ws.cand[idx & (LIST_CAP - 1)] = (o0 + (uint32_t)i) | cls;
-						}
-						head += __popc(bal);
-						bal = __ballot_sync(FULL, any != 0u);
-					} while (bal);
-					if (head - floor_ > (uint32_t)LIST_CAP) {  // absurd survivor density: the host re-runs the job generically
-						if (lane == 0)
-							atomicOr(&p.ctr->overflow, 4u);
-						head = floor_ + (uint32_t)LIST_CAP;
-					}
-				}
-				wd3 += WPB;
-			}
-			__syncwarp();  // envelope of sub-block k and the survivor ring visible to the warp
+			__syncwarp();  // envelope of sub-block k visible to the warp
 
 			//@region stage2
 			// ================= stage 2: decision bits ========================
 			{
 				// run handled here: 32k + lane - LAG2 (uniform sign per 8-lane group).  In sub-block 0 the
-				// first eight lanes work on whatever the ring holds: their words (index < 0) are never read.
+				// first eight lanes work on whatever the ring holds: their words (index < 0) are not stored.
 				uint32_t P = 0, Q = 0, B = 0;
 				{
 					int q2 = q_fir - LAG2;
@@ -589,53 +380,16 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 				const uint32_t Pn = __shfl_down_sync(FULL, P, 1, 8);
 				const uint32_t Qn = __shfl_down_sync(FULL, Q, 1, 8);
 				const uint32_t Bn = __shfl_down_sync(FULL, B, 1, 8);
-				if (j8 < 7) {
+				// words [0, n_words) of the span go to the bit arrays (coalesced: 28 consecutive words per array)
+				if (j8 < 7 && (uint32_t)wbase < n_words) {
 					const int sl = 4 + 4 * j8, sr = 24 - 4 * j8;
-					const uint32_t pw_ = (P << sl) | (Pn >> sr);
-					const uint32_t qw_ = (Q << sl) | (Qn >> sr);
-					const uint32_t bw_ = (B << sl) | (Bn >> sr);
-					const int wq = wbase & (WPQ - 1), wb = wbase & (WRB - 1);
-					ws.pbits[wq] = pw_;
-					ws.qbits[wq] = qw_;
-					ws.bbits[wb] = bw_;
-					if (wq < MIRROR_Q)  // mirrors: stages 3/4 read runs of words without wrapping
-						ws.qbits[WPQ + wq] = qw_;
-					if (wb < MIRROR_B)
-						ws.bbits[WRB + wb] = bw_;
-					if (DEBUG && p.dbg_p && span_idx == 0) {
-						if (wbase >= 0 && wbase < p.dbg_n / 32) {
-							p.dbg_p[wbase] = pw_;
-							p.dbg_q[wbase] = qw_;
-							p.dbg_b[wbase] = bw_;
-						}
-					}
+					out_p[wbase] = (P << sl) | (Pn >> sr);
+					out_q[wbase] = (Q << sl) | (Qn >> sr);
+					out_b[wbase] = (B << sl) | (Bn >> sr);
 				}
 			}
-			__syncwarp();  // bit arrays of sub-block k visible to the warp
-
-			//@region stage4
-			// ================= stage 4: slice + CRC, eight survivors per pass ==
-			// Entries appended before this sub-block have all their bits now.  Full passes only, unless
-			// the oldest entry has waited FORCE_AGE sub-blocks (its B words are about to be overwritten).
-			{
-				const bool last = k + 1 == nb;  // end of the span: LOOKBACK guarantees every entry has its bits
-				const uint32_t avail = (last ? head : ready) - done;
-				uint32_t nrun = last ? avail : (avail & ~(uint32_t)(BATCH - 1));
-				if (avail != 0u && nrun == 0u) {
-					const uint32_t oldest = ws.cand[done & (LIST_CAP - 1)] & 0x3FFFFFFFu;
-					if ((int)oldest < (k - FORCE_AGE) * S)
-						nrun = avail;
-				}
-				while (nrun) {
-					const uint32_t n = min(nrun, (uint32_t)BATCH);
-					slice_pass(n);
-					nrun -= n;
-				}
-				if (p.want_tries && (head - flushed >= (uint32_t)TRY_FLUSH || (last && head != flushed)))
-					flush_tries();
-			}
-			// no barrier here: the next one every lane meets is behind the mbarrier wait of sub-block
-			// k+1, and nothing shared is written before it except the raw stage, which is free
+			// no barrier here: the next one every lane meets is behind the register loads of sub-block k+1,
+			// in front of its first envelope store (which reuses the ring runs read above)
 			q_fir += 32;
 			if (q_fir >= RUNS) q_fir -= RUNS;
 			wbase += WPB;
@@ -645,12 +399,266 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 	}
 }
 
+// ============================================================================================
+// k_gate: bit arrays -> tries (demod.c:107 preamble test, demod.c:46-81 DF gate), one lane per 32 offsets
+// ============================================================================================
+// A single counter cannot take an atomic per 1024 offsets (same-address atomics retire at ~1.2 per ns in
+// the L2: 0.5 ms per 60 s capture), so every warp collects its tries in shared memory and reserves room
+// in the global list a few hundred at a time.
+constexpr int GATE_STAGE = 512;  // tries staged per warp (2 KB), as 32-bit offsets relative to j0
+
+// The try list gets the bare offsets here; k_slice, which reads the first frame bits anyway, adds the DF
+// class (demod.c:46-81: 10001 = DF17, 10010 = DF18, 01011 = DF11) that the statistics pass wants.
+__global__ void __launch_bounds__(256) k_gate(const GateParams p)
+{
+	//@region gate
+	__shared__ uint32_t stage_all[8][GATE_STAGE];
+	__shared__ uint32_t cnt_all[8];
+	const uint32_t lane = threadIdx.x & 31u;
+	uint32_t *const stage = stage_all[threadIdx.x >> 5];
+	uint32_t *const cnt = &cnt_all[threadIdx.x >> 5];
+	const uint32_t warp = blockIdx.x * 8u + (threadIdx.x >> 5);
+	const uint32_t stride = gridDim.x * 8u * 32u;
+	// words that hold owned offsets (n0 < n1, j0 <= n0, fewer than 2^31 offsets per launch) and the masks of
+	// the two words the range may own only in part
+	const uint32_t r0 = (uint32_t)(p.n0 - p.j0), r1 = (uint32_t)(p.n1 - 1 - p.j0);
+	const uint32_t g_lo = r0 >> 5, g_hi = r1 >> 5;
+	const uint32_t m_first = 0xFFFFFFFFu >> (r0 & 31u);
+	const uint32_t m_last = 0xFFFFFFFFu << (31u - (r1 & 31u));
+	const uint32_t df18_mask = p.accept_df18 ? 0xFFFFFFFFu : 0u;
+	const unsigned int *__restrict__ bp = p.bits_p;
+	const unsigned int *__restrict__ bq = p.bits_q;
+	const unsigned int *__restrict__ bb = p.bits_b;
+	if (lane == 0)
+		*cnt = 0;
+	__syncwarp();
+	uint32_t staged = 0;  // == *cnt, warp-uniform
+	bool ovf = false;
+
+	auto flush = [&]() {
+		unsigned long long base = 0;
+		if (lane == 0)
+			base = atomicAdd(&p.ctr->n_try, (unsigned long long)staged);
+		base = __shfl_sync(FULL, base, 0);
+		for (uint32_t i = lane; i < staged; i += 32u) {
+			if (base + i < p.try_cap)
+				p.tries[base + i] = (unsigned long long)(p.j0 + (long long)stage[i]);
+			else
+				ovf = true;
+		}
+		__syncwarp();
+		if (lane == 0)
+			*cnt = 0;
+		__syncwarp();
+		staged = 0;
+	};
+
+	for (uint32_t g0 = g_lo + warp * 32u; g0 <= g_hi; g0 += stride) {
+		const uint32_t g = g0 + lane;
+		uint32_t any = 0;
+		if (g <= g_hi) {
+			// demod.c:107: p1 > 2*s1 at n, p2 > 2*s2 at n+30
+			uint32_t pre = bp[g] & __funnelshift_l(bq[g + 1], bq[g], 30);
+			if (g == g_lo)
+				pre &= m_first;
+			if (g == g_hi)
+				pre &= m_last;
+			if (pre) {
+				const uint32_t b2 = bb[g + 2], b3 = bb[g + 3], b4 = bb[g + 4];
+				// first five data bits sit at n+80, +90, +100, +110, +120 (demod.c:110, :46-81)
+				const uint32_t x7 = __funnelshift_l(b3, b2, 16);  // 80  = 64 + 16
+				const uint32_t x6 = __funnelshift_l(b3, b2, 26);  // 90  = 64 + 26
+				const uint32_t x5 = __funnelshift_l(b4, b3, 4);   // 100 = 96 + 4
+				const uint32_t x4 = __funnelshift_l(b4, b3, 14);  // 110 = 96 + 14
+				const uint32_t x3 = __funnelshift_l(b4, b3, 24);  // 120 = 96 + 24
+				const uint32_t c0 = pre & ~x5;
+				const uint32_t lng = c0 & x7 & ~x6;
+				any = (lng & ~x4 & x3)                  // 10001
+				      | (lng & x4 & ~x3 & df18_mask)    // 10010 (only with -a, demod.c:59)
+				      | (c0 & ~x7 & x6 & x4 & x3);      // 01011
+			}
+		}
+		const uint32_t c = (uint32_t)__popc(any);
+		const uint32_t total = __reduce_add_sync(FULL, c);
+		if (total == 0u)
+			continue;
+		if (staged + total > (uint32_t)GATE_STAGE)
+			flush();
+		uint32_t rel = g << 5;  // offset of bit 31 of this lane's word, relative to j0
+		if (total > (uint32_t)GATE_STAGE) {
+			// absurd density (more than half of 1024 offsets pass the gate): straight to the list
+			unsigned long long at = c ? atomicAdd(&p.ctr->n_try, (unsigned long long)c) : 0ull;
+			while (any) {
+				const int i = __clz(any);
+				any &= ~(0x80000000u >> i);
+				if (at < p.try_cap)
+					p.tries[at] = (unsigned long long)(p.j0 + (long long)(rel + (uint32_t)i));
+				else
+					ovf = true;
+				at++;
+			}
+			continue;
+		}
+		uint32_t at = c ? atomicAdd(cnt, c) : 0u;
+		while (any) {
+			const int i = __clz(any);
+			any &= ~(0x80000000u >> i);
+			stage[at++] = rel + (uint32_t)i;
+		}
+		staged += total;
+		__syncwarp();
+	}
+	if (staged)
+		flush();
+	if (ovf)
+		atomicOr(&p.ctr->overflow, 2u);
+}
+
+// ============================================================================================
+// k_slice: tries -> CRC-valid candidates (demod.c:31-44 slicer, valid.c:39-82 syndrome), one lane per try
+// ============================================================================================
+// 28 frame bits starting at bit position pb of the B array (10 apart: 271 consecutive bits): ten words are
+// fetched once and shifted so that the first bit is bit 31 of W[0] - every later position is then a
+// compile-time constant (funnel shift + multiply-gather of bits 31, 21, 11, 1 into a nibble).  Returns
+// the 28 bits and XORs the syndromes of their seven nibbles (rows of `lutp`) into acc.
+__device__ __forceinline__ uint32_t slice28(const unsigned int *__restrict__ bits_b, uint32_t pb, const char *lutp,
+                                            uint32_t &acc)
+{
+	const unsigned int *bb = bits_b + (pb >> 5);
+	const uint32_t sh = pb & 31u;
+	uint32_t r[10], W[9];
+#pragma unroll
+	for (int i = 0; i < 10; i++)
+		r[i] = bb[i];
+#pragma unroll
+	for (int i = 0; i < 9; i++)
+		W[i] = __funnelshift_l(r[i + 1], r[i], sh);
+	uint32_t bits28 = 0;
+#pragma unroll
+	for (int s_ = 0; s_ < 7; s_++) {
+		const int kk = 40 * s_, i = kk >> 5, o = kk & 31;
+		const uint32_t x = o ? __funnelshift_l(W[i + 1], W[i], o) : W[i];
+		// the product's bits 27..22 are zero (no two partial products land there)
+		const uint32_t prod = (x & 0x80200802u) * 0x08040201u;
+		acc ^= *reinterpret_cast<const uint32_t *>(lutp + 64 * s_ + (prod >> 26));
+		bits28 = __funnelshift_l(prod, bits28, 4);
+	}
+	return bits28;
+}
+
+constexpr int SLICE_STAGE = 64;  // candidate records staged per warp (2 KB): a pass adds at most 32
+
+template <bool REPAIR>
+__global__ void __launch_bounds__(256) k_slice(const SliceParams p)
+{
+	//@region slice
+	__shared__ uint32_t lut[28 * 16];
+	__shared__ uint4 stage_all[8][SLICE_STAGE * 2];
+	for (int e = threadIdx.x; e < 28 * 16; e += 256)
+		lut[e] = g_lut[e];
+	__syncthreads();
+	const uint32_t lane = threadIdx.x & 31u;
+	uint4 *const stage = stage_all[threadIdx.x >> 5];
+	const unsigned long long first = p.ctr->try_mark;
+	unsigned long long last = p.ctr->n_try;
+	if (last > p.try_cap)
+		last = p.try_cap;
+	if (last <= first)
+		return;
+	const uint32_t count = (uint32_t)min(last - first, 0xFFFFFF00ull);
+	unsigned long long *tries = p.tries + first;
+	const uint32_t stride = gridDim.x * 256u;
+	uint32_t staged = 0;  // records in `stage`, warp-uniform
+	bool ovf = false;
+
+	// one atomic for all staged records (see k_gate), then a coalesced copy
+	auto flush = [&]() {
+		unsigned long long base = 0;
+		if (lane == 0)
+			base = atomicAdd(&p.ctr->n_cand, (unsigned long long)staged);
+		base = __shfl_sync(FULL, base, 0);
+		uint4 *out = reinterpret_cast<uint4 *>(p.cands);
+		for (uint32_t i = lane; i < 2u * staged; i += 32u) {
+			if (base + (i >> 1) < p.cand_cap)
+				out[2ull * base + i] = stage[i];
+			else
+				ovf = true;
+		}
+		__syncwarp();
+		staged = 0;
+	};
+
+	// whole warps iterate together (the ballot below needs every lane)
+	for (uint32_t t0 = blockIdx.x * 256u + (threadIdx.x & ~31u); t0 < count; t0 += stride) {
+		const uint32_t t = t0 + lane;
+		const bool have = t < count;
+		const long long n_abs = have ? (long long)(tries[t] & kTryMask) : p.j0;
+		// frame bit b sits at n + 80 + 10 b; the first one tells 10001 / 10010 (112 bits) from 01011 (56 bits,
+		// the tail of the syndrome table: rows 14..27)
+		const uint32_t pb = (uint32_t)(n_abs - p.j0) + 80u;
+		const bool is_long = ((p.bits_b[pb >> 5] << (pb & 31u)) >> 31) != 0u;
+		const char *lutp = reinterpret_cast<const char *>(lut) + (is_long ? 0 : 14 * 64);
+		uint32_t acc = 0, w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+		if (have) {
+			w0 = slice28(p.bits_b, pb, lutp, acc);
+			w1 = slice28(p.bits_b, pb + 280u, lutp + 7 * 64, acc);
+			if (is_long) {
+				w2 = slice28(p.bits_b, pb + 560u, lutp + 14 * 64, acc);
+				w3 = slice28(p.bits_b, pb + 840u, lutp + 21 * 64, acc);
+			}
+		}
+		if (have)  // the class for the statistics pass (valid.c:46, :68): frame bit 3 tells DF18 from DF17
+			tries[t] = ((unsigned long long)(is_long ? ((w0 >> 24) & 1u ? kClsDF18 : kClsDF17) : kClsDF11) << kTryClsShift) |
+			           (unsigned long long)n_abs;
+		// valid.c:48-52 / :70-74: CRC over all but the last 3 bytes, XOR the last 3, == 0
+		bool ok = have && acc == 0;
+		if (REPAIR && have && acc != 0) {
+			// extension (repair.h): the syndrome of one or two flipped bits
+			const uint32_t e = fix_lookup(p.fix_tab, acc);
+			if (e != kFixNone && fix_allowed(e, is_long, p.fix_level)) {
+				ok = true;
+				const uint32_t base = is_long ? 0u : 56u;
+				uint32_t nfix = 0;
+				for (uint32_t fb = e >> 8;; fb = e & 0xFFu) {
+					const uint32_t b = fb - base, m = 0x08000000u >> (b % 28u);
+					if (b < 28u) w0 ^= m;
+					else if (b < 56u) w1 ^= m;
+					else if (b < 84u) w2 ^= m;
+					else w3 ^= m;
+					nfix++;
+					if (nfix == 2 || (e & 0xFFu) == 0xFFu)
+						break;
+				}
+				w0 |= nfix << 28;  // bits 28, 29 of word 0: how many bits were repaired
+			}
+		}
+		const uint32_t okm = __ballot_sync(FULL, ok);
+		if (okm) {
+			if (ok) {
+				uint4 *rec = stage + 2u * (staged + (uint32_t)__popc(okm & ((1u << lane) - 1u)));
+				// pw is filled in by k_fill_pw (demod.c:127)
+				rec[0] = make_uint4((uint32_t)n_abs, (uint32_t)((unsigned long long)n_abs >> 32), 0u,
+				                    (is_long ? 14u : 7u) | kCandNibbleWords);
+				rec[1] = make_uint4(w0, w1, w2, w3);
+			}
+			staged += (uint32_t)__popc(okm);
+			__syncwarp();
+			if (staged > (uint32_t)(SLICE_STAGE - 32))
+				flush();
+		}
+	}
+	if (staged)
+		flush();
+	if (ovf)
+		atomicOr(&p.ctr->overflow, 1u);
+}
+
 int fused_block_outputs() { return S; }
-int fused_lookback() { return LOOKBACK; }
+int fused_span_quantum() { return QUANTUM; }
 int fused_threads() { return NT; }
 size_t fused_smem_bytes() { return sizeof(Smem); }
 
-// Configures the kernel and returns the number of autonomous workers (warps) per SM.
+// Configures the kernels and returns the number of autonomous workers (warps) per SM.
 int fused_prepare(int device)
 {
 	(void)device;
@@ -668,16 +676,13 @@ int fused_prepare(int device)
 	}
 	if (cudaMemcpyToSymbol(g_lut, lut, sizeof lut) != cudaSuccess)
 		return -1;
-	if (cudaFuncSetAttribute(k_fused<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                         (int)fused_smem_bytes()) != cudaSuccess ||
-	    cudaFuncSetAttribute(k_fused<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                         (int)fused_smem_bytes()) != cudaSuccess ||
-	    cudaFuncSetAttribute(k_fused<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                         (int)fused_smem_bytes()) != cudaSuccess)
+	if (cudaFuncSetAttribute(k_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_bytes()) !=
+	        cudaSuccess ||
+	    cudaFuncSetAttribute(k_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_bytes()) !=
+	        cudaSuccess)
 		return -1;
 	int per_sm = 0;
-	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<false, false>, NT, fused_smem_bytes()) !=
-	    cudaSuccess)
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<false>, NT, fused_smem_bytes()) != cudaSuccess)
 		return -1;
 	return per_sm * WPC;
 }
@@ -689,11 +694,29 @@ cudaError_t launch_fused(const FusedParams &p, int workers, cudaStream_t st)
 		return cudaSuccess;
 	const int grid = (workers + WPC - 1) / WPC;
 	if (p.dbg_amp)
-		k_fused<true, false><<<grid, NT, fused_smem_bytes(), st>>>(p);
-	else if (p.fix_level > 0)
-		k_fused<false, true><<<grid, NT, fused_smem_bytes(), st>>>(p);
+		k_fused<true><<<grid, NT, fused_smem_bytes(), st>>>(p);
 	else
-		k_fused<false, false><<<grid, NT, fused_smem_bytes(), st>>>(p);
+		k_fused<false><<<grid, NT, fused_smem_bytes(), st>>>(p);
+	return cudaGetLastError();
+}
+
+// Grids of the two light kernels: enough resident warps to hide the L2 latency of their loads.
+cudaError_t launch_gate(const GateParams &p, cudaStream_t st)
+{
+	if (p.n1 <= p.n0)
+		return cudaSuccess;
+	const long long words = ((p.n1 - 1 - p.j0) >> 5) - ((p.n0 - p.j0) >> 5) + 1;
+	const long long want = (words + 255) / 256;  // one step of 8 warps
+	k_gate<<<(unsigned)(want < 148 * 8 ? want : 148 * 8), 256, 0, st>>>(p);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_slice(const SliceParams &p, cudaStream_t st)
+{
+	if (p.fix_level > 0)
+		k_slice<true><<<148 * 8, 256, 0, st>>>(p);
+	else
+		k_slice<false><<<148 * 8, 256, 0, st>>>(p);
 	return cudaGetLastError();
 }
 

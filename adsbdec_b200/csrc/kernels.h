@@ -64,47 +64,69 @@ cudaError_t launch_count_tries_frames(const unsigned long long *tries, const uns
                                       cudaStream_t st);
 
 // ---- fused path (kernel_fused.cu) -----------------------------------------
+//
+// Three kernels per range of offsets:
+//   k_fused  samples -> three bit arrays in HBM, one bit per offset (0.375 B per offset, L2-resident):
+//            P (first preamble pulse pair beats its gap), Q (the mirrored test), B (PPM decision)
+//   k_gate   word-parallel preamble AND + DF gate over the bit arrays -> list of "tries"
+//   k_slice  PPM slicer + CRC-24 syndrome over the tries -> CRC-valid candidates
+// Bit arrays: word g, bit 31-i holds offset J0 + 32 g + i (MSB first), J0 = the first span's j_begin.
 
-// One contiguous run of offsets handled by one CTA of the fused kernel ("span").
+// One contiguous run of envelope samples handled by one warp of k_fused ("span").
 // Word W = the 32-bit pair of local samples (2W, 2W+1) = the newest input of envelope sample W.
 struct FusedSpan {
 	unsigned long long raw_w0;  // device address at which word 0 would sit (16-byte aligned; only
 	                            // words in [w_lo, w_hi) are ever dereferenced)
 	long long w_lo, w_hi;       // words present in the window, multiples of 4; words outside read as
 	                            // mid-scale (before the stream start the FIR ring is zero, air.c:33)
-	long long j_begin;          // first envelope sample computed: multiple of 4 and FIR phase 0
-	long long own_begin;        // candidates are emitted for own_begin <= n < own_end
-	long long own_end;
+	long long j_begin;          // first envelope sample computed: J0 + multiple of 224 (FIR phase 0, bit word 0)
+	long long word_base;        // index in the bit arrays of the span's first bit word
+	int n_words;                // bit words [0, n_words) of the span are stored
 	int n_blocks;               // sub-blocks to run (each fused_block_outputs() envelope samples)
-	int pad_;
 };
 
 struct FusedParams {
 	const FusedSpan *spans;
 	int n_spans;
+	int *span_ticket;      // dynamic span scheduler (zeroed before launch)
+	Counters *ctr;         // only `wide` is written here
+	unsigned int *bits_p, *bits_q, *bits_b;
+	// parity tap (null in production): envelope of span 0, indexed from its j_begin
+	float *dbg_amp;
+	long long dbg_n;       // capacity of dbg_amp in samples
+};
+
+struct GateParams {
+	const unsigned int *bits_p, *bits_q, *bits_b;
+	long long j0;          // offset of bit 31 of word 0
+	long long n0, n1;      // offsets owned by this launch: tries are emitted for n0 <= n < n1
 	int accept_df18;
-	int want_tries;
-	CandRec *cands;
-	unsigned long long cand_cap;
 	unsigned long long *tries;
 	unsigned long long try_cap;
 	Counters *ctr;
-	int *span_ticket;      // dynamic span scheduler (zeroed before launch)
+};
+
+struct SliceParams {
+	const unsigned int *bits_b;
+	long long j0;
+	unsigned long long *tries;         // entries [ctr->try_mark, ctr->n_try) are sliced and get their DF class
+	unsigned long long try_cap;
+	CandRec *cands;
+	unsigned long long cand_cap;
+	Counters *ctr;
 	const unsigned long long *fix_tab;  // repair.h table, null unless fix_level > 0 (extension, off by default)
 	int fix_level;
-	// parity taps (all null in production): envelope / bit arrays of span 0, indexed from its j_begin
-	float *dbg_amp;
-	unsigned int *dbg_p, *dbg_q, *dbg_b;
-	long long dbg_n;       // capacity of dbg_amp in samples (dbg_p/q/b hold dbg_n/32 words)
 };
 
 // Geometry the host needs to cut spans.
-int fused_block_outputs();      // envelope samples per sub-block
-int fused_lookback();           // offsets emitted lag the FIR front by this many samples
+int fused_block_outputs();      // envelope samples per sub-block (896)
+int fused_span_quantum();       // span lengths are multiples of this many offsets (224 = lcm(28, 32))
 int fused_threads();
 size_t fused_smem_bytes();
-// Configures the kernel (max dynamic smem) and reports resident CTAs per SM; <0 on error.
+// Configures the kernels (max dynamic smem, syndrome table) and reports the workers (warps) per SM; <0 on error.
 int fused_prepare(int device);
-cudaError_t launch_fused(const FusedParams &p, int grid, cudaStream_t st);
+cudaError_t launch_fused(const FusedParams &p, int workers, cudaStream_t st);
+cudaError_t launch_gate(const GateParams &p, cudaStream_t st);
+cudaError_t launch_slice(const SliceParams &p, cudaStream_t st);
 
 }  // namespace adsb

@@ -170,6 +170,9 @@ int adsbdec_b200_telemetry(adsbdec_b200_t *h, adsbdec_b200_telemetry_t *out, int
 /* Per-kernel timing of the fused kernel alone (for the roofline line). */
 int adsbdec_b200_fused_time(adsbdec_b200_t *h, double *ms, uint64_t *launches,
                             uint64_t *samples, int reset);
+/* Time of the two light kernels behind it (k_gate + k_slice: bit arrays -> tries -> candidates),
+ * summed over the same launches. */
+int adsbdec_b200_gate_time(adsbdec_b200_t *h, double *ms, int reset);
 
 /* formatpkt(): fmt 0 = avr "*HEX;\n", 1 = avrmlat "@TTTTTTTTTTTT HEX;\n" (12 MHz
  * timestamp = ts*12/10, output.c:218), 2 = beast binary.  pkt must hold 256 bytes

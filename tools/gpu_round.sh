@@ -13,7 +13,7 @@ timeout 300 python tools/run_resident.py 60 6 > gpurun_out/${tag}_resident.log 2
 tail -4 gpurun_out/${tag}_resident.log
 if [ -x tools/ubench/pipes ]; then timeout 120 tools/ubench/pipes > gpurun_out/${tag}_pipes.log 2>&1; cat gpurun_out/${tag}_pipes.log; fi
 if [ "${3:-ncu}" = "ncu" ]; then
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_fused -s 1 -c 1 -f -o gpurun_out/${tag}_fused \
-      python tools/run_resident.py 20 2 > gpurun_out/${tag}_ncu.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k "regex:k_fused|k_gate|k_slice" -s 6 -c 3 -f -o gpurun_out/${tag}_fused \
+      python tools/run_resident.py 20 3 > gpurun_out/${tag}_ncu.log 2>&1
   tail -3 gpurun_out/${tag}_ncu.log
 fi

@@ -23,4 +23,4 @@ for i in range(steps):
     wall = (time.perf_counter() - t0) * 1e3
     print(f"   wall {wall:.3f} ms, kernels {dec.kernel_time(reset=True)[0]:.3f} ms, host {dec.host_time()}")
     ms, n, s = dec.fused_time(reset=True)
-    print(f"step {i}: frames {dec.num_frames}, fused {ms:.3f} ms / {n} launches, {2*s/ms/1e6 if ms else 0:.1f} GB/s")
+    print(f"step {i}: frames {dec.num_frames}, fused {ms:.3f} ms / {n} launches, {2*s/ms/1e6 if ms else 0:.1f} GB/s, gate+slice {dec.gate_time(reset=True):.3f} ms")
