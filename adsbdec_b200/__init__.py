@@ -100,10 +100,12 @@ def lib():
     """The loaded C-ABI library.  Raises if it has not been built - never falls back."""
     global _lib
     if _lib is None:
-        if not LIB_PATH.exists():
+        import os
+        path = Path(os.environ.get("ADSB_B200_LIB", LIB_PATH))  # kernel A/B runs (tools/try_variants.sh)
+        if not path.exists():
             raise FileNotFoundError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; "
                                     "g.build()'` (there is no CPU fallback)")
-        L = C.CDLL(str(LIB_PATH))
+        L = C.CDLL(str(path.resolve()))
         vp, u64, u32p = C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32)
         L.adsbdec_b200_default_config.argtypes = [C.POINTER(Config)]
         L.adsbdec_b200_default_config.restype = None

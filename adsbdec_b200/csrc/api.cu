@@ -74,9 +74,9 @@ constexpr int64_t kMinFused = 1 << 16;     // ranges smaller than this use the g
 constexpr int64_t kStageSlice = 4ll << 20; // pageable pushes are staged and uploaded in slices
 constexpr int64_t kBulkRead = 16ll << 20;  // decode_file: samples fetched per parallel read
 constexpr int64_t kPackSlice = 32ll << 20; // push_packed12: samples uploaded and unpacked per step
-constexpr unsigned long long kSpecCands = 1ull << 15;  // results copied back speculatively, at least
 constexpr unsigned long long kPendCap = 1ull << 18;
-constexpr int kSlots = 2;
+constexpr int kSlots = 3;                  // scan jobs in flight: three keep the GPU busy while the host hands frames out
+constexpr int kResolveSMs = 8;             // SMs k_fused leaves to the resolve chain of the previous job
 
 __global__ void k_reset_counters(Counters *c)
 {
@@ -120,6 +120,26 @@ inline double now_ms()
 	return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// ADSB_B200_TRACE=1: host timeline of the job pipeline on stderr at finish() (development aid).
+struct Tracer {
+	bool on = getenv("ADSB_B200_TRACE") != nullptr;
+	std::vector<std::pair<const char *, double>> ev;
+	void mark(const char *what)
+	{
+		if (on)
+			ev.emplace_back(what, now_ms());
+	}
+	void dump()
+	{
+		if (!on || ev.empty())
+			return;
+		const double t0 = ev.front().second;
+		for (auto &e : ev)
+			fprintf(stderr, "  [trace] %8.3f ms  %s\n", e.second - t0, e.first);
+		ev.clear();
+	}
+};
+
 inline int64_t align_down(int64_t v, int64_t a) { return v - (((v % a) + a) % a); }
 
 // One scan of offsets [n0, n1) over a device window, possibly still running.
@@ -142,6 +162,12 @@ struct adsbdec_b200 {
 	cudaStream_t st = nullptr;       // kernels + result copies
 	cudaStream_t st_copy = nullptr;  // uploads of sample batches
 	cudaStream_t st_d2h = nullptr;   // the rest of a job's results when the speculative copy fell short
+	// Ordering / greedy / compaction / statistics of a job's candidates: a chain of small kernels that runs
+	// BESIDE the next job's scan.  k_fused leaves kResolveSMs SMs free for it (a persistent CTA holds a
+	// whole SM's registers, so nothing else fits next to one).
+	cudaStream_t st_res = nullptr;
+	cudaEvent_t ev_scan[kSlots] = {};   // the slot's scan kernels are done (recorded on st)
+	cudaEvent_t ev_stats[kSlots] = {};  // the slot's lists have been read by the statistics pass
 	unsigned long long origin = 0;   // absolute index of local sample 0 (FIR phase / fidx wrap)
 
 	// stream position (local sample / offset indices, 0 = first sample ever pushed)
@@ -166,30 +192,27 @@ struct adsbdec_b200 {
 	// per-slot job state and result buffers
 	Job job[kSlots];
 	int next_slot = 0;
-	Counters *d_ctr[kSlots] = {nullptr, nullptr}, *h_ctr[kSlots] = {nullptr, nullptr};
-	CandRec *d_cands[kSlots] = {nullptr, nullptr};
-	unsigned char *h_cands[kSlots] = {nullptr, nullptr};  // accepted frames (FrameRec) or sorted candidates (CandRec)
-	unsigned long long cand_cap[kSlots] = {0, 0};
-	unsigned long long spec_n[kSlots] = {0, 0};  // records the job's speculative result copy covered
-	unsigned long long spec_want = kSpecCands;   // sized from what the last jobs returned
-	unsigned long long *d_tries[kSlots] = {nullptr, nullptr};
-	unsigned long long try_cap[kSlots] = {0, 0};
+	Counters *d_ctr[kSlots] = {}, *h_ctr[kSlots] = {};
+	CandRec *d_cands[kSlots] = {};
+	unsigned long long cand_cap[kSlots] = {};
+	unsigned long long *d_tries[kSlots] = {};
+	unsigned long long try_cap[kSlots] = {};
 	// on-GPU ordering + greedy resolve (kernels_resolve.cu)
 	ResolveBuffers rb[kSlots] = {};
-	int nb_cap[kSlots] = {0, 0};
-	SlotResolve *d_slot[kSlots] = {nullptr, nullptr}, *h_slot[kSlots] = {nullptr, nullptr};
-	FrameRec *d_acc[kSlots] = {nullptr, nullptr};  // accepted frames of the job, in order, stamped
+	int nb_cap[kSlots] = {};
+	SlotResolve *d_slot[kSlots] = {}, *h_slot[kSlots] = {};
+	FrameRec *d_acc[kSlots] = {};  // accepted frames of the job, in order, stamped
 	ResolveState *d_state = nullptr;
 	int last_slot = 0;
-	unsigned int *d_bits[kSlots] = {nullptr, nullptr};  // P | Q | B bit arrays of the slot's fused range
-	long long bits_cap[kSlots] = {0, 0};                // words per array
-	FusedSpan *d_fspans[kSlots] = {nullptr, nullptr};
-	int fspan_cap[kSlots] = {0, 0};
-	int *d_ticket[kSlots] = {nullptr, nullptr};
-	cudaEvent_t ev_done[kSlots] = {nullptr, nullptr};
-	cudaEvent_t ev_a[kSlots] = {nullptr, nullptr}, ev_b[kSlots] = {nullptr, nullptr};
-	cudaEvent_t ev_fa[kSlots] = {nullptr, nullptr}, ev_fb[kSlots] = {nullptr, nullptr};
-	cudaEvent_t ev_fc[kSlots] = {nullptr, nullptr};     // behind k_gate + k_slice of the slot's last fused range
+	unsigned int *d_bits[kSlots] = {};  // P | Q | B bit arrays of the slot's fused range
+	long long bits_cap[kSlots] = {};                // words per array
+	FusedSpan *d_fspans[kSlots] = {};
+	int fspan_cap[kSlots] = {};
+	int *d_ticket[kSlots] = {};
+	cudaEvent_t ev_done[kSlots] = {};
+	cudaEvent_t ev_a[kSlots] = {}, ev_b[kSlots] = {};
+	cudaEvent_t ev_fa[kSlots] = {}, ev_fb[kSlots] = {};
+	cudaEvent_t ev_fc[kSlots] = {};     // behind k_gate + k_slice of the slot's last fused range
 
 	// statistics
 	StreamStats *d_stats = nullptr, *h_stats = nullptr;
@@ -200,7 +223,11 @@ struct adsbdec_b200 {
 	int fused_ctas = 0;      // autonomous workers (warps) of the fused kernel on this device (0 = unavailable)
 
 	Resolver *res = nullptr;
-	std::vector<adsbdec_b200_frame_t> frames;
+	// Accepted frames, page-locked so that every job's result lands at its final place straight from the GPU:
+	// [0, n_vis) have been reached by the deqframe call schedule (what the API shows), [n_vis, n_total) are
+	// accepted by the greedy scan but still in front of the schedule (air.c:94-99).
+	adsbdec_b200_frame_t *frames = nullptr;
+	size_t frames_cap = 0, n_total = 0, n_vis = 0;
 	size_t emitted = 0;
 	size_t counted = 0;      // frames[0 .. counted) are in stat_ok already (the resolver counts while it copies)
 	uint32_t stat_ok[3] = {0, 0, 0};
@@ -208,6 +235,7 @@ struct adsbdec_b200 {
 	void *sink_user = nullptr;
 
 	double kernel_ms = 0, fused_ms = 0, gate_ms = 0;
+	Tracer tr;
 	uint64_t launches = 0, fused_launches = 0, fused_samples = 0;
 
 	std::vector<adsbdec_b200_candidate_t> cand_tmp;
@@ -228,16 +256,21 @@ struct adsbdec_b200 {
 
 namespace {
 
+int sync_compute(adsbdec_b200 *h)
+{
+	CU(cudaStreamSynchronize(h->st));
+	CU(cudaStreamSynchronize(h->st_res));
+	return 0;
+}
+
 int alloc_slot_outputs(adsbdec_b200 *h, int s, unsigned long long cand_cap, unsigned long long try_cap)
 {
 	if (cand_cap != h->cand_cap[s]) {
 		if (h->d_cands[s]) cudaFree(h->d_cands[s]);
-		if (h->h_cands[s]) cudaFreeHost(h->h_cands[s]);
 		if (h->d_acc[s]) cudaFree(h->d_acc[s]);
 		if (h->rb[s].sorted) cudaFree(h->rb[s].sorted);
 		if (h->rb[s].accept) cudaFree(h->rb[s].accept);
 		h->d_cands[s] = h->rb[s].sorted = nullptr;
-		h->h_cands[s] = nullptr;
 		h->d_acc[s] = nullptr;
 		h->rb[s].accept = nullptr;
 		h->cand_cap[s] = 0;  // a failed allocation below must not leave the old capacity behind
@@ -245,7 +278,6 @@ int alloc_slot_outputs(adsbdec_b200 *h, int s, unsigned long long cand_cap, unsi
 		CU(cudaMalloc(&h->d_acc[s], cand_cap * sizeof(FrameRec)));
 		CU(cudaMalloc(&h->rb[s].sorted, cand_cap * sizeof(CandRec)));
 		CU(cudaMalloc(&h->rb[s].accept, cand_cap));
-		CU(cudaMallocHost(&h->h_cands[s], cand_cap * sizeof(FrameRec)));  // accepted frames / sorted candidates land here
 		h->cand_cap[s] = cand_cap;
 	}
 	if (try_cap != h->try_cap[s]) {
@@ -267,7 +299,7 @@ int presize_lists(adsbdec_b200 *h, int s, int64_t offsets)
 	const unsigned long long tc = std::max<unsigned long long>(h->try_cap[s], (unsigned long long)offsets / 24);
 	if (cc == h->cand_cap[s] && tc == h->try_cap[s])
 		return 0;
-	CU(cudaStreamSynchronize(h->st));
+	RC(sync_compute(h));
 	return alloc_slot_outputs(h, s, cc, tc);
 }
 
@@ -275,7 +307,7 @@ int ensure_buckets(adsbdec_b200 *h, int s, int nb)
 {
 	if (nb + 1 <= h->nb_cap[s])
 		return 0;
-	CU(cudaStreamSynchronize(h->st));
+	RC(sync_compute(h));
 	ResolveBuffers &rb = h->rb[s];
 	unsigned int **arr[7] = {&rb.cnt, &rb.cur, &rb.off, &rb.bacc, &rb.bacc_x, &rb.bdrift, &rb.bdrift_x};
 	const int cap = nb + 1 + 4096;
@@ -447,9 +479,11 @@ int enqueue_job(adsbdec_b200 *h, int s, bool force_generic)
 	Job &j = h->job[s];
 	j.used_fused = false;
 	if (j.n1 <= j.n0) {
-		CU(cudaEventRecord(h->ev_done[s], h->st));
+		CU(cudaEventRecord(h->ev_done[s], h->st_res));
 		return 0;
 	}
+	// the statistics pass of the job that used this slot before reads its try list on the resolve stream
+	CU(cudaStreamWaitEvent(h->st, h->ev_stats[s], 0));
 	force_generic = force_generic || h->cfg.kernel == 1 || h->fused_ctas <= 0;
 	k_reset_counters<<<1, 1, 0, h->st>>>(h->d_ctr[s]);
 	CU(cudaGetLastError());
@@ -482,40 +516,34 @@ int enqueue_job(adsbdec_b200 *h, int s, bool force_generic)
 		h->launches += 1;
 	}
 	// order the candidates on the GPU; for a stream job also apply the greedy skip there, so that
-	// only accepted frames come back
+	// only accepted frames come back.  All of it on the resolve stream, behind the scan.
 	RC(ensure_buckets(h, s, resolve_bucket_count(j.n0, j.n1)));
-	const void *result;
-	const size_t rec = j.resolve ? sizeof(FrameRec) : sizeof(CandRec);
+	CU(cudaEventRecord(h->ev_scan[s], h->st));
+	CU(cudaStreamWaitEvent(h->st_res, h->ev_scan[s], 0));
 	if (j.resolve) {
 		CU(launch_resolve(h->rb[s], h->d_cands[s], h->d_ctr[s], h->cand_cap[s], j.n0, j.n1, h->d_state, h->d_slot[s],
-		                  h->d_acc[s], h->cand_cap[s], h->st));
+		                  h->d_acc[s], h->cand_cap[s], h->st_res));
 		h->launches += 10;
-		result = h->d_acc[s];
 	} else {
-		CU(launch_sort(h->rb[s], h->d_cands[s], h->d_ctr[s], h->cand_cap[s], j.n0, j.n1, h->st));
+		CU(launch_sort(h->rb[s], h->d_cands[s], h->d_ctr[s], h->cand_cap[s], j.n0, j.n1, h->st_res));
 		h->launches += 4;
-		result = h->rb[s].sorted;
 	}
-	CU(cudaEventRecord(h->ev_b[s], h->st));
-	CU(cudaMemcpyAsync(h->h_ctr[s], h->d_ctr[s], sizeof(Counters), cudaMemcpyDeviceToHost, h->st));
+	CU(cudaEventRecord(h->ev_b[s], h->st_res));
+	CU(cudaMemcpyAsync(h->h_ctr[s], h->d_ctr[s], sizeof(Counters), cudaMemcpyDeviceToHost, h->st_res));
 	if (j.resolve)
-		CU(cudaMemcpyAsync(h->h_slot[s], h->d_slot[s], sizeof(SlotResolve), cudaMemcpyDeviceToHost, h->st));
-	// The result count is only known on the device: copy what recent jobs needed plus a margin now, in
-	// stream order; complete_job fetches any remainder on a stream of its own (a copy queued on THIS
-	// stream would sit behind the next job and stall the host for a whole scan).
-	h->spec_n[s] = std::min(h->spec_want, h->cand_cap[s]);
-	CU(cudaMemcpyAsync(h->h_cands[s], result, h->spec_n[s] * rec, cudaMemcpyDeviceToHost, h->st));
-	CU(cudaEventRecord(h->ev_done[s], h->st));
+		CU(cudaMemcpyAsync(h->h_slot[s], h->d_slot[s], sizeof(SlotResolve), cudaMemcpyDeviceToHost, h->st_res));
+	// (the results themselves are fetched by complete_job, when their number and their place are known)
+	CU(cudaEventRecord(h->ev_done[s], h->st_res));
 	return 0;
 }
 
 void emit_new_frames(adsbdec_b200 *h)
 {
-	if (!h->sink && h->counted == h->frames.size()) {
-		h->emitted = h->frames.size();  // nothing to call, nothing to count
+	if (!h->sink && h->counted == h->n_vis) {
+		h->emitted = h->n_vis;  // nothing to call, nothing to count
 		return;
 	}
-	for (; h->emitted < h->frames.size(); h->emitted++) {
+	for (; h->emitted < h->n_vis; h->emitted++) {
 		const adsbdec_b200_frame_t &f = h->frames[h->emitted];
 		if (h->emitted >= h->counted) {
 			const int df = f.bytes[0] >> 3;
@@ -525,7 +553,32 @@ void emit_new_frames(adsbdec_b200 *h)
 		if (h->sink)
 			h->sink(f.bytes, f.len, f.ts, f.pw, h->sink_user);
 	}
+	// a consumer that takes its frames through the sink never has to call clear_frames: the store is emptied
+	// for it once it holds a million delivered frames (a live stream would otherwise grow it for ever)
+	if (h->sink && h->n_vis >= (1u << 20))
+		adsbdec_b200_clear_frames(h);
 }
+
+// Room for `more` frames behind the n_total the store holds.
+int reserve_frames(adsbdec_b200 *h, size_t more)
+{
+	if (h->n_total + more <= h->frames_cap)
+		return 0;
+	size_t cap = std::max<size_t>(h->frames_cap * 2, 1 << 16);
+	while (cap < h->n_total + more)
+		cap *= 2;
+	adsbdec_b200_frame_t *p = nullptr;
+	CU(cudaMallocHost(&p, cap * sizeof(adsbdec_b200_frame_t)));
+	if (h->n_total)
+		memcpy(p, h->frames, h->n_total * sizeof(adsbdec_b200_frame_t));
+	if (h->frames)
+		cudaFreeHost(h->frames);
+	h->frames = p;
+	h->frames_cap = cap;
+	return 0;
+}
+
+inline int next_of(int s) { return (s + 1) % kSlots; }
 
 // Stats pass for the tries of slot s (and the pending list), entirely on the GPU: a try counts if
 // it lies below the resolver's scan end and outside the accepted frames of the job (which are
@@ -539,14 +592,15 @@ int stats_pass(adsbdec_b200 *h, int s, bool with_slot_list)
 	if (with_slot_list) {
 		CU(launch_count_tries_frames(h->d_tries[s], &h->d_ctr[s]->n_try, h->try_cap[s], h->d_acc[s], h->d_slot[s],
 		                             h->cand_cap[s], h->rb[s], h->job[s].n0, h->job[s].n1, scan_end, h->d_pend[pout],
-		                             &h->d_stats->n_pend[pout], kPendCap, h->d_stats, h->st));
+		                             &h->d_stats->n_pend[pout], kPendCap, h->d_stats, h->st_res));
 		h->launches += 1;
 	}
 	CU(launch_count_tries_frames(h->d_pend[pin], &h->d_stats->n_pend[pin], kPendCap, h->d_acc[s], h->d_slot[s],
 	                             h->cand_cap[s], h->rb[s], h->job[s].n0, h->job[s].n1, scan_end, h->d_pend[pout],
-	                             &h->d_stats->n_pend[pout], kPendCap, h->d_stats, h->st));
-	k_zero_u64<<<1, 1, 0, h->st>>>(&h->d_stats->n_pend[pin]);
+	                             &h->d_stats->n_pend[pout], kPendCap, h->d_stats, h->st_res));
+	k_zero_u64<<<1, 1, 0, h->st_res>>>(&h->d_stats->n_pend[pin]);
 	CU(cudaGetLastError());
+	CU(cudaEventRecord(h->ev_stats[s], h->st_res));
 	h->launches += 2;
 	h->pend_in = pout;
 	return 0;
@@ -565,7 +619,9 @@ int complete_job(adsbdec_b200 *h, int s)
 		bool force_generic = false;
 		for (int attempt = 0;; attempt++) {
 			const double t0 = now_ms();
+			h->tr.mark("complete_job: wait");
 			CU(cudaEventSynchronize(h->ev_done[s]));
+			h->tr.mark("complete_job: job done");
 			h->tel.wait_job_ms += now_ms() - t0;
 			float ms = 0;
 			cudaEventElapsedTime(&ms, h->ev_a[s], h->ev_b[s]);
@@ -587,32 +643,22 @@ int complete_job(adsbdec_b200 *h, int s)
 				return fail(ADSB_B200_ERANGE, "candidate lists keep overflowing");
 			// Redo.  Everything issued since this job started ran on a truncated list: drain the GPU,
 			// put the scan position back to where it was before this job, grow the lists and re-issue
-			// this job and the (newer) one in the other slot.
-			CU(cudaStreamSynchronize(h->st));
+			// this job and the newer ones in flight.
+			RC(sync_compute(h));
 			if (j.resolve)
 				CU(launch_set_state(h->d_state, h->h_slot[s]->span0_start, h->h_slot[s]->span0_end,
-				                    h->h_slot[s]->drift0, h->st));
+				                    h->h_slot[s]->drift0, h->st_res));
 			if (c.overflow & 3u)
 				RC(alloc_slot_outputs(h, s, (c.overflow & 1u) ? h->cand_cap[s] * 4 : h->cand_cap[s],
 				                      (c.overflow & 2u) ? h->try_cap[s] * 4 : h->try_cap[s]));
 			RC(enqueue_job(h, s, force_generic));
-			if (h->job[1 - s].active)
-				RC(enqueue_job(h, 1 - s, false));
+			for (int t = next_of(s); t != s; t = next_of(t))  // the newer jobs, oldest first
+				if (h->job[t].active)
+					RC(enqueue_job(h, t, false));
 		}
 		h->tel.candidates += h->h_ctr[s]->n_cand;
 		h->tel.tries += h->cfg.collect_stats ? h->h_ctr[s]->n_try : 0;
 		n_res = j.resolve ? (size_t)h->h_slot[s]->n_accept : (size_t)std::min<unsigned long long>(h->h_ctr[s]->n_cand, h->cand_cap[s]);
-		if (n_res > h->spec_n[s]) {
-			const size_t rec = j.resolve ? sizeof(FrameRec) : sizeof(CandRec);
-			const unsigned char *src = j.resolve ? reinterpret_cast<const unsigned char *>(h->d_acc[s])
-			                                     : reinterpret_cast<const unsigned char *>(h->rb[s].sorted);
-			const size_t done = (size_t)h->spec_n[s];
-			CU(cudaMemcpyAsync(h->h_cands[s] + done * rec, src + done * rec, (n_res - done) * rec,
-			                   cudaMemcpyDeviceToHost, h->st_d2h));  // the job is done: no dependency to wait for
-			CU(cudaStreamSynchronize(h->st_d2h));
-		}
-		// next time copy 1.25 x what this job returned up front (never less than the floor)
-		h->spec_want = std::max<unsigned long long>(kSpecCands, (unsigned long long)n_res + n_res / 4 + 1024);
 	} else {
 		CU(cudaEventSynchronize(h->ev_done[s]));
 	}
@@ -620,17 +666,34 @@ int complete_job(adsbdec_b200 *h, int s)
 	static_assert(sizeof(CandRec) == sizeof(adsbdec_b200_candidate_t), "record layouts must agree");
 	static_assert(sizeof(FrameRec) == sizeof(adsbdec_b200_frame_t), "record layouts must agree");
 	if (!j.resolve) {
-		const adsbdec_b200_candidate_t *res = reinterpret_cast<const adsbdec_b200_candidate_t *>(h->h_cands[s]);
-		h->cand_tmp.assign(res, res + n_res);  // chunk mode: sorted candidates for the caller
+		h->cand_tmp.resize(n_res);  // chunk mode: sorted candidates for the caller
+		if (n_res)
+			CU(cudaMemcpy(h->cand_tmp.data(), h->rb[s].sorted, n_res * sizeof(CandRec), cudaMemcpyDeviceToHost));
 		return 0;
 	}
-	// The greedy skip and the timestamps (demod.c:99, :128, :134) have been applied on the GPU; what
-	// is left is the deqframe call schedule (air.c:94-99), which decides how far the scan has come.
+	// The greedy skip and the timestamps (demod.c:99, :128, :134) have been applied on the GPU.  The job's
+	// accepted frames are fetched to their final place behind the earlier ones (the job is done: the copy
+	// has nothing to wait for and runs beside whatever the GPU does next); what is left for the host is
+	// the deqframe call schedule (air.c:94-99), which decides how far the scan has come - a few binary
+	// searches over the new frames, no copy.
 	const double t2 = now_ms();
-	h->res->feed_frames(reinterpret_cast<const adsbdec_b200_frame_t *>(h->h_cands[s]), n_res,
-	                    (uint64_t)std::max<int64_t>(j.n1, 0), (uint64_t)j.total_out, h->frames, h->stat_ok);
-	h->counted = h->frames.size();
+	if (n_res) {
+		RC(reserve_frames(h, n_res));
+		CU(cudaMemcpyAsync(h->frames + h->n_total, h->d_acc[s], n_res * sizeof(FrameRec), cudaMemcpyDeviceToHost,
+		                   h->st_d2h));
+		CU(cudaStreamSynchronize(h->st_d2h));
+		h->n_total += n_res;
+	}
+	h->n_vis = h->res->advance_frames(h->frames, h->n_vis, h->n_total, (uint64_t)std::max<int64_t>(j.n1, 0),
+	                                  (uint64_t)j.total_out);
+	h->counted = h->n_vis;
+	// (Ok counters: the GPU counted the job's accepted frames per class; the few the call schedule has not
+	// reached yet are taken off again wherever the counters are read)
+	if (scanned)
+		for (int c = 0; c < 3; c++)
+			h->stat_ok[c] += h->h_slot[s]->ok[c];
 	const double t3 = now_ms();
+	h->tr.mark("complete_job: frames fed");
 	if (scanned) {
 		RC(stats_pass(h, s, true));
 		h->last_slot = s;
@@ -646,10 +709,9 @@ int complete_job(adsbdec_b200 *h, int s)
 
 int complete_all(adsbdec_b200 *h)
 {
-	// oldest first
-	const int a = h->next_slot, b = 1 - h->next_slot;
-	RC(complete_job(h, a));
-	RC(complete_job(h, b));
+	// oldest first: slots are used round-robin, next_slot holds the oldest job
+	for (int k = 0, s = h->next_slot; k < kSlots; k++, s = next_of(s))
+		RC(complete_job(h, s));
 	return 0;
 }
 
@@ -669,8 +731,10 @@ int submit_window(adsbdec_b200 *h, const uint16_t *buf, int64_t u0, int64_t u1)
 	j.resolve = true;
 	j.active = true;
 	h->own_next = j.n1;
+	h->tr.mark("submit: enqueue");
 	RC(enqueue_job(h, s, false));
-	h->next_slot = 1 - s;
+	h->tr.mark("submit: enqueued");
+	h->next_slot = next_of(s);
 	return 0;
 }
 
@@ -726,7 +790,8 @@ int flush_batch(adsbdec_b200 *h)
 	// The other device buffer is about to be refilled (carry copy now, uploads next), and a job may
 	// have to be re-run on its window (list overflow, out-of-range samples): finish the job that used
 	// it first.  Its host work overlaps the scan that was just submitted.
-	RC(complete_job(h, h->next_slot));
+	for (int k = 0, t = h->next_slot; k < kSlots - 1; k++, t = next_of(t))  // all but the one just submitted
+		RC(complete_job(h, t));
 	RC(carry_to_next(h, buf, u0, u1));
 	// dev[old] may be overwritten once this job and the carry copy out of it are done
 	CU(cudaEventRecord(h->ev_dev_free[old], h->st));
@@ -805,6 +870,7 @@ int adsbdec_b200_open(const adsbdec_b200_config_t *cfg, adsbdec_b200_t **out)
 		bool ok = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) == cudaSuccess &&
 		          cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking) == cudaSuccess &&
 		          cudaStreamCreateWithFlags(&h->st_d2h, cudaStreamNonBlocking) == cudaSuccess &&
+		          cudaStreamCreateWithFlags(&h->st_res, cudaStreamNonBlocking) == cudaSuccess &&
 		          cudaEventCreateWithFlags(&h->ev_h2d, cudaEventDisableTiming) == cudaSuccess &&
 		          cudaMalloc(&h->d_stats, sizeof(StreamStats)) == cudaSuccess &&
 		          cudaMalloc(&h->d_state, sizeof(ResolveState)) == cudaSuccess &&
@@ -821,6 +887,8 @@ int adsbdec_b200_open(const adsbdec_b200_config_t *cfg, adsbdec_b200_t **out)
 			     cudaEventCreate(&h->ev_fa[s]) == cudaSuccess && cudaEventCreate(&h->ev_fb[s]) == cudaSuccess &&
 			     cudaEventCreate(&h->ev_fc[s]) == cudaSuccess &&
 			     cudaEventCreateWithFlags(&h->ev_done[s], cudaEventDisableTiming) == cudaSuccess &&
+			     cudaEventCreateWithFlags(&h->ev_scan[s], cudaEventDisableTiming) == cudaSuccess &&
+			     cudaEventCreateWithFlags(&h->ev_stats[s], cudaEventDisableTiming) == cudaSuccess &&
 			     cudaMalloc(&h->d_ctr[s], sizeof(Counters)) == cudaSuccess &&
 			     cudaMalloc(&h->d_slot[s], sizeof(SlotResolve)) == cudaSuccess &&
 			     cudaMemset(h->d_slot[s], 0, sizeof(SlotResolve)) == cudaSuccess &&
@@ -850,7 +918,10 @@ int adsbdec_b200_open(const adsbdec_b200_config_t *cfg, adsbdec_b200_t **out)
 				rc = fail(ADSB_B200_ENODEV, "fused kernel cannot be configured on device %d", cfg->device);
 				break;
 			}
-			h->fused_ctas = per_sm * prop.multiProcessorCount;
+			// leave a few SMs to the resolve chain of the previous job (see st_res)
+			const int sms = prop.multiProcessorCount > 4 * kResolveSMs ? prop.multiProcessorCount - kResolveSMs
+			                                                            : prop.multiProcessorCount;
+			h->fused_ctas = per_sm * sms;
 		}
 		// reserved[3]: opt-in error repair (repair.h) - 0 = the reference's behaviour
 		if (cfg->reserved[3] > 2) {
@@ -884,6 +955,7 @@ void adsbdec_b200_close(adsbdec_b200_t *h)
 	cudaSetDevice(h->device);
 	if (h->st_copy) cudaStreamSynchronize(h->st_copy);
 	if (h->st) cudaStreamSynchronize(h->st);
+	if (h->st_res) cudaStreamSynchronize(h->st_res);
 	for (int i = 0; i < 2; i++) {
 		if (h->dev[i]) cudaFree(h->dev[i]);
 		if (h->pin[i]) cudaFreeHost(h->pin[i]);
@@ -894,7 +966,6 @@ void adsbdec_b200_close(adsbdec_b200_t *h)
 	for (int s = 0; s < kSlots; s++) {
 		if (h->d_tries[s]) cudaFree(h->d_tries[s]);
 		if (h->d_cands[s]) cudaFree(h->d_cands[s]);
-		if (h->h_cands[s]) cudaFreeHost(h->h_cands[s]);
 		if (h->d_ctr[s]) cudaFree(h->d_ctr[s]);
 		if (h->h_ctr[s]) cudaFreeHost(h->h_ctr[s]);
 		if (h->d_acc[s]) cudaFree(h->d_acc[s]);
@@ -918,6 +989,8 @@ void adsbdec_b200_close(adsbdec_b200_t *h)
 		if (h->ev_fc[s]) cudaEventDestroy(h->ev_fc[s]);
 		if (h->d_bits[s]) cudaFree(h->d_bits[s]);
 		if (h->ev_done[s]) cudaEventDestroy(h->ev_done[s]);
+		if (h->ev_scan[s]) cudaEventDestroy(h->ev_scan[s]);
+		if (h->ev_stats[s]) cudaEventDestroy(h->ev_stats[s]);
 	}
 	if (h->d_fix) cudaFree(h->d_fix);
 	if (h->d_pk) cudaFree(h->d_pk);
@@ -933,6 +1006,8 @@ void adsbdec_b200_close(adsbdec_b200_t *h)
 	if (h->st) cudaStreamDestroy(h->st);
 	if (h->st_copy) cudaStreamDestroy(h->st_copy);
 	if (h->st_d2h) cudaStreamDestroy(h->st_d2h);
+	if (h->st_res) cudaStreamDestroy(h->st_res);
+	if (h->frames) cudaFreeHost(h->frames);
 	delete h->res;
 	delete h;
 }
@@ -945,7 +1020,7 @@ int adsbdec_b200_reset(adsbdec_b200_t *h, uint64_t start_sample)
 		return fail(ADSB_B200_EINVAL, "start_sample must be a multiple of 4");
 	CU(cudaSetDevice(h->device));
 	CU(cudaStreamSynchronize(h->st_copy));
-	CU(cudaStreamSynchronize(h->st));
+	RC(sync_compute(h));
 	h->origin = start_sample;
 	h->cfg.start_sample = start_sample;
 	h->pushed = 0;
@@ -963,7 +1038,7 @@ int adsbdec_b200_reset(adsbdec_b200_t *h, uint64_t start_sample)
 		h->job[s].active = false;
 	delete h->res;
 	h->res = new Resolver(h->cfg.emulate_reference_tail != 0);
-	h->frames.clear();  // keeps its capacity
+	h->n_total = h->n_vis = 0;  // the store keeps its capacity
 	h->emitted = 0;
 	h->counted = 0;
 	for (int i = 0; i < 3; i++)
@@ -1108,6 +1183,7 @@ int adsbdec_b200_push_device(adsbdec_b200_t *h, const void *dev_samples, size_t 
 	if (n == 0)
 		return 0;
 	CU(cudaSetDevice(h->device));
+	h->tr.mark("push_device");
 	RC(ensure_batch_buffers(h, false));
 	const uint16_t *src = (const uint16_t *)dev_samples;
 	const int64_t seam = 2 * kLookahead + 2 * kCarryBack;  // samples of the piece the seam window needs
@@ -1168,7 +1244,7 @@ int adsbdec_b200_push_device(adsbdec_b200_t *h, const void *dev_samples, size_t 
 	RC(complete_all(h));  // the caller's memory is no longer needed after this ...
 	h->dev_fill = 0;
 	RC(carry_to_next(h, src, piece_u0, piece_u1));  // ... except for the tail we keep
-	CU(cudaStreamSynchronize(h->st));
+	CU(cudaStreamSynchronize(h->st));  // (the resolve stream is idle: complete_all waited for both jobs)
 	return 0;
 }
 
@@ -1227,11 +1303,22 @@ int adsbdec_b200_finish(adsbdec_b200_t *h)
 	if (h->dev[0] && (h->pin_fill > 0 || h->dev_fill > 0))
 		RC(flush_batch(h));
 	RC(complete_all(h));
-	h->res->finish(h->frames, h->stat_ok);  // the stream path only ever feeds stamped frames: counted as they are accepted
-	h->counted = h->frames.size();
+	// the stream path only ever feeds stamped frames, counted on the GPU: what the call schedule never reaches
+	// (air.c:243-244 drops it) is taken off the counters
+	// the last deqframe calls; what they do not reach is dropped (air.c:243-244) and comes off the Ok counters,
+	// which the GPU keeps for everything it accepted
+	h->n_vis = h->res->finish_frames(h->frames, h->n_vis, h->n_total);
+	for (size_t i = h->n_vis; i < h->n_total; i++) {
+		const int df = h->frames[i].bytes[0] >> 3;
+		h->stat_ok[df == 11 ? 0 : df == 17 ? 1 : 2]--;
+	}
+	h->n_total = h->n_vis;
+	h->counted = h->n_vis;
 	RC(stats_pass(h, h->last_slot, false));  // pending tries against the final scan end
 	emit_new_frames(h);
-	CU(cudaStreamSynchronize(h->st));
+	RC(sync_compute(h));
+	h->tr.mark("finish: done");
+	h->tr.dump();
 	h->finished = true;
 	return 0;
 }
@@ -1349,32 +1436,39 @@ int adsbdec_b200_stats(adsbdec_b200_t *h, uint32_t try_[3], uint32_t ok[3])
 		return fail(ADSB_B200_EINVAL, "null handle");
 	CU(cudaSetDevice(h->device));
 	RC(complete_all(h));
-	CU(cudaMemcpyAsync(h->h_stats, h->d_stats, sizeof(StreamStats), cudaMemcpyDeviceToHost, h->st));
-	CU(cudaStreamSynchronize(h->st));
+	CU(cudaMemcpyAsync(h->h_stats, h->d_stats, sizeof(StreamStats), cudaMemcpyDeviceToHost, h->st_res));
+	CU(cudaStreamSynchronize(h->st_res));
 	if (h->h_stats->pend_overflow)
 		return fail(ADSB_B200_ERANGE, "pending-try list overflow");
+	uint32_t pend[3] = {0, 0, 0};  // frames the GPU has accepted but the deqframe call schedule has not reached
+	for (size_t k = h->n_vis; k < h->n_total; k++) {
+		const int df = h->frames[k].bytes[0] >> 3;
+		pend[df == 11 ? 0 : df == 17 ? 1 : 2]++;
+	}
 	for (int i = 0; i < 3; i++) {
 		if (try_) try_[i] = h->h_stats->stat_try[i];
-		if (ok) ok[i] = h->stat_ok[i];
+		if (ok) ok[i] = h->stat_ok[i] - pend[i];
 	}
 	return 0;
 }
 
-size_t adsbdec_b200_num_frames(const adsbdec_b200_t *h) { return h ? h->frames.size() : 0; }
+size_t adsbdec_b200_num_frames(const adsbdec_b200_t *h) { return h ? h->n_vis : 0; }
 const adsbdec_b200_frame_t *adsbdec_b200_frames(const adsbdec_b200_t *h)
 {
-	return h && !h->frames.empty() ? h->frames.data() : nullptr;
+	return h && h->n_vis ? h->frames : nullptr;
 }
 void adsbdec_b200_clear_frames(adsbdec_b200_t *h)
 {
-	if (!h)
+	if (!h || h->emitted != h->n_vis)
 		return;
-	// keep the last frame: its span may still cover tries of the next stats pass
-	if (h->emitted == h->frames.size() && h->frames.size() > 1) {
-		h->frames.erase(h->frames.begin(), h->frames.end() - 1);
-		h->emitted = h->frames.size();
-		h->counted = h->frames.size();
-	}
+	// every frame shown so far goes; the ones still in front of the call schedule move up
+	const size_t keep = h->n_total - h->n_vis;
+	if (keep)
+		memmove(h->frames, h->frames + h->n_vis, keep * sizeof(adsbdec_b200_frame_t));
+	h->n_total = keep;
+	h->n_vis = 0;
+	h->emitted = 0;
+	h->counted = 0;
 }
 
 int adsbdec_b200_kernel_time(adsbdec_b200_t *h, double *ms, uint64_t *launches, int reset)

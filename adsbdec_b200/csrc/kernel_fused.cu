@@ -61,6 +61,15 @@ namespace {
 #ifndef ADSB_WPC
 #define ADSB_WPC 20  // warps per CTA
 #endif
+#ifndef ADSB_PQ_INT
+#define ADSB_PQ_INT 0      // preamble comparisons on the integer pipe instead of FFMA
+#endif
+#ifndef ADSB_B_INT
+#define ADSB_B_INT 0       // PPM comparison on the integer pipe instead of FADD
+#endif
+#ifndef ADSB_BITS_SPLIT
+#define ADSB_BITS_SPLIT 0  // two funnel-shift chains per bit stream
+#endif
 #ifndef ADSB_MINB
 #define ADSB_MINB 1  // CTAs per SM
 #endif
@@ -333,6 +342,9 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 				// run handled here: 32k + lane - LAG2 (uniform sign per 8-lane group).  In sub-block 0 the
 				// first eight lanes work on whatever the ring holds: their words (index < 0) are not stored.
 				uint32_t P = 0, Q = 0, B = 0;
+#if ADSB_BITS_SPLIT
+				uint32_t P2 = 0, Q2 = 0, B2 = 0;
+#endif
 				{
 					int q2 = q_fir - LAG2;
 					if (q2 < 0) q2 += RUNS;
@@ -366,15 +378,44 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 					for (int i = 0; i < R; i++) {
 						// demod.c:107, first half: p1 > 2*s1 with p1 = f[n], s1 = f[n+5]
 						//   <=> 2*s1 - p1 < 0 (exact small integers, so the sign bit is the answer)
-						const float e = __fmaf_rn(f[i + 5], 2.0f, -f[i]);
-						P = __funnelshift_l(__float_as_uint(e), P, 1);
 						// second half, as seen from m = n+30: p2 = f[m+5] > 2*s2, s2 = f[m]
-						const float e2 = __fmaf_rn(f[i], 2.0f, -f[i + 5]);
-						Q = __funnelshift_l(__float_as_uint(e2), Q, 1);
+#if ADSB_PQ_INT
+						// the same on the integer pipe: for integer-valued floats x > 2y <=> bits(x) > bits(y) + 2^23
+						const uint32_t e = __float_as_uint(f[i + 5]) + 0x00800000u - __float_as_uint(f[i]);
+						const uint32_t e2 = __float_as_uint(f[i]) + 0x00800000u - __float_as_uint(f[i + 5]);
+#else
+						const uint32_t e = __float_as_uint(__fmaf_rn(f[i + 5], 2.0f, -f[i]));
+						const uint32_t e2 = __float_as_uint(__fmaf_rn(f[i], 2.0f, -f[i + 5]));
+#endif
 						// demod.c:34: a[n] > a[n+5]  <=>  a[n+5] - a[n] < 0  (no FTZ: x-y==0 iff x==y)
-						const float d = __fsub_rn(a[i + 5], a[i]);
-						B = __funnelshift_l(__float_as_uint(d), B, 1);
+#if ADSB_B_INT
+						// non-negative floats order like their bit patterns
+						const uint32_t d = __float_as_uint(a[i + 5]) - __float_as_uint(a[i]);
+#else
+						const uint32_t d = __float_as_uint(__fsub_rn(a[i + 5], a[i]));
+#endif
+#if ADSB_BITS_SPLIT
+						// two chains per bit stream: the dependent funnel shifts are the longest chain of the stage
+						if (i < R / 2) {
+							P = __funnelshift_l(e, P, 1);
+							Q = __funnelshift_l(e2, Q, 1);
+							B = __funnelshift_l(d, B, 1);
+						} else {
+							P2 = __funnelshift_l(e, P2, 1);
+							Q2 = __funnelshift_l(e2, Q2, 1);
+							B2 = __funnelshift_l(d, B2, 1);
+						}
+#else
+						P = __funnelshift_l(e, P, 1);
+						Q = __funnelshift_l(e2, Q, 1);
+						B = __funnelshift_l(d, B, 1);
+#endif
 					}
+#if ADSB_BITS_SPLIT
+					P = (P << (R / 2)) | P2;
+					Q = (Q << (R / 2)) | Q2;
+					B = (B << (R / 2)) | B2;
+#endif
 				}
 				// 8 runs x 28 bits -> 7 words x 32 bits inside each 8-lane group (MSB = first offset)
 				const uint32_t Pn = __shfl_down_sync(FULL, P, 1, 8);
@@ -409,7 +450,13 @@ constexpr int GATE_STAGE = 512;  // tries staged per warp (2 KB), as 32-bit offs
 
 // The try list gets the bare offsets here; k_slice, which reads the first frame bits anyway, adds the DF
 // class (demod.c:46-81: 10001 = DF17, 10010 = DF18, 01011 = DF11) that the statistics pass wants.
-__global__ void __launch_bounds__(256) k_gate(const GateParams p)
+#ifndef ADSB_GATE_MINB
+#define ADSB_GATE_MINB 8
+#endif
+#ifndef ADSB_SLICE_MINB
+#define ADSB_SLICE_MINB 6
+#endif
+__global__ void __launch_bounds__(256, ADSB_GATE_MINB) k_gate(const GateParams p)
 {
 	//@region gate
 	__shared__ uint32_t stage_all[8][GATE_STAGE];
@@ -453,30 +500,49 @@ __global__ void __launch_bounds__(256) k_gate(const GateParams p)
 		staged = 0;
 	};
 
+	// The six words of the NEXT step are requested before this step is worked on: the kernel is a chain of
+	// L2 loads -> a few logic ops -> shared-memory appends, and one step in flight per warp left the
+	// schedulers idle half of the time (profiles/r2c).
+	struct Words {
+		uint32_t p0, q0, q1, b2, b3, b4;
+	};
+	auto fetch = [&](uint32_t g) {
+		Words w = {0u, 0u, 0u, 0u, 0u, 0u};
+		if (g <= g_hi) {
+			w.p0 = bp[g];
+			w.q0 = bq[g];
+			w.q1 = bq[g + 1];
+			w.b2 = bb[g + 2];
+			w.b3 = bb[g + 3];
+			w.b4 = bb[g + 4];
+		}
+		return w;
+	};
+	Words nxt = fetch(g_lo + warp * 32u + lane);
 	for (uint32_t g0 = g_lo + warp * 32u; g0 <= g_hi; g0 += stride) {
 		const uint32_t g = g0 + lane;
+		const Words w = nxt;
+		if (g0 + stride <= g_hi && g0 + stride > g0)
+			nxt = fetch(g + stride);
 		uint32_t any = 0;
-		if (g <= g_hi) {
-			// demod.c:107: p1 > 2*s1 at n, p2 > 2*s2 at n+30
-			uint32_t pre = bp[g] & __funnelshift_l(bq[g + 1], bq[g], 30);
+		{
+			// demod.c:107: p1 > 2*s1 at n, p2 > 2*s2 at n+30 (words past g_hi are zero)
+			uint32_t pre = w.p0 & __funnelshift_l(w.q1, w.q0, 30);
 			if (g == g_lo)
 				pre &= m_first;
 			if (g == g_hi)
 				pre &= m_last;
-			if (pre) {
-				const uint32_t b2 = bb[g + 2], b3 = bb[g + 3], b4 = bb[g + 4];
-				// first five data bits sit at n+80, +90, +100, +110, +120 (demod.c:110, :46-81)
-				const uint32_t x7 = __funnelshift_l(b3, b2, 16);  // 80  = 64 + 16
-				const uint32_t x6 = __funnelshift_l(b3, b2, 26);  // 90  = 64 + 26
-				const uint32_t x5 = __funnelshift_l(b4, b3, 4);   // 100 = 96 + 4
-				const uint32_t x4 = __funnelshift_l(b4, b3, 14);  // 110 = 96 + 14
-				const uint32_t x3 = __funnelshift_l(b4, b3, 24);  // 120 = 96 + 24
-				const uint32_t c0 = pre & ~x5;
-				const uint32_t lng = c0 & x7 & ~x6;
-				any = (lng & ~x4 & x3)                  // 10001
-				      | (lng & x4 & ~x3 & df18_mask)    // 10010 (only with -a, demod.c:59)
-				      | (c0 & ~x7 & x6 & x4 & x3);      // 01011
-			}
+			// first five data bits sit at n+80, +90, +100, +110, +120 (demod.c:110, :46-81)
+			const uint32_t x7 = __funnelshift_l(w.b3, w.b2, 16);  // 80  = 64 + 16
+			const uint32_t x6 = __funnelshift_l(w.b3, w.b2, 26);  // 90  = 64 + 26
+			const uint32_t x5 = __funnelshift_l(w.b4, w.b3, 4);   // 100 = 96 + 4
+			const uint32_t x4 = __funnelshift_l(w.b4, w.b3, 14);  // 110 = 96 + 14
+			const uint32_t x3 = __funnelshift_l(w.b4, w.b3, 24);  // 120 = 96 + 24
+			const uint32_t c0 = pre & ~x5;
+			const uint32_t lng = c0 & x7 & ~x6;
+			any = (lng & ~x4 & x3)                  // 10001
+			      | (lng & x4 & ~x3 & df18_mask)    // 10010 (only with -a, demod.c:59)
+			      | (c0 & ~x7 & x6 & x4 & x3);      // 01011
 		}
 		const uint32_t c = (uint32_t)__popc(any);
 		const uint32_t total = __reduce_add_sync(FULL, c);
@@ -549,7 +615,7 @@ __device__ __forceinline__ uint32_t slice28(const unsigned int *__restrict__ bit
 constexpr int SLICE_STAGE = 64;  // candidate records staged per warp (2 KB): a pass adds at most 32
 
 template <bool REPAIR>
-__global__ void __launch_bounds__(256) k_slice(const SliceParams p)
+__global__ void __launch_bounds__(256, ADSB_SLICE_MINB) k_slice(const SliceParams p)
 {
 	//@region slice
 	__shared__ uint32_t lut[28 * 16];

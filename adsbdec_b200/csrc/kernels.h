@@ -39,6 +39,8 @@ struct SlotResolve {         // per job, copied back to the host
 	unsigned long long span0_start;  // scan position before this job (for the statistics pass and redo)
 	unsigned long long span0_end;
 	unsigned long long drift0;       // ResolveState::drift before this job
+	unsigned int ok[3];              // accepted DF11 / DF17 / DF18 frames of the job (valid.c:53, :75)
+	unsigned int pad_;
 };
 
 struct ResolveBuffers {      // per job slot scratch

@@ -225,6 +225,7 @@ __global__ void k_snapshot(const ResolveState *st, SlotResolve *slot)
 	slot->span0_start = st->carry_start;
 	slot->span0_end = st->carry_pos;
 	slot->drift0 = st->drift;
+	slot->ok[0] = slot->ok[1] = slot->ok[2] = 0;  // k_compact counts into them
 }
 
 // Greedy acceptance.  Thread i walks the segment that starts at candidate i (if one does).
@@ -285,6 +286,7 @@ __global__ void k_compact(const CandRec *__restrict__ sorted, const unsigned cha
                           unsigned long long out_cap, ResolveState *st, SlotResolve *slot)
 {
 	const unsigned long long drift0 = slot->drift0;
+	unsigned int ok[3] = {0, 0, 0};  // accepted frames per class (valid.c:53, :75), one atomic per warp at the end
 	for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
 		unsigned long long p = bacc_x[b];
 		unsigned long long drift = drift0 + bdrift_x[b];
@@ -312,7 +314,15 @@ __global__ void k_compact(const CandRec *__restrict__ sorted, const unsigned cha
 				}
 				drift += skip_of(c.len) - 1ull;
 				p++;
+				const int df = c.bytes[0] >> 3;
+				ok[df == 11 ? 0 : df == 17 ? 1 : 2]++;
 			}
+	}
+#pragma unroll
+	for (int c = 0; c < 3; c++) {
+		const unsigned int w = __reduce_add_sync(0xFFFFFFFFu, ok[c]);
+		if ((threadIdx.x & 31) == 0 && w)
+			atomicAdd(&slot->ok[c], w);
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) {
 		slot->n_sorted = off[nb];

@@ -15,20 +15,28 @@ void Resolver::scan_to(uint64_t cutoff, std::vector<adsbdec_b200_frame_t> &accep
 	// offsets (demod.c:89).  idx starts at ampbuff[0] = base_.  Candidates come from the few left
 	// over from earlier feeds (pending_) and then, in place, from the array being fed.
 	uint64_t pos = base_;
-	// stamped frames: everything below the cutoff is accepted as it is
+	// stamped frames: everything below the cutoff is accepted as it is.  A call covers ~40 k offsets, i.e. a
+	// dozen frames of a dense capture, so the end of its run is searched (first in a short window, then in the
+	// rest) instead of walked, and the frames are copied once per feed (flush_stamped), not once per call:
+	// 15 000 calls per minute of signal used to cost a millisecond of host time.
 	for (int src = 0; src < 2; src++) {
 		const adsbdec_b200_frame_t *f = src == 0 ? fpending_.data() : fin_;
 		size_t &i = src == 0 ? fhead_ : fin_i_;
 		const size_t n = src == 0 ? fpending_.size() : fin_n_, i0 = i;
-		while (i < n && f[i].n < cutoff) {
-			if (ok_) {
-				const int df = f[i].bytes[0] >> 3;
-				ok_[df == 11 ? 0 : df == 17 ? 1 : 2]++;
-			}
-			i++;
+		if (i < n && f[i].n < cutoff) {
+			const auto below = [cutoff](const adsbdec_b200_frame_t &x, uint64_t) { return x.n < cutoff; };
+			const size_t w = std::min(n, i + 64);
+			size_t e = (size_t)(std::lower_bound(f + i, f + w, cutoff, below) - f);
+			if (e == w && w < n)
+				e = (size_t)(std::lower_bound(f + w, f + n, cutoff, below) - f);
+			i = e;
 		}
 		if (i > i0) {
-			accepted.insert(accepted.end(), f + i0, f + i);
+			if (ok_)
+				for (size_t k = i0; k < i; k++) {
+					const int df = f[k].bytes[0] >> 3;
+					ok_[df == 11 ? 0 : df == 17 ? 1 : 2]++;
+				}
 			pos = f[i - 1].n + (f[i - 1].len == 7 ? kSkipShort : kSkipLong);
 		}
 		if (i < n)
@@ -69,8 +77,36 @@ void Resolver::scan_to(uint64_t cutoff, std::vector<adsbdec_b200_frame_t> &accep
 	scan_end_ = cutoff;
 }
 
+// Stamped frames consumed since the last flush: [fdone_, fhead_) of the pending vector, then
+// [fin_done_, fin_i_) of the array being fed.
+void Resolver::flush_stamped(std::vector<adsbdec_b200_frame_t> &accepted)
+{
+	if (inplace_)
+		return;
+	if (fhead_ > fdone_)
+		accepted.insert(accepted.end(), fpending_.begin() + (ptrdiff_t)fdone_, fpending_.begin() + (ptrdiff_t)fhead_);
+	fdone_ = fhead_;
+	if (fin_ && fin_i_ > fin_done_)
+		accepted.insert(accepted.end(), fin_ + fin_done_, fin_ + fin_i_);
+	fin_done_ = fin_i_;
+}
+
+void Resolver::count_pending(uint32_t out[3]) const
+{
+	out[0] = out[1] = out[2] = 0;
+	for (size_t k = fhead_; k < fpending_.size(); k++) {
+		const int df = fpending_[k].bytes[0] >> 3;
+		out[df == 11 ? 0 : df == 17 ? 1 : 2]++;
+	}
+}
+
 void Resolver::run_calls(std::vector<adsbdec_b200_frame_t> &accepted)
 {
+	struct Flush {  // whatever way the loop is left
+		Resolver *r;
+		std::vector<adsbdec_b200_frame_t> &a;
+		~Flush() { r->flush_stamped(a); }
+	} flush_on_exit{this, accepted};
 	for (;;) {
 		// air.c:94: the test runs after every 2 envelope samples; the call happens at the first
 		// even sample count P with P - base >= APBUFFSZ.
@@ -114,22 +150,57 @@ void Resolver::feed_frames(const adsbdec_b200_frame_t *f, size_t count, uint64_t
 	ok_ = ok;
 	if (fhead_ == fpending_.size()) {
 		fpending_.clear();
-		fhead_ = 0;
+		fhead_ = fdone_ = 0;
 	}
 	fin_ = f;
 	fin_n_ = count;
-	fin_i_ = 0;
+	fin_i_ = fin_done_ = 0;
 	scanned_upto_ = std::max(scanned_upto_, scanned_upto);
 	total_out_ = std::max(total_out_, total_out);
 	run_calls(accepted);
 	if (fhead_ == fpending_.size()) {
 		fpending_.clear();
-		fhead_ = 0;
+		fhead_ = fdone_ = 0;
 	}
 	fpending_.insert(fpending_.end(), f + fin_i_, f + count);
 	fin_ = nullptr;
-	fin_n_ = fin_i_ = 0;
+	fin_n_ = fin_i_ = fin_done_ = 0;
 	ok_ = nullptr;  // the caller's counters are only borrowed for the call
+}
+
+size_t Resolver::advance_frames(const adsbdec_b200_frame_t *f, size_t n_vis, size_t n_total, uint64_t scanned_upto,
+                                uint64_t total_out)
+{
+	std::vector<adsbdec_b200_frame_t> none;
+	inplace_ = true;
+	ok_ = nullptr;
+	fin_ = f + n_vis;
+	fin_n_ = n_total - n_vis;
+	fin_i_ = fin_done_ = 0;
+	scanned_upto_ = std::max(scanned_upto_, scanned_upto);
+	total_out_ = std::max(total_out_, total_out);
+	run_calls(none);
+	const size_t r = n_vis + fin_i_;
+	fin_ = nullptr;
+	fin_n_ = fin_i_ = fin_done_ = 0;
+	inplace_ = false;
+	return r;
+}
+
+size_t Resolver::finish_frames(const adsbdec_b200_frame_t *f, size_t n_vis, size_t n_total)
+{
+	std::vector<adsbdec_b200_frame_t> none;
+	inplace_ = true;
+	ok_ = nullptr;
+	fin_ = f + n_vis;
+	fin_n_ = n_total - n_vis;
+	fin_i_ = fin_done_ = 0;
+	finish(none, nullptr);
+	const size_t r = n_vis + fin_i_;
+	fin_ = nullptr;
+	fin_n_ = fin_i_ = fin_done_ = 0;
+	inplace_ = false;
+	return r;
 }
 
 void Resolver::finish(std::vector<adsbdec_b200_frame_t> &accepted, uint32_t ok[3])
@@ -141,13 +212,15 @@ void Resolver::finish(std::vector<adsbdec_b200_frame_t> &accepted, uint32_t ok[3
 		uint64_t cutoff = std::min(scanned_upto_, total_out_ >= (uint64_t)kLookahead
 		                                              ? total_out_ - kLookahead
 		                                              : 0);
-		if (cutoff > scan_end_)
+		if (cutoff > scan_end_) {
 			scan_to(cutoff, accepted);
+			flush_stamped(accepted);
+		}
 	}
 	pending_.clear();
 	head_ = 0;  // the reference drops whatever is left in ampbuff at EOF (air.c:243-244)
 	fpending_.clear();
-	fhead_ = 0;
+	fhead_ = fdone_ = 0;
 	ok_ = nullptr;
 }
 

@@ -33,6 +33,16 @@ public:
 	// ok (may be null): counters for the stamped frames still accepted here.
 	void finish(std::vector<adsbdec_b200_frame_t> &accepted, uint32_t ok[3] = nullptr);
 
+	// In-place form of feed_frames for a caller that keeps ALL stamped frames in one array f[0 .. n_total):
+	// f[0 .. n_vis) have been reached by the call schedule before, the rest is new or still in front of it.
+	// Returns the new n_vis (the frames stay where they are; nothing is copied).
+	size_t advance_frames(const adsbdec_b200_frame_t *f, size_t n_vis, size_t n_total, uint64_t scanned_upto,
+	                      uint64_t total_out);
+	size_t finish_frames(const adsbdec_b200_frame_t *f, size_t n_vis, size_t n_total);
+
+	// DF11 / DF17 / DF18 frames fed as stamped frames that the call schedule has not reached yet.
+	void count_pending(uint32_t out[3]) const;
+
 	// Offsets below this have been visited (or skipped) by the emulated scan.
 	uint64_t scan_end() const { return scan_end_; }
 	// Where the next deqframe call would start (= absolute index of ampbuff[0]).
@@ -41,8 +51,10 @@ public:
 private:
 	void run_calls(std::vector<adsbdec_b200_frame_t> &accepted);
 	void scan_to(uint64_t cutoff, std::vector<adsbdec_b200_frame_t> &accepted);
+	void flush_stamped(std::vector<adsbdec_b200_frame_t> &accepted);
 
 	bool emulate_tail_;
+	bool inplace_ = false;    // advance_frames / finish_frames: consumed frames are not copied anywhere
 	uint64_t base_ = 0;       // absolute index of ampbuff[0] at the next deqframe call
 	uint64_t drift_ = 0;      // iterations saved by skips so far: sum(skip - 1)
 	uint64_t scan_end_ = 0;
@@ -53,9 +65,9 @@ private:
 	const adsbdec_b200_candidate_t *in_ = nullptr;  // array being fed, consumed in place
 	size_t in_n_ = 0, in_i_ = 0;
 	std::vector<adsbdec_b200_frame_t> fpending_;    // stamped frames the call schedule has not reached
-	size_t fhead_ = 0;
+	size_t fhead_ = 0, fdone_ = 0;                  // [fdone_, fhead_) consumed but not copied out yet
 	const adsbdec_b200_frame_t *fin_ = nullptr;
-	size_t fin_n_ = 0, fin_i_ = 0;
+	size_t fin_n_ = 0, fin_i_ = 0, fin_done_ = 0;
 	uint32_t *ok_ = nullptr;  // where scan_to counts the stamped frames it accepts
 };
 

@@ -143,10 +143,12 @@ int adsbdec_b200_decode_file(adsbdec_b200_t *h, const char *path);
 /* stat_try / stat_ok for DF 11, 17, 18, in print_stats order (valid.c:88-97). */
 int adsbdec_b200_stats(adsbdec_b200_t *h, uint32_t try_[3], uint32_t ok[3]);
 
-/* Frames accepted so far are also kept in the handle (in ts order). */
+/* Frames accepted so far are also kept in the handle (in ts order, page-locked memory the GPU
+ * writes them to; the pointer is valid until the next push / flush / poll / finish / clear). */
 size_t adsbdec_b200_num_frames(const adsbdec_b200_t *h);
 const adsbdec_b200_frame_t *adsbdec_b200_frames(const adsbdec_b200_t *h);
-/* Drop the kept frames (long-running streams). */
+/* Drop ALL kept frames (long-running streams); a no-op while frames wait for the sink.  With a
+ * sink installed the library does this itself once a million delivered frames have piled up. */
 void adsbdec_b200_clear_frames(adsbdec_b200_t *h);
 
 /* Device time (ms, CUDA events on the library's stream) spent in the demodulation
