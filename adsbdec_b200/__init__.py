@@ -31,7 +31,7 @@ EXPORTS = [
     "adsbdec_b200_flush", "adsbdec_b200_poll", "adsbdec_b200_push_packed12", "adsbdec_b200_repair_lookup",
     "adsbdec_b200_stats", "adsbdec_b200_num_frames", "adsbdec_b200_frames", "adsbdec_b200_clear_frames",
     "adsbdec_b200_kernel_time", "adsbdec_b200_telemetry", "adsbdec_b200_fused_time", "adsbdec_b200_gate_time",
-    "adsbdec_b200_format_packet",
+    "adsbdec_b200_format_packet", "adsbdec_b200_format_frames",
     "adsbdec_b200_envelope", "adsbdec_b200_resolver_new", "adsbdec_b200_resolver_free",
     "adsbdec_b200_resolver_feed", "adsbdec_b200_resolver_feed_frames", "adsbdec_b200_resolver_finish",
     "adsbdec_b200_resolver_scan_end",
@@ -133,6 +133,8 @@ def lib():
         L.adsbdec_b200_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64), C.c_int]
         L.adsbdec_b200_telemetry.argtypes = [vp, C.POINTER(Telemetry), C.c_int]
         L.adsbdec_b200_fused_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64), C.POINTER(u64), C.c_int]
+        L.adsbdec_b200_format_frames.argtypes = [C.c_int, vp, C.c_size_t, vp, C.c_size_t]
+        L.adsbdec_b200_format_frames.restype = C.c_int64
         L.adsbdec_b200_gate_time.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
         L.adsbdec_b200_format_packet.argtypes = [C.c_int, C.c_char_p, C.c_int, u64, C.c_uint32, C.c_char_p]
         L.adsbdec_b200_envelope.argtypes = [C.c_int, vp, C.c_size_t, C.c_int, u64, vp, C.c_size_t]
@@ -166,6 +168,14 @@ def format_packet(fmt: int, frame: bytes, ts: int, pw: int) -> bytes:
     buf = C.create_string_buffer(256)
     n = _check(lib().adsbdec_b200_format_packet(fmt, frame, len(frame), ts, pw, buf))
     return buf.raw[:n]
+
+
+def format_frames(fmt: int, frames: np.ndarray) -> bytes:
+    """formatpkt() over a FRAME_DTYPE array, packets back to back (what runOutput() writes)."""
+    a = np.ascontiguousarray(frames, dtype=FRAME_DTYPE)
+    out = np.empty(48 * max(1, a.size), dtype=np.uint8)
+    n = _check(int(lib().adsbdec_b200_format_frames(fmt, a.ctypes.data, a.size, out.ctypes.data, out.size)))
+    return out[:n].tobytes()
 
 
 def _frames_from_array(arr: np.ndarray) -> list[Frame]:

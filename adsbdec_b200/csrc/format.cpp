@@ -60,3 +60,26 @@ extern "C" int adsbdec_b200_format_packet(int fmt, const uint8_t *frame, int len
 	*p = 0;
 	return (int)(p - pkt);
 }
+
+// Every frame of an array through format_packet(), packets back to back: what runOutput() (output.c:286-336)
+// writes for them.  Returns the bytes written, or ADSB_B200_ERANGE if `cap` is too small (a packet is at most
+// 2 + 12 + 1 + 28 bytes binary, 13 + 28 + 3 as text).
+extern "C" int64_t adsbdec_b200_format_frames(int fmt, const adsbdec_b200_frame_t *frames, size_t count, char *out,
+                                              size_t cap)
+{
+	if ((!frames && count) || !out)
+		return ADSB_B200_EINVAL;
+	char pkt[256];
+	size_t at = 0;
+	for (size_t i = 0; i < count; i++) {
+		const int n = adsbdec_b200_format_packet(fmt, frames[i].bytes, frames[i].len, frames[i].ts, frames[i].pw, pkt);
+		if (n < 0)
+			return n;
+		if (at + (size_t)n > cap)
+			return ADSB_B200_ERANGE;
+		for (int k = 0; k < n; k++)
+			out[at + k] = pkt[k];
+		at += (size_t)n;
+	}
+	return (int64_t)at;
+}

@@ -10,11 +10,16 @@ overlapping frames), decoded to the final frame list (DF18 on, Try/Ok counters o
   e2e        same metric from HOST buffers through adsbdec_b200_push(): pinned host memory ->
              H2D -> kernels -> frames on the host, copies inside the timed region
   roofline   the fused kernel alone: 2 B/sample x samples / its CUDA-event duration vs measured HBM
+             (+ roofline.path: k_fused + k_gate + k_slice, the whole per-offset path)
   cpu_baseline  the reference's own CPU path (oracle/_ref binary built from the unmodified
-             sources, or the oracle port) on a bounded sample of the same workload
+             sources, or the oracle port) on the run's own capture: one process over all of it, then
+             one process per core on pre-split chunk files
+  parity     the run certifies itself: the reference's stdout and Try/Ok on the capture are compared
+             byte for byte with what this library decoded from it ("identical": true, sha256 of both)
 
-`--impl reference` times the reference CPU implementation instead (one process per core on
-pre-split chunk files) and prints the same JSON line with "impl": "reference".
+The capture is rendered on the host (seeded per tile), so `--impl reference` - which times the
+reference CPU implementation (one process per core on pre-split chunk files of the same 60 s capture)
+and prints the same JSON line with "impl": "reference" - sees the same bytes.
 """
 from __future__ import annotations
 
@@ -36,7 +41,7 @@ sys.path.insert(0, str(ROOT))
 
 FS = 20_000_000
 WORKLOAD = "60s dense capture, ~2000 aircraft, DF11/17/18/20/21 mix with overlaps, 20 MS/s real u16 (configs[1])"
-SEG_SECONDS = 2.0          # host-rendered dense segment, tiled on the device with fresh noise
+SEG_SECONDS = 2.0          # host-rendered dense segment, tiled with fresh noise per tile
 AIRCRAFT = 2000
 FRAMES_PER_AIRCRAFT_S = 6.0
 SIGMA = 25.0
@@ -80,25 +85,55 @@ def dense_segment(seed: int, seconds: float = SEG_SECONDS):
     return sig, n_frames
 
 
-def quantise_host(sig: np.ndarray, seed: int) -> np.ndarray:
-    rng = np.random.default_rng(seed)
-    x = sig + rng.standard_normal(sig.size, dtype=np.float32) * np.float32(SIGMA)
-    return np.clip(np.rint(x + 2048.0), 0, 4095).astype("<u2")
+PAD_SAMPLES = 1 << 21      # mid-scale tail: lets the reference drain its frame queue before EOF
+
+
+def quantise_host(sig: np.ndarray, seed: int, tile: int) -> np.ndarray:
+    rng = np.random.default_rng([seed, 7, tile])
+    x = rng.standard_normal(sig.size, dtype=np.float32)
+    x *= np.float32(SIGMA)
+    x += sig
+    x += np.float32(2048.0)
+    np.rint(x, out=x)
+    np.clip(x, 0, 4095, out=x)
+    return x.astype("<u2")
+
+
+def build_capture(seconds: float, seed: int, out: np.ndarray | None = None):
+    """The workload, rendered on the HOST so that both arms (and the parity check inside the run) see the
+    same bytes: the dense 2 s segment tiled, every tile with its own AWGN (seeded per tile), then 2 Mi
+    mid-scale samples.  Tiles are rendered by a thread pool (numpy releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    sig, n_frames = dense_segment(seed)
+    tiles = max(1, int(round(seconds / SEG_SECONDS)))
+    n = tiles * sig.size + PAD_SAMPLES
+    cap = out if out is not None else np.empty(n, dtype="<u2")
+    assert cap.size == n
+
+    def one(i):
+        cap[i * sig.size:(i + 1) * sig.size] = quantise_host(sig, seed, i)
+
+    with ThreadPoolExecutor(max_workers=max(1, min(tiles, host_cores()))) as ex:
+        list(ex.map(one, range(tiles)))
+    cap[tiles * sig.size:] = 2048
+    return cap, n_frames * tiles
 
 
 def build_device_capture(torch, dev, seconds: float, seed: int):
-    """The capture in HBM: the dense segment tiled, every tile with its own AWGN (torch is only
-    used to synthesise the input)."""
-    sig, n_frames = dense_segment(seed)
-    seg = torch.from_numpy(sig).to(dev)
-    tiles = max(1, int(round(seconds / SEG_SECONDS)))
-    out = torch.empty(tiles * seg.numel(), dtype=torch.int16, device=dev)
-    g = torch.Generator(device=dev)
-    g.manual_seed(seed)
-    for i in range(tiles):
-        x = seg + torch.randn(seg.numel(), device=dev, generator=g) * SIGMA
-        out[i * seg.numel():(i + 1) * seg.numel()] = torch.clamp(torch.round(x + 2048.0), 0, 4095).to(torch.int16)
-    return out, n_frames * tiles, sig
+    """build_capture() uploaded to `dev` (tools/ use this): (int16 tensor, injected frames, None)."""
+    cap, injected = build_capture(seconds, seed)
+    return torch.from_numpy(cap.view(np.int16)).to(dev), injected, None
+
+
+def cpu_sample(seed: int, seconds: float) -> np.ndarray:
+    """The first `seconds` of the workload as a host array (tools/)."""
+    return build_capture(seconds, seed)[0]
+
+
+def capture_samples(seconds: float) -> int:
+    n = int(SEG_SECONDS * FS)
+    n -= n % 8
+    return max(1, int(round(seconds / SEG_SECONDS))) * n + PAD_SAMPLES
 
 
 # ---------------------------------------------------------------------------------------------
@@ -167,54 +202,68 @@ def ref_binary():
     return pyoracle.ref_binary()
 
 
-def run_reference_cpu(sample: np.ndarray, n_procs: int, flags=("-a", "-m")):
-    """Times `adsbdec -f` (unmodified reference, oracle/_ref) on `sample`: one process over the
-    whole sample, then n_procs processes at once, one per core, each on its own pre-split chunk
-    file.  Falls back to the oracle port (single thread) if the binary cannot run here.
-    Returns dict(single_msps, multi_msps, kind, procs, sample_samples)."""
-    binary = ref_binary()
-    tmpdir = Path(tempfile.mkdtemp(prefix="adsb_cpu_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None))
-    try:
-        if binary is None:
-            from oracle import pyoracle
-            t0 = time.perf_counter()
-            pyoracle.decode(sample, accept_df18=True)
-            dt = time.perf_counter() - t0
-            v = sample.size / dt / 1e6
-            return {"single_msps": v, "multi_msps": v, "kind": "port", "procs": 1, "sample_samples": int(sample.size)}
-        whole = tmpdir / "whole.bin"
-        sample.tofile(whole)
-        with open(os.devnull, "wb") as null:
-            t0 = time.perf_counter()
-            subprocess.run([str(binary), *flags, "-f", str(whole)], stdout=null, stderr=null, check=True)
-            single = sample.size / (time.perf_counter() - t0) / 1e6
-            # pre-split chunks, one per process
-            n_files = min(n_procs, 16)
-            per = sample.size // n_files
-            per -= per % 8
-            files = []
-            for i in range(n_files):
-                f = tmpdir / f"chunk{i}.bin"
-                sample[i * per:(i + 1) * per].tofile(f)
-                files.append(f)
-            t0 = time.perf_counter()
-            procs = [subprocess.Popen([str(binary), *flags, "-f", str(files[i % n_files])], stdout=null, stderr=null)
-                     for i in range(n_procs)]
-            for p in procs:
-                p.wait()
-            multi = per * n_procs / (time.perf_counter() - t0) / 1e6
-        return {"single_msps": single, "multi_msps": multi, "kind": "reference", "procs": n_procs,
-                "sample_samples": int(sample.size), "chunk_samples": int(per)}
-    finally:
-        for f in tmpdir.glob("*"):
+class RefFiles:
+    """The capture as page-cached files for the reference binary: the whole capture, and the same samples
+    pre-split into one chunk per process.  /dev/shm when there is room (2 x the capture), else a shorter
+    prefix of the capture for the chunks."""
+
+    def __init__(self, cap: np.ndarray, n_procs: int):
+        base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+        self.dir = Path(tempfile.mkdtemp(prefix="adsb_cpu_", dir=base))
+        self.cap = cap
+        self.n_procs = n_procs
+        self.whole = self.dir / "whole.bin"
+        cap.tofile(self.whole)
+        free = shutil.disk_usage(self.dir).free
+        body = cap.size - PAD_SAMPLES
+        use = body if free > cap.nbytes + (1 << 28) else min(body, int(free * 0.8) // 2)
+        per = use // n_procs
+        per -= per % 8
+        self.chunk_samples = per
+        self.files = []
+        for i in range(n_procs):
+            f = self.dir / f"chunk{i}.bin"
+            cap[i * per:(i + 1) * per].tofile(f)
+            self.files.append(f)
+
+    def close(self):
+        for f in self.dir.glob("*"):
             f.unlink()
-        tmpdir.rmdir()
+        self.dir.rmdir()
 
 
-def cpu_sample(seed: int, seconds: float) -> np.ndarray:
-    sig, _ = dense_segment(seed)
-    tiles = max(1, int(round(seconds / SEG_SECONDS)))
-    return np.concatenate([quantise_host(sig, seed + 1000 + i) for i in range(tiles)])
+def ref_flavour(binary) -> str:
+    return "gcc -O3 -march=native (the reference's own flags)" if str(binary).endswith("_native") else \
+        "gcc -O3 -march=x86-64-v3 (same FMA-contracted arithmetic; runs on any AVX2 host)"
+
+
+def run_reference_single(binary, files: RefFiles, flags=("-a", "-m")):
+    """One `adsbdec -a -m -f` process over the whole capture: (Msamples/s, stdout, (try, ok))."""
+    from oracle import pyoracle
+    t0 = time.perf_counter()
+    r = pyoracle.run_ref(files.whole, flags=flags, binary=binary, timeout=900)
+    dt = time.perf_counter() - t0
+    return files.cap.size / dt / 1e6, r.stdout, r.stats()
+
+
+def run_reference_multi(binary, files: RefFiles, flags=("-a", "-m")):
+    """One process per core, each on its own pre-split chunk file: aggregate Msamples/s."""
+    with open(os.devnull, "wb") as null:
+        t0 = time.perf_counter()
+        procs = [subprocess.Popen([str(binary), *flags, "-f", str(f)], stdout=null, stderr=null) for f in files.files]
+        for p in procs:
+            p.wait()
+        dt = time.perf_counter() - t0
+    return files.chunk_samples * len(files.files) / dt / 1e6
+
+
+def run_port_cpu(cap: np.ndarray):
+    """Fallback when the compiled reference cannot run on this host: the oracle port, one thread, on 2 s."""
+    from oracle import pyoracle
+    n = min(cap.size, 2 * FS)
+    t0 = time.perf_counter()
+    pyoracle.decode(cap[:n], accept_df18=True)
+    return n / (time.perf_counter() - t0) / 1e6, n
 
 
 def reference_arm(args):
@@ -222,27 +271,44 @@ def reference_arm(args):
     if rank != 0:
         return 0
     cores = host_cores()
-    sample = cpu_sample(1234, 10.0)          # 10 s of the workload = 200 M samples
-    times = []
-    res = None
-    for i in range(args.warmup + args.steps):
-        res = run_reference_cpu(sample, cores)
-        if i >= args.warmup:
-            times.append(res)
-        if i == 0 and args.warmup:
-            pass
-    multi = float(np.mean([r["multi_msps"] for r in times]))
-    single = float(np.mean([r["single_msps"] for r in times]))
-    samples_per_step = res["chunk_samples"] * res["procs"] if "chunk_samples" in res else res["sample_samples"]
+    cap, _ = build_capture(args.seconds, 1234)     # the b200 arm's capture of rank 0, byte for byte
+    binary = ref_binary()
+    if binary is None:
+        v, n = run_port_cpu(cap)
+        line = {"impl": "reference", "metric": "Msamples/s", "value": v, "unit": "Msamples/s", "n_gpus": args.gpus,
+                "steps": 1, "warmup": 0, "ms_per_step": n / v / 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "sample": f"first {n} samples, oracle port (oracle/_ref cannot run on this host)"},
+                "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": 1, "kind": "port", "sample": f"{n} samples"},
+                "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+    files = RefFiles(cap, cores)
+    try:
+        single, _, _ = run_reference_single(binary, files)
+        vals = []
+        for i in range(args.warmup + args.steps):
+            v = run_reference_multi(binary, files)
+            if i >= args.warmup:
+                vals.append(v)
+    finally:
+        files.close()
+    multi = float(np.mean(vals))
+    samples_per_step = files.chunk_samples * cores
     line = {
         "impl": "reference", "metric": "Msamples/s", "value": multi, "unit": "Msamples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": samples_per_step / multi / 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": "10 s of the workload per step, pre-split into per-process chunk files"},
+        "config": {"workload": WORKLOAD, "samples_per_gpu": int(cap.size), "seconds_per_gpu": cap.size / FS,
+                   "sample": f"the whole capture per step, pre-split into {cores} per-process chunk files of "
+                             f"{files.chunk_samples} samples"},
         "realtime_x": multi * 1e6 / FS,
-        "cpu_baseline": {"value": multi, "unit": "Msamples/s", "cores": res["procs"], "kind": res["kind"],
-                         "sample": f"{res['procs']} processes x {samples_per_step // max(1, res['procs'])} samples (adsbdec -a -m -f), "
-                                   f"single process: {single:.1f} Msamples/s", "single_process": single},
+        "cpu_baseline": {"value": multi, "unit": "Msamples/s", "cores": cores, "kind": "reference",
+                         "sample": f"{cores} processes x {files.chunk_samples} samples (adsbdec -a -m -f, page-cached chunk "
+                                   f"files of the 60 s capture); one process over the whole capture: {single:.1f} "
+                                   f"Msamples/s; binary: {Path(binary).name}, {ref_flavour(binary)}",
+                         "single_process": single},
         "e2e": {"value": multi, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -282,8 +348,11 @@ def main():
         bind_to_gpu_numa_node(local)
 
     seed = 1234 + rank     # every rank = its own receiver stream (weak scaling, no data-path collective)
-    cap, injected, sig = build_device_capture(torch, dev, args.seconds, seed)
-    n_samples = cap.numel()
+    n_samples = capture_samples(args.seconds)
+    host = torch.empty(n_samples, dtype=torch.int16, pin_memory=True)   # page-locked: the e2e leg uploads from here
+    host_np = host.numpy().view("<u2")
+    _, injected = build_capture(args.seconds, seed, out=host_np)
+    cap = host.to(dev)
     torch.cuda.synchronize()
 
     dec = A.Decoder(device=local, accept_df18=True, kernel=args.kernel)   # one handle, reset per step
@@ -300,18 +369,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def gather(x: float):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if not dist:
+            return [x]
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        return [float(v.item()) for v in allt]
+
     # ---- device-resident: warm-up, then K timed steps ----
-    last = None
     for _ in range(args.warmup):
         step_resident()
     barrier()
     dec.fused_time(reset=True)
+    dec.gate_time(reset=True)
     dec.kernel_time(reset=True)
     dec.host_time(reset=True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    fused_ms = fused_launches = fused_samples = 0.0
-    launches = 0
-    kernel_ms = 0.0
     frames = 0
     with ClockSampler(local) as clk:
         ev0.record()
@@ -321,28 +395,19 @@ def main():
         ev1.record()
         barrier()
     fused_ms, fused_launches, fused_samples = dec.fused_time()
+    gate_ms = dec.gate_time()
     kernel_ms, launches = dec.kernel_time()
     host_tel = dec.host_time()
     stats = dec.stats()
-    ms_total = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms_total], device=dev)
-    per_rank = [ms_total / args.steps]
-    if dist:
-        allt = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(allt, t)
-        per_rank = [float(x.item()) / args.steps for x in allt]
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
+    frames_arr = dec.frames_array          # the last step's result: compared with the reference below
+    per_rank = [v / args.steps for v in gather(ev0.elapsed_time(ev1))]
+    ms_step = max(per_rank)
     value = world * n_samples / (ms_step * 1e-3) / 1e6
+    host_ranks = gather(sum(v for k, v in host_tel.items() if k.endswith("_ms")) / args.steps)
 
     # ---- end to end from pinned host memory through push() ----
     e2e = None
     if not args.no_e2e:
-        host = torch.empty(n_samples, dtype=torch.int16, pin_memory=True)
-        host.copy_(cap)
-        torch.cuda.synchronize()
-        host_np = host.numpy().view("<u2")
-
         def step_e2e():
             dec.reset()
             dec.push(host_np)
@@ -352,20 +417,19 @@ def main():
 
         step_e2e()
         barrier()
+        ne = max(1, args.steps // 2)
         t0 = time.perf_counter()
         ev0.record()
-        for _ in range(max(1, args.steps // 2)):
+        for _ in range(ne):
             nf, d2h = step_e2e()
         ev1.record()
         barrier()
-        ne = max(1, args.steps // 2)
-        te = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-        if dist:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e_ms = float(te.item()) / ne
+        e_ranks = [v / ne for v in gather(ev0.elapsed_time(ev1))]
+        e_ms = max(e_ranks)
         e2e = {"value": world * n_samples / (e_ms * 1e-3) / 1e6, "unit": "Msamples/s",
                "h2d_bytes_per_step": int(2 * n_samples), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": e_ms, "frames": nf, "wall_ms_per_step": (time.perf_counter() - t0) * 1e3 / ne}
+               "ms_per_step": e_ms, "frames": nf, "wall_ms_per_step": (time.perf_counter() - t0) * 1e3 / ne,
+               "ms_per_step_ranks": e_ranks, "h2d_gbs_ranks": [2 * n_samples / (m * 1e-3) / 1e9 for m in e_ranks]}
         assert nf == frames, (nf, frames)
         # the same capture in the airspy's packed 12-bit wire format (8 samples in 12 bytes):
         # a quarter less to move over PCIe, unpacked on the GPU.  Not the reference's file format: reported
@@ -392,29 +456,8 @@ def main():
                                "what": "pinned host memory, 12-bit packed samples -> adsbdec_b200_push_packed12 -> "
                                        "frames on the host, best of 3, wall clock"}
             del packed
-        # the reference's own entry point for this path, fileInput (air.c:219-246): the same capture as a
-        # page-cached file through adsbdec_b200_decode_file (rank 0 at N=1 only; needs 2.4 GB of /dev/shm)
-        if world == 1 and os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 3 * host_np.nbytes:
-            fpath = Path("/dev/shm") / f"adsb_b200_bench_{os.getpid()}.bin"
-            try:
-                host_np.tofile(fpath)
-                best = None
-                for _ in range(3):
-                    dec.reset()
-                    tf = time.perf_counter()
-                    dec.decode_file(fpath)
-                    nff = dec.num_frames
-                    dt = time.perf_counter() - tf
-                    best = dt if best is None else min(best, dt)
-                assert nff == frames, (nff, frames)
-                e2e["file"] = {"value": n_samples / best / 1e6, "unit": "Msamples/s", "ms_per_step": best * 1e3,
-                               "what": "page-cached /dev/shm file -> adsbdec_b200_decode_file -> frames on the host, "
-                                       "best of 3, wall clock"}
-            finally:
-                fpath.unlink(missing_ok=True)
-        del host
 
-    # ---- roofline of the dominant kernel (fused), CUDA events on its own stream ----
+    # ---- roofline of the dominant kernel (k_fused), CUDA events on its own stream ----
     peaks_path = ROOT / "MEASURED_PEAKS.json"
     if peaks_path.exists():
         peak = float(json.loads(peaks_path.read_text())["hbm_gbs"])
@@ -424,31 +467,77 @@ def main():
     roof = None
     if fused_launches:
         per_launch_ms = fused_ms / fused_launches
-        achieved = 2.0 * fused_samples / fused_launches / (per_launch_ms * 1e-3) / 1e9
-        # DRAM traffic of the kernel from the committed ncu capture (bytes moved per algorithmic byte),
-        # scaled to this run's average launch
+        alg = 2.0 * fused_samples / fused_launches
+        achieved = alg / (per_launch_ms * 1e-3) / 1e9
+        # DRAM traffic of the kernel from the committed ncu capture of this build (bytes moved per algorithmic
+        # byte), scaled to this run's average launch
         traffic, traffic_src = None, None
-        tp = ROOT / "profiles" / "r1_traffic.json"
+        tp = ROOT / "profiles" / "r2_traffic.json"
         if tp.exists():
             t = json.loads(tp.read_text())
             ratio = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["algorithmic_bytes"]
-            traffic = ratio * 2.0 * fused_samples / fused_launches
-            traffic_src = f"profiles/r1_traffic.json: DRAM read+write = {ratio:.3f} x algorithmic bytes"
+            traffic = ratio * alg
+            traffic_src = f"profiles/r2_traffic.json: DRAM read+write = {ratio:.3f} x algorithmic bytes"
+        path_ms = (fused_ms + gate_ms) / fused_launches
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "kernel": "k_fused", "ms_per_launch": per_launch_ms,
-                "algorithmic_bytes_per_launch": 2.0 * fused_samples / fused_launches, "peak_source": peak_src,
-                "kernel_share_of_step": fused_ms / (ms_step * args.steps)}
+                "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
+                "kernel_share_of_step": fused_ms / (ms_step * args.steps),
+                # the whole per-offset path (k_fused + k_gate + k_slice: samples -> CRC-valid candidates)
+                "path": {"kernels": "k_fused + k_gate + k_slice", "ms_per_launch": path_ms,
+                         "achieved": alg / (path_ms * 1e-3) / 1e9, "frac": alg / (path_ms * 1e-3) / 1e9 / peak,
+                         "share_of_step": (fused_ms + gate_ms) / (ms_step * args.steps)}}
 
-    # ---- reference CPU path on this box's cores (rank 0, N=1 only) ----
-    cpu = None
+    # ---- the reference's own CPU path on this box's cores, on the SAME capture, and the parity check
+    #      (rank 0, N=1 only): one `adsbdec -a -m -f` process over the whole capture gives the golden output
+    #      of this very run; then one process per core on pre-split chunks for the multi-core figure ----
+    cpu, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample = cpu_sample(1234, 10.0)
-        r = run_reference_cpu(sample, host_cores())
-        cpu = {"value": r["multi_msps"], "unit": "Msamples/s", "cores": r["procs"], "kind": r["kind"],
-               "sample": f"10 s of the workload: {r['procs']} processes x {r.get('chunk_samples', r['sample_samples'])} samples "
-                         f"(adsbdec -a -m -f, page-cached chunk files); single process over the 10 s: "
-                         f"{r['single_msps']:.1f} Msamples/s",
-               "single_process": r["single_msps"]}
+        import hashlib
+        binary = ref_binary()
+        ours = A.format_frames(1, frames_arr)
+        if binary is not None:
+            files = RefFiles(host_np, host_cores())
+            try:
+                single, ref_out, ref_stats = run_reference_single(binary, files)
+                multi = run_reference_multi(binary, files)
+                # the same capture as a page-cached file through adsbdec_b200_decode_file, the reference's own
+                # entry point for this path (fileInput, air.c:219-246)
+                best = None
+                for _ in range(3):
+                    dec.reset()
+                    tf = time.perf_counter()
+                    dec.decode_file(files.whole)
+                    nff = dec.num_frames
+                    dt = time.perf_counter() - tf
+                    best = dt if best is None else min(best, dt)
+                file_out = A.format_frames(1, dec.frames_array)
+                if e2e is not None:
+                    e2e["file"] = {"value": n_samples / best / 1e6, "unit": "Msamples/s", "ms_per_step": best * 1e3,
+                                   "what": "page-cached /dev/shm file -> adsbdec_b200_decode_file -> frames on the "
+                                           "host, best of 3, wall clock"}
+            finally:
+                files.close()
+            same = ours == ref_out and file_out == ref_out and ref_stats == (tuple(stats[0]), tuple(stats[1]))
+            parity = {"parity_checked": True, "identical": bool(same),
+                      "what": "avrmlat byte stream (adsbdec -a -m -f stdout) and Try/Ok counters of the unmodified "
+                              "reference on this run's 60 s capture vs push_device and decode_file of this library",
+                      "frames": int(len(frames_arr)), "bytes": len(ref_out),
+                      "sha256_reference": hashlib.sha256(ref_out).hexdigest(),
+                      "sha256_b200": hashlib.sha256(ours).hexdigest(),
+                      "try_ok_reference": [list(ref_stats[0] or ()), list(ref_stats[1] or ())]}
+            if not same:
+                print(f"PARITY FAILURE: {len(ours)} vs {len(ref_out)} bytes, stats {stats} vs {ref_stats}", file=sys.stderr)
+            cpu = {"value": multi, "unit": "Msamples/s", "cores": host_cores(), "kind": "reference",
+                   "sample": f"the run's own 60 s capture: {host_cores()} processes x {files.chunk_samples} samples "
+                             f"(adsbdec -a -m -f, page-cached chunk files); one process over the whole capture: "
+                             f"{single:.1f} Msamples/s; binary: {Path(binary).name}, {ref_flavour(binary)}",
+                   "single_process": single}
+        else:
+            v, n = run_port_cpu(host_np)
+            cpu = {"value": v, "unit": "Msamples/s", "cores": 1, "kind": "port",
+                   "sample": f"first {n} samples of the capture, oracle port (oracle/_ref cannot run on this host)"}
+            parity = {"parity_checked": False, "why": "oracle/_ref cannot run on this host"}
 
     if rank == 0:
         line = {
@@ -463,8 +552,9 @@ def main():
             "stats_try_ok": [list(stats[0]), list(stats[1])],
             "kernel_ms_per_step": kernel_ms / args.steps, "ms_per_step_ranks": per_rank,
             "host_ms_per_step": {k: (v / args.steps if isinstance(v, float) else v) for k, v in host_tel.items()},
+            "host_ms_per_step_ranks": host_ranks,
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roof, "cpu_baseline": cpu,
+            "roofline": roof, "cpu_baseline": cpu, "parity": parity,
         }
         print(json.dumps(line))
     if dist:

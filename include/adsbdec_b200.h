@@ -181,6 +181,10 @@ int adsbdec_b200_gate_time(adsbdec_b200_t *h, double *ms, int reset);
  * (output.c:267).  Returns the packet length. */
 int adsbdec_b200_format_packet(int fmt, const uint8_t *frame, int len, uint64_t ts,
                                uint32_t pw, char *pkt);
+/* The same for an array of frames, packets back to back - the byte stream runOutput()
+ * (output.c:286-336) writes for them.  Returns the bytes written (<= 48 per frame) or <0. */
+int64_t adsbdec_b200_format_frames(int fmt, const adsbdec_b200_frame_t *frames, size_t count,
+                                   char *out, size_t cap);
 
 /* Debug / parity tap: envelope samples amp[first_out .. first_out+count) of a capture
  * held in device or host memory, computed by the generic kernel (is_device = 0/1).
