@@ -166,6 +166,7 @@ struct adsbdec_b200 {
 	// BESIDE the next job's scan.  k_fused leaves kResolveSMs SMs free for it (a persistent CTA holds a
 	// whole SM's registers, so nothing else fits next to one).
 	cudaStream_t st_res = nullptr;
+	cudaStream_t st_stat = nullptr;  // the Try statistics passes (they only read a finished job's lists)
 	cudaEvent_t ev_scan[kSlots] = {};   // the slot's scan kernels are done (recorded on st)
 	cudaEvent_t ev_stats[kSlots] = {};  // the slot's lists have been read by the statistics pass
 	unsigned long long origin = 0;   // absolute index of local sample 0 (FIR phase / fidx wrap)
@@ -260,6 +261,7 @@ int sync_compute(adsbdec_b200 *h)
 {
 	CU(cudaStreamSynchronize(h->st));
 	CU(cudaStreamSynchronize(h->st_res));
+	CU(cudaStreamSynchronize(h->st_stat));
 	return 0;
 }
 
@@ -482,8 +484,9 @@ int enqueue_job(adsbdec_b200 *h, int s, bool force_generic)
 		CU(cudaEventRecord(h->ev_done[s], h->st_res));
 		return 0;
 	}
-	// the statistics pass of the job that used this slot before reads its try list on the resolve stream
+	// the statistics pass of the job that used this slot before reads its lists on a stream of its own
 	CU(cudaStreamWaitEvent(h->st, h->ev_stats[s], 0));
+	CU(cudaStreamWaitEvent(h->st_res, h->ev_stats[s], 0));
 	force_generic = force_generic || h->cfg.kernel == 1 || h->fused_ctas <= 0;
 	k_reset_counters<<<1, 1, 0, h->st>>>(h->d_ctr[s]);
 	CU(cudaGetLastError());
@@ -511,7 +514,7 @@ int enqueue_job(adsbdec_b200 *h, int s, bool force_generic)
 		}
 		a = b;
 	}
-	if (j.used_fused) {
+	if (j.used_fused && !j.resolve) {  // chunk mode hands candidates out: all of them get their signal level
 		CU(launch_fill_pw(j.buf, j.u0, j.origin, h->d_cands[s], &h->d_ctr[s]->n_cand, h->cand_cap[s], h->st));
 		h->launches += 1;
 	}
@@ -524,6 +527,11 @@ int enqueue_job(adsbdec_b200 *h, int s, bool force_generic)
 		CU(launch_resolve(h->rb[s], h->d_cands[s], h->d_ctr[s], h->cand_cap[s], j.n0, j.n1, h->d_state, h->d_slot[s],
 		                  h->d_acc[s], h->cand_cap[s], h->st_res));
 		h->launches += 10;
+		if (j.used_fused) {  // demod.c:127: the signal level, for the frames that were accepted
+			CU(launch_fill_pw_frames(j.buf, j.u0, j.origin, h->d_acc[s], &h->d_slot[s]->n_accept, h->cand_cap[s],
+			                         h->st_res));
+			h->launches += 1;
+		}
 	} else {
 		CU(launch_sort(h->rb[s], h->d_cands[s], h->d_ctr[s], h->cand_cap[s], j.n0, j.n1, h->st_res));
 		h->launches += 4;
@@ -592,15 +600,15 @@ int stats_pass(adsbdec_b200 *h, int s, bool with_slot_list)
 	if (with_slot_list) {
 		CU(launch_count_tries_frames(h->d_tries[s], &h->d_ctr[s]->n_try, h->try_cap[s], h->d_acc[s], h->d_slot[s],
 		                             h->cand_cap[s], h->rb[s], h->job[s].n0, h->job[s].n1, scan_end, h->d_pend[pout],
-		                             &h->d_stats->n_pend[pout], kPendCap, h->d_stats, h->st_res));
+		                             &h->d_stats->n_pend[pout], kPendCap, h->d_stats, h->st_stat));
 		h->launches += 1;
 	}
 	CU(launch_count_tries_frames(h->d_pend[pin], &h->d_stats->n_pend[pin], kPendCap, h->d_acc[s], h->d_slot[s],
 	                             h->cand_cap[s], h->rb[s], h->job[s].n0, h->job[s].n1, scan_end, h->d_pend[pout],
-	                             &h->d_stats->n_pend[pout], kPendCap, h->d_stats, h->st_res));
-	k_zero_u64<<<1, 1, 0, h->st_res>>>(&h->d_stats->n_pend[pin]);
+	                             &h->d_stats->n_pend[pout], kPendCap, h->d_stats, h->st_stat));
+	k_zero_u64<<<1, 1, 0, h->st_stat>>>(&h->d_stats->n_pend[pin]);
 	CU(cudaGetLastError());
-	CU(cudaEventRecord(h->ev_stats[s], h->st_res));
+	CU(cudaEventRecord(h->ev_stats[s], h->st_stat));
 	h->launches += 2;
 	h->pend_in = pout;
 	return 0;
@@ -871,6 +879,7 @@ int adsbdec_b200_open(const adsbdec_b200_config_t *cfg, adsbdec_b200_t **out)
 		          cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking) == cudaSuccess &&
 		          cudaStreamCreateWithFlags(&h->st_d2h, cudaStreamNonBlocking) == cudaSuccess &&
 		          cudaStreamCreateWithFlags(&h->st_res, cudaStreamNonBlocking) == cudaSuccess &&
+		          cudaStreamCreateWithFlags(&h->st_stat, cudaStreamNonBlocking) == cudaSuccess &&
 		          cudaEventCreateWithFlags(&h->ev_h2d, cudaEventDisableTiming) == cudaSuccess &&
 		          cudaMalloc(&h->d_stats, sizeof(StreamStats)) == cudaSuccess &&
 		          cudaMalloc(&h->d_state, sizeof(ResolveState)) == cudaSuccess &&
@@ -919,8 +928,11 @@ int adsbdec_b200_open(const adsbdec_b200_config_t *cfg, adsbdec_b200_t **out)
 				break;
 			}
 			// leave a few SMs to the resolve chain of the previous job (see st_res)
-			const int sms = prop.multiProcessorCount > 4 * kResolveSMs ? prop.multiProcessorCount - kResolveSMs
-			                                                            : prop.multiProcessorCount;
+			int reserve = kResolveSMs;
+			if (const char *e = getenv("ADSB_B200_RESOLVE_SMS"))  // development knob
+				reserve = atoi(e);
+			const int sms = prop.multiProcessorCount > 4 * reserve && reserve >= 0 ? prop.multiProcessorCount - reserve
+			                                                                      : prop.multiProcessorCount;
 			h->fused_ctas = per_sm * sms;
 		}
 		// reserved[3]: opt-in error repair (repair.h) - 0 = the reference's behaviour
@@ -956,6 +968,7 @@ void adsbdec_b200_close(adsbdec_b200_t *h)
 	if (h->st_copy) cudaStreamSynchronize(h->st_copy);
 	if (h->st) cudaStreamSynchronize(h->st);
 	if (h->st_res) cudaStreamSynchronize(h->st_res);
+	if (h->st_stat) cudaStreamSynchronize(h->st_stat);
 	for (int i = 0; i < 2; i++) {
 		if (h->dev[i]) cudaFree(h->dev[i]);
 		if (h->pin[i]) cudaFreeHost(h->pin[i]);
@@ -1007,6 +1020,7 @@ void adsbdec_b200_close(adsbdec_b200_t *h)
 	if (h->st_copy) cudaStreamDestroy(h->st_copy);
 	if (h->st_d2h) cudaStreamDestroy(h->st_d2h);
 	if (h->st_res) cudaStreamDestroy(h->st_res);
+	if (h->st_stat) cudaStreamDestroy(h->st_stat);
 	if (h->frames) cudaFreeHost(h->frames);
 	delete h->res;
 	delete h;
@@ -1227,16 +1241,29 @@ int adsbdec_b200_push_device(adsbdec_b200_t *h, const void *dev_samples, size_t 
 	// the per-job overheads and the tails of the kernel launches small, while the host's work on the
 	// results of one job hides behind the scan of the next (60 s capture, 1144 Mi samples: three jobs,
 	// 1.93-1.95 ms; five jobs of 256 Mi 2.07 ms; one job 2.3 ms, on the same box).
-	const int64_t total = piece_u1 - piece_u0, cap = std::max(h->batch, kDeviceJob);
+	int64_t dev_job = kDeviceJob;
+	if (const char *e = getenv("ADSB_B200_DEVICE_JOB"))  // development knob: samples per scan job
+		dev_job = std::max<int64_t>(1 << 22, atoll(e));
+	const int64_t total = piece_u1 - piece_u0, cap = std::max(h->batch, dev_job);
 	int64_t n_jobs = (total + cap - 1) / cap;
 	if (n_jobs < 2 && total >= 2 * std::max(h->batch, kDeviceJobMin))
 		n_jobs = 2;
 	const int64_t per = align_down((total + n_jobs - 1) / n_jobs + 7, 8);
-	if (piece_u0 == 0 && !h->job[0].active && !h->job[1].active)  // a fresh stream: nothing refers to the lists yet
+	if (piece_u0 == 0 && !h->job[0].active && !h->job[1].active && !h->job[2].active)  // a fresh stream: nothing refers to the lists yet
 		for (int s = 0; s < kSlots; s++)
 			RC(presize_lists(h, s, per / 2));
+	// (cutting the last job in two, so that less of its resolve chain and hand-over is exposed, measured no
+	// gain: 1.55 ms per 60 s capture either way, profiles/README.md)
+	int tail_split = 0;
+	if (const char *e = getenv("ADSB_B200_TAIL_SPLIT"))  // development knob
+		tail_split = atoi(e);
 	for (int64_t end = piece_u0; end < piece_u1;) {
-		end = std::min(piece_u1, end + per);
+		int64_t step = per;
+		if (tail_split && piece_u1 - end <= per && piece_u1 - end > (8 << 20)) {
+			step = align_down((piece_u1 - end) / 2 + 7, 8);
+			tail_split = 0;  // once
+		}
+		end = std::min(piece_u1, end + step);
 		// window: from the FIR history of the next owned offset to `end`, inside the caller's memory
 		const int64_t w0 = std::max<int64_t>(piece_u0, align_down(2 * h->own_next - kCarryBack, 8));
 		RC(submit_window(h, src + (w0 - piece_u0), w0, end));
@@ -1436,8 +1463,8 @@ int adsbdec_b200_stats(adsbdec_b200_t *h, uint32_t try_[3], uint32_t ok[3])
 		return fail(ADSB_B200_EINVAL, "null handle");
 	CU(cudaSetDevice(h->device));
 	RC(complete_all(h));
-	CU(cudaMemcpyAsync(h->h_stats, h->d_stats, sizeof(StreamStats), cudaMemcpyDeviceToHost, h->st_res));
-	CU(cudaStreamSynchronize(h->st_res));
+	CU(cudaMemcpyAsync(h->h_stats, h->d_stats, sizeof(StreamStats), cudaMemcpyDeviceToHost, h->st_stat));
+	CU(cudaStreamSynchronize(h->st_stat));
 	if (h->h_stats->pend_overflow)
 		return fail(ADSB_B200_ERANGE, "pending-try list overflow");
 	uint32_t pend[3] = {0, 0, 0};  // frames the GPU has accepted but the deqframe call schedule has not reached

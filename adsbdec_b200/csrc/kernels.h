@@ -15,6 +15,10 @@ cudaError_t launch_envelope_generic(const uint16_t *raw, long long u_raw0, unsig
 cudaError_t launch_fill_pw(const uint16_t *raw, long long u_raw0, unsigned long long origin, CandRec *cands,
                            const unsigned long long *n_cand_ptr, unsigned long long cap, cudaStream_t st);
 
+// pw for the n accepted frames of a job (*n_ptr, read on the device)
+cudaError_t launch_fill_pw_frames(const uint16_t *raw, long long u_raw0, unsigned long long origin, FrameRec *frames,
+                                  const unsigned long long *n_ptr, unsigned long long cap, cudaStream_t st);
+
 cudaError_t launch_scan_generic(const float *amp, long long j_amp0, long long n0, long long count,
                                 int accept_df18, int want_tries, CandRec *cands,
                                 unsigned long long cand_cap, unsigned long long *tries,

@@ -123,6 +123,33 @@ __global__ void k_fill_pw(const uint16_t *__restrict__ raw, long long u_raw0, un
 	}
 }
 
+// The same for ACCEPTED frames (the stream path): a third of the candidates survive the greedy rule, so the
+// signal level is only worked out for those, behind the compaction.
+__global__ void k_fill_pw_frames(const uint16_t *__restrict__ raw, long long u_raw0, unsigned long long phase_origin,
+                                 FrameRec *frames, const unsigned long long *n_ptr, unsigned long long cap)
+{
+	unsigned long long n_fr = *n_ptr;
+	if (n_fr > cap)
+		n_fr = cap;
+	const int sub = threadIdx.x & 3;
+	const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x / 4;
+	const unsigned long long rounds = (n_fr + stride - 1) / stride;
+	unsigned long long i = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) / 4;
+	for (unsigned long long r = 0; r < rounds; r++, i += stride) {
+		const bool todo = i < n_fr;
+		float a = 0.0f;
+		if (todo) {
+			const long long n = (long long)frames[i].n;
+			a = envelope_at(raw, u_raw0, phase_origin, n + (sub == 0 ? 0 : sub == 1 ? 10 : sub == 2 ? 35 : 45));
+		}
+		const float pair = __fadd_rn(a, __shfl_xor_sync(0xFFFFFFFFu, a, 1));
+		const int pi = __float2int_rz(pair);
+		const int sum = pi + __shfl_xor_sync(0xFFFFFFFFu, pi, 2);
+		if (todo && sub == 0)
+			frames[i].pw = (uint32_t)(sum / 4);
+	}
+}
+
 __device__ __forceinline__ bool ppm(const float *a, int at)
 {
 	return a[at] > a[at + kPulse];  // demod.c:34
@@ -258,6 +285,13 @@ cudaError_t launch_fill_pw(const uint16_t *raw, long long u_raw0, unsigned long 
                            const unsigned long long *n_cand_ptr, unsigned long long cap, cudaStream_t st)
 {
 	k_fill_pw<<<592, 256, 0, st>>>(raw, u_raw0, origin, cands, n_cand_ptr, cap);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_fill_pw_frames(const uint16_t *raw, long long u_raw0, unsigned long long origin, FrameRec *frames,
+                                  const unsigned long long *n_ptr, unsigned long long cap, cudaStream_t st)
+{
+	k_fill_pw_frames<<<296, 256, 0, st>>>(raw, u_raw0, origin, frames, n_ptr, cap);
 	return cudaGetLastError();
 }
 
