@@ -44,6 +44,9 @@ def build(force: bool = False) -> None:
         subprocess.run(["make", "-C", str(HERE), "port"], check=True, capture_output=True)
     if Path("/root/reference/air.c").exists():
         subprocess.run(["make", "-C", str(HERE), "ref"], check=True, capture_output=True)
+        if (HERE.parent / "adsbdec_b200" / "libadsbdec_b200.so").exists():
+            # the reference with INTEGRATION.md's patch applied, linked against the product library
+            subprocess.run(["make", "-C", str(HERE), "patched"], check=True, capture_output=True)
 
 
 _lib = None

@@ -307,6 +307,31 @@ def test_cli_matches_golden(adsb, tmp_path, path):
     assert r.stdout == g["beast_a"]
 
 
+@pytest.mark.parametrize("path", GOLDEN, ids=[p.stem for p in GOLDEN])
+def test_patched_reference_binary_matches_golden(adsb, oracle, tmp_path, path):
+    """INTEGRATION.md section 3, compiled: the reference's OWN main.c / output.c / demod.c with
+    integration/apply_patch.py applied to air.c (fileInput -> libadsbdec_b200) and valid.c (stats setter),
+    built by `make -C oracle patched`.  Same stdout, same beast bytes over TCP, same stats block as the
+    unmodified reference printed for the golden captures: the C ABI is a drop-in for air.c:219-246 and
+    feeds output.c:159 (netout) like validShort/validLong did."""
+    patched = oracle.REF_DIR / "adsbdec_patched"
+    if not patched.exists():
+        if not any(oracle.REF_DIR.glob("adsbdec_*")):
+            pytest.skip("oracle/_ref was never built in this tree")
+        pytest.fail("oracle/_ref/adsbdec_patched is missing: `make -C oracle patched` (needs the built library)")
+    g = _load_golden(path)
+    f = tmp_path / "cap.bin"
+    g["samples"].astype("<u2").tofile(f)
+    r = subprocess.run([str(patched), "-f", str(f)], capture_output=True, timeout=120)
+    assert r.returncode == 0 and r.stdout == g["avr"], r.stderr[-300:]
+    assert _parse_stats(r.stderr.decode()) == g["stats"].tolist()
+    r = subprocess.run([str(patched), "-a", "-m", "-f", str(f)], capture_output=True, timeout=120)
+    assert r.stdout == g["avrmlat_a"]
+    assert _parse_stats(r.stderr.decode()) == g["stats_a"].tolist()
+    rb = oracle.run_ref_tcp(f, flags=("-a", "-b"), binary=patched, timeout=120)
+    assert rb.stdout == g["beast_a"]
+
+
 def test_cli_beast_over_tcp_and_missing_file(adsb, tmp_path):
     import socket
     import threading
