@@ -34,7 +34,7 @@ EXPORTS = [
     "adsbdec_b200_format_packet", "adsbdec_b200_format_frames",
     "adsbdec_b200_envelope", "adsbdec_b200_resolver_new", "adsbdec_b200_resolver_free",
     "adsbdec_b200_resolver_feed", "adsbdec_b200_resolver_feed_frames", "adsbdec_b200_resolver_finish",
-    "adsbdec_b200_resolver_scan_end",
+    "adsbdec_b200_resolver_scan_end", "adsbdec_b200_resolver_num_frames", "adsbdec_b200_resolver_frames",
     "adsbdec_b200_chunk_candidates", "adsbdec_b200_debug_fused", "adsbdec_b200_last_error",
     "adsbdec_b200_version",
 ]
@@ -149,6 +149,10 @@ def lib():
         L.adsbdec_b200_resolver_scan_end.restype = u64
         L.adsbdec_b200_chunk_candidates.argtypes = [vp, vp, C.c_size_t, u64, u64, u64, vp, C.c_size_t, u32p]
         L.adsbdec_b200_chunk_candidates.restype = C.c_int64
+        L.adsbdec_b200_resolver_num_frames.argtypes = [vp]
+        L.adsbdec_b200_resolver_num_frames.restype = C.c_size_t
+        L.adsbdec_b200_resolver_frames.argtypes = [vp]
+        L.adsbdec_b200_resolver_frames.restype = vp
         L.adsbdec_b200_debug_fused.argtypes = [vp, vp, C.c_size_t, u64, vp, vp, vp, vp, C.c_size_t,
                                                C.POINTER(C.c_int64)]
         L.adsbdec_b200_last_error.restype = C.c_char_p
@@ -408,13 +412,23 @@ def envelope(samples: np.ndarray, count: int | None = None, *, device: int = 0, 
 class Resolver:
     """Host-only sequential rules over a sorted candidate list."""
 
-    def __init__(self, emulate_reference_tail: bool = True):
+    def __init__(self, emulate_reference_tail: bool = True, keep: bool = False):
+        """keep=True: no per-frame callback; the frames pile up in the C resolver (frames_array)."""
         self._r = lib().adsbdec_b200_resolver_new(int(emulate_reference_tail))
         self.out: list[Frame] = []
 
         def tramp(p, n, ts, pw, _u):
             self.out.append(Frame(-1, int(ts), int(pw), bytes(p[:n])))
-        self._cb = SINK_FN(tramp)
+        self._cb = SINK_FN() if keep else SINK_FN(tramp)
+
+    @property
+    def frames_array(self) -> np.ndarray:
+        L = lib()
+        n = L.adsbdec_b200_resolver_num_frames(self._r)
+        if n == 0:
+            return np.zeros(0, dtype=FRAME_DTYPE)
+        buf = (C.c_uint8 * (n * FRAME_DTYPE.itemsize)).from_address(L.adsbdec_b200_resolver_frames(self._r))
+        return np.frombuffer(buf, dtype=FRAME_DTYPE).copy()
 
     def feed(self, cands: np.ndarray, scanned_upto: int, total_out: int) -> None:
         c = np.ascontiguousarray(cands, dtype=CAND_DTYPE)

@@ -71,15 +71,19 @@ def merge_candidates(parts: list[tuple[Chunk, np.ndarray]]) -> np.ndarray:
             assert c["n"].min() >= ch.own_begin and c["n"].max() < ch.own_end, "candidate outside its chunk"
         out.append(c)
     merged = np.concatenate(out) if out else np.zeros(0, dtype=CAND_DTYPE)
-    order = np.argsort(merged["n"], kind="stable")
-    return merged[order]
+    # every chunk's list comes sorted and the ownership ranges are disjoint and taken in order: the
+    # concatenation IS the merge (a sort of millions of records would cost more than the scans)
+    if merged.size > 1 and not np.all(merged["n"][1:] >= merged["n"][:-1]):
+        merged = merged[np.argsort(merged["n"], kind="stable")]
+    return merged
 
 
-def resolve_merged(merged: np.ndarray, n_samples: int, *, emulate_reference_tail: bool = True):
-    """Sequential rules over the merged list; returns the accepted frames (ts, pw, bytes)."""
+def resolve_merged(merged: np.ndarray, n_samples: int, *, emulate_reference_tail: bool = True, as_array: bool = False):
+    """Sequential rules over the merged list; returns the accepted frames (ts, pw, bytes) - as a list of
+    Frame, or (as_array) as a FRAME_DTYPE array without a Python call per frame."""
     from . import Resolver
     total_out = n_samples // 2
-    r = Resolver(emulate_reference_tail)
+    r = Resolver(emulate_reference_tail, keep=as_array)
     r.feed(merged, max(0, total_out - LOOKAHEAD), total_out)
     r.finish()
-    return r.out
+    return r.frames_array if as_array else r.out

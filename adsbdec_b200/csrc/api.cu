@@ -1692,9 +1692,10 @@ void adsbdec_b200_resolver_free(adsbdec_b200_resolver_t *r) { delete r; }
 
 static void resolver_emit(adsbdec_b200_resolver_t *r, adsbdec_b200_sink_fn fn, void *user)
 {
-	if (fn)
-		for (const adsbdec_b200_frame_t &f : r->out)
-			fn(f.bytes, f.len, f.ts, f.pw, user);
+	if (!fn)
+		return;  // no sink: the frames stay in the resolver (adsbdec_b200_resolver_frames)
+	for (const adsbdec_b200_frame_t &f : r->out)
+		fn(f.bytes, f.len, f.ts, f.pw, user);
 	r->out.clear();
 }
 
@@ -1727,6 +1728,12 @@ int adsbdec_b200_resolver_finish(adsbdec_b200_resolver_t *r, adsbdec_b200_sink_f
 	r->r.finish(r->out);
 	resolver_emit(r, fn, user);
 	return 0;
+}
+
+size_t adsbdec_b200_resolver_num_frames(const adsbdec_b200_resolver_t *r) { return r ? r->out.size() : 0; }
+const adsbdec_b200_frame_t *adsbdec_b200_resolver_frames(const adsbdec_b200_resolver_t *r)
+{
+	return r && !r->out.empty() ? r->out.data() : nullptr;
 }
 
 uint64_t adsbdec_b200_resolver_scan_end(const adsbdec_b200_resolver_t *r) { return r ? r->r.scan_end() : 0; }

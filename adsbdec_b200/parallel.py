@@ -39,11 +39,63 @@ def bind_to_gpu_numa_node(local_rank: int) -> list[int] | None:
     return None
 
 
+def pin_host_array(a: np.ndarray) -> bool:
+    """Page-lock an existing host array in place (cudaHostRegister) so that uploads out of it are real
+    asynchronous DMA.  Returns False (and leaves it pageable) if the driver refuses."""
+    import torch
+    try:
+        rc = torch.cuda.cudart().cudaHostRegister(a.ctypes.data, a.nbytes, 0)
+        return int(rc) == 0
+    except Exception:
+        return False
+
+
+def unpin_host_array(a: np.ndarray) -> None:
+    import torch
+    try:
+        torch.cuda.cudart().cudaHostUnregister(a.ctypes.data)
+    except Exception:
+        pass
+
+
+def scan_chunks(dec: Decoder, samples: np.ndarray, chunks, device: int, cand_cap: int = 1 << 20):
+    """Upload and scan `chunks` of the host array `samples` (best page-locked) on `device`, the upload of the
+    next chunk running on a side stream beside the scan of the current one (two device buffers).  Yields
+    (chunk, candidates)."""
+    import torch
+    if not chunks:
+        return
+    dev = torch.device("cuda", device)
+    longest = max(c.sample_end - c.sample_begin for c in chunks)
+    bufs = [torch.empty(longest, dtype=torch.int16, device=dev) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    host = samples.view(np.int16)
+
+    def upload(i):
+        ch = chunks[i]
+        n = ch.sample_end - ch.sample_begin
+        with torch.cuda.stream(copy_stream):
+            bufs[i % 2][:n].copy_(torch.from_numpy(host[ch.sample_begin:ch.sample_end]), non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    upload(0)
+    for i, ch in enumerate(chunks):
+        ready[i % 2].synchronize()
+        if i + 1 < len(chunks):
+            upload(i + 1)          # into the other buffer: its last scan has returned (chunk_candidates is synchronous)
+        lo, hi = ch.local_own
+        cands, _ = dec.chunk_candidates(bufs[i % 2].data_ptr(), ch.sample_end - ch.sample_begin, ch.sample_begin, lo, hi,
+                                        cap=cand_cap)
+        yield ch, cands
+
+
 def decode_chunked(samples: np.ndarray, *, n_chunks: int | None = None, accept_df18: bool = False,
-                   emulate_reference_tail: bool = True, device: int | None = None):
+                   emulate_reference_tail: bool = True, device: int | None = None, as_array: bool = False):
     """Decode ``samples`` (host uint16) split over all ranks of the default process group (or on
     one GPU when torch.distributed is not initialised).  Returns the accepted frames on rank 0
-    (``None`` elsewhere)."""
+    (``None`` elsewhere).  The chunks are uploaded from page-locked memory (the array is registered for the
+    duration of the call if it is not already)."""
     import torch
     import torch.distributed as dist
 
@@ -56,12 +108,12 @@ def decode_chunked(samples: np.ndarray, *, n_chunks: int | None = None, accept_d
     samples = np.ascontiguousarray(samples, dtype="<u2")
     chunks = plan_chunks(samples.size, n_chunks or 4 * world)
     dec = Decoder(device=device, accept_df18=accept_df18, collect_stats=False)
-    mine = []
-    for ch in assign(chunks, world, rank):
-        seg = torch.from_numpy(samples[ch.sample_begin:ch.sample_end].view(np.int16)).to(f"cuda:{device}")
-        lo, hi = ch.local_own
-        cands, _ = dec.chunk_candidates(seg.data_ptr(), seg.numel(), ch.sample_begin, lo, hi)
-        mine.append((ch, cands))
+    pinned_here = pin_host_array(samples)
+    try:
+        mine = list(scan_chunks(dec, samples, assign(chunks, world, rank), device))
+    finally:
+        if pinned_here:
+            unpin_host_array(samples)
     dec.close()
     if have_pg:
         gathered = [None] * world if rank == 0 else None
@@ -71,4 +123,5 @@ def decode_chunked(samples: np.ndarray, *, n_chunks: int | None = None, accept_d
         parts = [p for part in gathered for p in part]
     else:
         parts = mine
-    return resolve_merged(merge_candidates(parts), samples.size, emulate_reference_tail=emulate_reference_tail)
+    return resolve_merged(merge_candidates(parts), samples.size, emulate_reference_tail=emulate_reference_tail,
+                          as_array=as_array)

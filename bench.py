@@ -57,6 +57,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--kernel", type=int, default=0)
+    ap.add_argument("--mode", default="stream", choices=["stream", "chunked", "streams256"],
+                    help="stream: the headline (one 60 s capture per GPU); chunked / streams256: the two halves of "
+                         "configs[4] - ONE long capture halo-chunked over the GPUs, 256 receiver streams over the GPUs")
     return ap.parse_args()
 
 
@@ -317,6 +320,156 @@ def reference_arm(args):
 
 
 # ---------------------------------------------------------------------------------------------
+# configs[4]: one long capture halo-chunked over the GPUs / 256 receiver streams over the GPUs
+
+def _max_over_ranks(torch, dist, dev, x: float) -> float:
+    if not dist:
+        return x
+    t = torch.tensor([x], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def mode_chunked(args, torch, A, dist, world, rank, local):
+    """ONE capture (default 240 s = 4.8 G samples, longer than a 2^32-sample fidx epoch) in page-locked host
+    memory shared by the ranks; chunks with a 1200-sample halo go round-robin to the GPUs
+    (adsbdec_b200_chunk_candidates, upload beside scan), candidate lists to rank 0 (gather_object: results
+    only), one sequential resolve there.  Timed: uploads + scans + gather + merge + resolve.  Checked in the
+    run against a single decoder fed the same capture."""
+    from adsbdec_b200.chunking import assign, merge_candidates, plan_chunks, resolve_merged
+    from adsbdec_b200.parallel import pin_host_array, scan_chunks
+    dev = torch.device("cuda", local)
+    seconds = args.seconds if args.seconds != 60.0 else 240.0
+    n = capture_samples(seconds)
+    path = Path("/dev/shm") / f"adsb_b200_chunked_{os.environ.get('MASTER_PORT', '0')}.bin"
+    if rank == 0:
+        cap = np.memmap(path, dtype="<u2", mode="w+", shape=(n,))
+        build_capture(seconds, 4242, out=cap)
+        cap.flush()
+    if dist:
+        dist.barrier()
+    cap = np.memmap(path, dtype="<u2", mode="r+", shape=(n,))
+    pinned = pin_host_array(cap)
+    chunks = plan_chunks(n, max(4 * world, -(-n // (256 << 20))))
+    mine_chunks = assign(chunks, world, rank)
+    dec = A.Decoder(device=local, accept_df18=True, collect_stats=False)
+    times, frames = [], None
+    for it in range(args.warmup + args.steps):
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        mine = list(scan_chunks(dec, cap, mine_chunks, local))
+        t_scan = time.perf_counter() - t0
+        if dist:
+            gathered = [None] * world if rank == 0 else None
+            dist.gather_object(mine, gathered, dst=0)
+            parts = [p for part in gathered for p in part] if rank == 0 else None
+        else:
+            parts = mine
+        if rank == 0:
+            frames = resolve_merged(merge_candidates(parts), n, as_array=True)
+        dt = _max_over_ranks(torch, dist, dev, time.perf_counter() - t0)
+        if it >= args.warmup:
+            times.append((dt, _max_over_ranks(torch, dist, dev, t_scan)))
+    line = None
+    if rank == 0:
+        single = A.Decoder(device=local, accept_df18=True, collect_stats=False)
+        single.push(cap)
+        single.finish()
+        ref = single.frames_array
+        same = len(ref) == len(frames) and all(np.array_equal(ref[k], frames[k]) for k in ("ts", "pw", "len", "bytes"))
+        ms = float(np.mean([t[0] for t in times])) * 1e3
+        line = {"mode": "chunked", "metric": "Msamples/s", "value": n / (ms * 1e-3) / 1e6, "unit": "Msamples/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                "scan_ms_per_step": float(np.mean([t[1] for t in times])) * 1e3,
+                "higher_is_better": True, "scaling": "strong", "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"ONE {seconds:.0f} s capture ({n} samples, {2 * n / 1e9:.1f} GB, crosses a 2^32-sample "
+                                       f"fidx wrap) from page-locked host memory, {len(chunks)} chunks with a 1200-sample "
+                                       f"halo round-robin over {world} GPU(s), host merge + resolve on rank 0 (configs[4])",
+                           "chunks": len(chunks), "pinned": bool(pinned)},
+                "realtime_x": n / (ms * 1e-3) / FS, "frames": int(len(frames)),
+                "h2d_bytes_per_step": int(sum(2 * (c.sample_end - c.sample_begin) for c in chunks)),
+                "parity": {"parity_checked": True, "identical": bool(same),
+                           "what": "frames (ts, pw, len, bytes) of the chunked decode vs ONE decoder fed the whole capture"}}
+        print(json.dumps(line))
+    if dist:
+        dist.barrier()
+    del cap
+    if rank == 0:
+        path.unlink(missing_ok=True)
+    return 0
+
+
+def mode_streams256(args, torch, A, dist, world, rank, local):
+    """256 receiver streams spread over the GPUs (256 / N decoder handles per GPU), fed the way live
+    receivers deliver: 1 Mi-sample buffers (52 ms of signal, the reference's read size) round-robin over the
+    streams, from page-locked host memory, frames fetched as they come (flush + poll).  Every stream of a
+    rank carries the same 4 s capture (replicated data); all of them must decode to what one plain decode of
+    that capture gives."""
+    dev = torch.device("cuda", local)
+    total_streams = 256
+    per = total_streams // world
+    seconds = 4.0 if args.seconds == 60.0 else args.seconds
+    n = capture_samples(seconds)
+    host = torch.empty(n, dtype=torch.int16, pin_memory=True)
+    host_np = host.numpy().view("<u2")
+    build_capture(seconds, 777 + rank, out=host_np)
+    ref = A.Decoder(device=local, accept_df18=True)
+    ref.push(host_np)
+    ref.finish()
+    want, want_stats = ref.frames_array, ref.stats()
+    ref.close()
+    decs = [A.Decoder(device=local, accept_df18=True, batch_samples=4 << 20) for _ in range(per)]
+    piece = 1 << 20
+    times = []
+    for it in range(args.warmup + args.steps):
+        for d in decs:
+            d.reset()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for at in range(0, n, piece):
+            for d in decs:
+                d.push(host_np[at:at + piece])
+                d.flush()
+            for d in decs:
+                d.poll()
+        for d in decs:
+            d.finish()
+        dt = _max_over_ranks(torch, dist, dev, time.perf_counter() - t0)
+        if it >= args.warmup:
+            times.append(dt)
+    ok = True
+    for d in decs:
+        fa = d.frames_array
+        ok = ok and len(fa) == len(want) and all(np.array_equal(fa[k], want[k]) for k in ("ts", "pw", "len", "bytes")) \
+            and d.stats() == want_stats
+    okt = torch.tensor([1.0 if ok else 0.0], device=dev, dtype=torch.float64)
+    if dist:
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        ms = float(np.mean(times)) * 1e3
+        total = per * world * n
+        line = {"mode": "streams256", "metric": "Msamples/s", "value": total / (ms * 1e-3) / 1e6, "unit": "Msamples/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "strong", "dtype": "f32", "data": "synthetic (replicated per stream)",
+                "config": {"workload": f"{per * world} receiver streams x {seconds:.0f} s, {per} decoder handles per GPU on "
+                                       f"{world} GPU(s), 1 Mi-sample pushes round-robin from page-locked host memory, "
+                                       f"flush + poll after every push (configs[4])",
+                           "streams": per * world, "samples_per_stream": int(n)},
+                "realtime_x_per_stream": n / (ms * 1e-3) / FS, "streams_at_realtime": total / (ms * 1e-3) / FS,
+                "h2d_bytes_per_step": int(2 * total),
+                "parity": {"parity_checked": True, "identical": bool(okt.item() > 0.5),
+                           "what": "every stream's frames, timestamps and Try/Ok vs one plain decode of its capture"}}
+        print(json.dumps(line))
+    for d in decs:
+        d.close()
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
 # B200 arm
 
 def main():
@@ -346,6 +499,12 @@ def main():
         # keep each rank (and the page-locked memory it allocates) on the NUMA node of its GPU
         from adsbdec_b200.parallel import bind_to_gpu_numa_node
         bind_to_gpu_numa_node(local)
+
+    if args.mode != "stream":
+        rc = (mode_chunked if args.mode == "chunked" else mode_streams256)(args, torch, A, dist, world, rank, local)
+        if dist:
+            dist.destroy_process_group()
+        return rc
 
     seed = 1234 + rank     # every rank = its own receiver stream (weak scaling, no data-path collective)
     n_samples = capture_samples(args.seconds)

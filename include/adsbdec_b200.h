@@ -234,6 +234,10 @@ int adsbdec_b200_resolver_feed_frames(adsbdec_b200_resolver_t *r, const adsbdec_
 int adsbdec_b200_resolver_finish(adsbdec_b200_resolver_t *r, adsbdec_b200_sink_fn fn, void *user);
 /* Number of spans accepted so far / copy them ([start, start+skip) pairs). */
 uint64_t adsbdec_b200_resolver_scan_end(const adsbdec_b200_resolver_t *r);
+/* Without a sink (fn == NULL in feed / feed_frames / finish) the accepted frames are kept in the
+ * resolver, in ts order, and read here (valid until the next call on the resolver). */
+size_t adsbdec_b200_resolver_num_frames(const adsbdec_b200_resolver_t *r);
+const adsbdec_b200_frame_t *adsbdec_b200_resolver_frames(const adsbdec_b200_resolver_t *r);
 
 /* Raw candidate access for multi-GPU time-chunking: scan one chunk of a longer
  * capture and return every CRC-valid candidate whose preamble starts in [own_begin, own_end)
