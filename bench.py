@@ -362,16 +362,34 @@ def mode_chunked(args, torch, A, dist, world, rank, local):
         mine = list(scan_chunks(dec, cap, mine_chunks, local))
         t_scan = time.perf_counter() - t0
         if dist:
-            gathered = [None] * world if rank == 0 else None
-            dist.gather_object(mine, gathered, dst=0)
-            parts = [p for part in gathered for p in part] if rank == 0 else None
+            # results only: every rank's candidate records as one byte tensor, gathered on rank 0 over NCCL
+            # (a pickled gather_object of two million records cost more than the scans)
+            counts = torch.tensor([len(c) for _, c in mine] + [0] * (len(chunks) - len(mine)), device=dev)
+            all_counts = [torch.zeros_like(counts) for _ in range(world)]
+            dist.all_gather(all_counts, counts)
+            flat = np.concatenate([c for _, c in mine]) if mine else np.zeros(0, dtype=A.CAND_DTYPE)
+            longest = max(int(ac.sum().item()) for ac in all_counts)
+            send = torch.zeros(max(1, longest) * A.CAND_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+            send[:flat.nbytes] = torch.from_numpy(flat.view(np.uint8)).to(dev)
+            recv = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
+            dist.gather(send, recv, dst=0)
+            parts = None
+            if rank == 0:
+                parts = []
+                for r in range(world):
+                    rc = recv[r].cpu().numpy().view(A.CAND_DTYPE)
+                    at = 0
+                    for ch, cnt in zip(assign(chunks, world, r), all_counts[r].tolist()):
+                        parts.append((ch, rc[at:at + cnt]))
+                        at += cnt
         else:
             parts = mine
+        t_gather = time.perf_counter() - t0
         if rank == 0:
             frames = resolve_merged(merge_candidates(parts), n, as_array=True)
         dt = _max_over_ranks(torch, dist, dev, time.perf_counter() - t0)
         if it >= args.warmup:
-            times.append((dt, _max_over_ranks(torch, dist, dev, t_scan)))
+            times.append((dt, _max_over_ranks(torch, dist, dev, t_scan), t_gather - t_scan))
     line = None
     if rank == 0:
         single = A.Decoder(device=local, accept_df18=True, collect_stats=False)
@@ -383,6 +401,8 @@ def mode_chunked(args, torch, A, dist, world, rank, local):
         line = {"mode": "chunked", "metric": "Msamples/s", "value": n / (ms * 1e-3) / 1e6, "unit": "Msamples/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                 "scan_ms_per_step": float(np.mean([t[1] for t in times])) * 1e3,
+                "gather_ms_per_step": float(np.mean([t[2] for t in times])) * 1e3,
+                "merge_resolve_ms_per_step": float(np.mean([t[0] - t[1] - t[2] for t in times])) * 1e3,
                 "higher_is_better": True, "scaling": "strong", "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"ONE {seconds:.0f} s capture ({n} samples, {2 * n / 1e9:.1f} GB, crosses a 2^32-sample "
                                        f"fidx wrap) from page-locked host memory, {len(chunks)} chunks with a 1200-sample "
@@ -488,8 +508,19 @@ def main():
         import torch.distributed as dist_
         dist = dist_
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG", "WARN")     # keep NCCL's version banner off stdout (one JSON line)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        # NCCL's version banner goes to stdout when the communicator comes up: keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            torch.cuda.set_device(local)
+            dist.barrier()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the demodulation path has no CPU fallback")
     torch.cuda.set_device(local)
