@@ -28,6 +28,7 @@ namespace {
 
 int g_format = 0;  // 0 avr, 1 avrmlat, 2 beast (output.c:40)
 int g_sock = -1;
+bool g_network = false;  // -s / -l given: outmode 1 / 2 of the reference (output.c:38)
 
 void usage()
 {
@@ -103,7 +104,12 @@ void sink(const uint8_t *frame, int len, uint64_t ts, uint32_t pw, void *)
 	int n = adsbdec_b200_format_packet(g_format, frame, len, ts, pw, pkt);
 	if (n <= 0)
 		return;
-	if (g_sock >= 0) {
+	if (g_network) {
+		// -s / -l: frames only ever go to the socket.  After a write error the reference drops its queue
+		// and reconnects (output.c:320-327, :290-299); with a file as input there is nothing to wait for,
+		// so the remaining frames are dropped - never printed on stdout (binary beast with -b).
+		if (g_sock < 0)
+			return;
 		const char *p = pkt;
 		while (n > 0) {
 			ssize_t w = write(g_sock, p, (size_t)n);
@@ -167,6 +173,7 @@ int main(int argc, char **argv)
 		return 1;
 	}
 	if (addr) {
+		g_network = true;
 		g_sock = open_socket(addr, listener);
 		if (g_sock < 0) {
 			fprintf(stderr, "adsbdec_b200: cannot %s %s\n", listener ? "listen on" : "connect to", addr);

@@ -273,10 +273,11 @@ __global__ void __launch_bounds__(NT, ADSB_MINB) k_fused(const FusedParams p)
 					w[4 * i + 3] = t.w;
 				}
 
-				// 12-bit domain check (the float tricks below are exact for samples < 4096)
+				// 12-bit domain check (the float tricks below are exact for samples < 4096), over every word this
+				// lane uses: the history words in front of a job's first span belong to nobody else's check
 				uint32_t any = 0;
 #pragma unroll
-				for (int i = HIST; i < 36; i++)
+				for (int i = 2; i < 36; i++)
 					any |= w[i];
 				if (any & 0xF000F000u)
 					p.ctr->wide = 1;
