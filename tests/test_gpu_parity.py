@@ -88,6 +88,21 @@ def test_tail_and_tiny_inputs(adsb, oracle, n_samples):
         assert_same(ref, got, st)
 
 
+@pytest.mark.parametrize("kernel", [1, 0], ids=["generic", "fused"])
+def test_saturated_traffic_is_one_long_greedy_chain(adsb, oracle, kernel):
+    """Short frames back to back (one every 713 offsets, each 640 long): no two candidates are a full frame
+    (1200 offsets) apart, so the greedy rule (demod.c:128, :134) links the whole capture into ONE chain,
+    which k_greedy walks with a single thread.  Slow by design (the walk is the reference's own sequential
+    dependency) - but exact."""
+    cap = synth_capture(0.1, 1400, snr_db=22, seed=61, df_mix=((11, 1.0),), pad=1 << 16, poisson=False)
+    ref = oracle.decode(cap.samples, accept_df18=True)
+    d = adsb.decode(cap.samples, accept_df18=True, kernel=kernel)
+    assert frames_key(d.frames) == frames_key(ref.frames)
+    assert d.stats() == (ref.tried, ref.ok)
+    n = np.array([f.n for f in ref.frames])
+    assert len(n) > 1300 and np.diff(n).max() < 1200
+
+
 def test_tail_not_emulated_decodes_more(adsb, oracle):
     cap = synth_capture(0.06, 40, snr_db=20, seed=61, pad=0, poisson=False)
     d0 = adsb.decode(cap.samples)
