@@ -203,6 +203,7 @@ struct adsbdec_b200 {
 	int nb_cap[kSlots] = {};
 	SlotResolve *d_slot[kSlots] = {}, *h_slot[kSlots] = {};
 	FrameRec *d_acc[kSlots] = {};  // accepted frames of the job, in order, stamped
+	unsigned long long *d_key[kSlots] = {};  // (start << 1 | long) of the same frames: all the call schedule needs
 	ResolveState *d_state = nullptr;
 	int last_slot = 0;
 	unsigned int *d_bits[kSlots] = {};  // P | Q | B bit arrays of the slot's fused range
@@ -228,6 +229,7 @@ struct adsbdec_b200 {
 	// [0, n_vis) have been reached by the deqframe call schedule (what the API shows), [n_vis, n_total) are
 	// accepted by the greedy scan but still in front of the schedule (air.c:94-99).
 	adsbdec_b200_frame_t *frames = nullptr;
+	unsigned long long *fkeys = nullptr;  // fkeys[i] = frames[i].n << 1 | (112-bit frame): what the schedule reads
 	size_t frames_cap = 0, n_total = 0, n_vis = 0;
 	size_t emitted = 0;
 	size_t counted = 0;      // frames[0 .. counted) are in stat_ok already (the resolver counts while it copies)
@@ -270,16 +272,22 @@ int alloc_slot_outputs(adsbdec_b200 *h, int s, unsigned long long cand_cap, unsi
 	if (cand_cap != h->cand_cap[s]) {
 		if (h->d_cands[s]) cudaFree(h->d_cands[s]);
 		if (h->d_acc[s]) cudaFree(h->d_acc[s]);
+		if (h->d_key[s]) cudaFree(h->d_key[s]);
 		if (h->rb[s].sorted) cudaFree(h->rb[s].sorted);
 		if (h->rb[s].accept) cudaFree(h->rb[s].accept);
+		if (h->rb[s].keys) cudaFree(h->rb[s].keys);
 		h->d_cands[s] = h->rb[s].sorted = nullptr;
 		h->d_acc[s] = nullptr;
+		h->d_key[s] = nullptr;
 		h->rb[s].accept = nullptr;
+		h->rb[s].keys = nullptr;
 		h->cand_cap[s] = 0;  // a failed allocation below must not leave the old capacity behind
 		CU(cudaMalloc(&h->d_cands[s], cand_cap * sizeof(CandRec)));
 		CU(cudaMalloc(&h->d_acc[s], cand_cap * sizeof(FrameRec)));
+		CU(cudaMalloc(&h->d_key[s], cand_cap * sizeof(unsigned long long)));
 		CU(cudaMalloc(&h->rb[s].sorted, cand_cap * sizeof(CandRec)));
 		CU(cudaMalloc(&h->rb[s].accept, cand_cap));
+		CU(cudaMalloc(&h->rb[s].keys, cand_cap * sizeof(unsigned int)));
 		h->cand_cap[s] = cand_cap;
 	}
 	if (try_cap != h->try_cap[s]) {
@@ -311,13 +319,18 @@ int ensure_buckets(adsbdec_b200 *h, int s, int nb)
 		return 0;
 	RC(sync_compute(h));
 	ResolveBuffers &rb = h->rb[s];
-	unsigned int **arr[7] = {&rb.cnt, &rb.cur, &rb.off, &rb.bacc, &rb.bacc_x, &rb.bdrift, &rb.bdrift_x};
+	unsigned int **arr[6] = {&rb.cnt, &rb.off, &rb.bacc, &rb.bacc_x, &rb.bdrift, &rb.bdrift_x};
 	const int cap = nb + 1 + 4096;
 	for (unsigned int **a : arr) {
 		if (*a) cudaFree(*a);
 		*a = nullptr;
 		CU(cudaMalloc(a, (size_t)cap * sizeof(unsigned int)));
 	}
+	if (rb.part) cudaFree(rb.part);
+	rb.part = nullptr;
+	CU(cudaMalloc(&rb.part, (size_t)(cap / 4096 + 2) * sizeof(unsigned long long)));
+	// the bucket counts are zero between jobs: the scatter counts them back down (kernels_resolve.cu)
+	CU(cudaMemset(rb.cnt, 0, (size_t)cap * sizeof(unsigned int)));
 	h->nb_cap[s] = cap;
 	return 0;
 }
@@ -412,7 +425,7 @@ int launch_fused_range(adsbdec_b200 *h, int s, const Job &j, int64_t n0, int64_t
 		if (h->d_bits[s]) cudaFree(h->d_bits[s]);
 		h->d_bits[s] = nullptr;
 		h->bits_cap[s] = 0;
-		const int64_t cap = words_alloc + words_alloc / 8;
+		const int64_t cap = (words_alloc + words_alloc / 8 + 3) & ~(int64_t)3;  // the three arrays stay 16-byte aligned
 		CU(cudaMalloc(&h->d_bits[s], (size_t)cap * 3 * sizeof(unsigned int)));
 		h->bits_cap[s] = cap;
 	}
@@ -525,8 +538,8 @@ int enqueue_job(adsbdec_b200 *h, int s, bool force_generic)
 	CU(cudaStreamWaitEvent(h->st_res, h->ev_scan[s], 0));
 	if (j.resolve) {
 		CU(launch_resolve(h->rb[s], h->d_cands[s], h->d_ctr[s], h->cand_cap[s], j.n0, j.n1, h->d_state, h->d_slot[s],
-		                  h->d_acc[s], h->cand_cap[s], h->st_res));
-		h->launches += 10;
+		                  h->d_acc[s], h->d_key[s], h->cand_cap[s], h->st_res));
+		h->launches += 11;
 		if (j.used_fused) {  // demod.c:127: the signal level, for the frames that were accepted
 			CU(launch_fill_pw_frames(j.buf, j.u0, j.origin, h->d_acc[s], &h->d_slot[s]->n_accept, h->cand_cap[s],
 			                         h->st_res));
@@ -534,7 +547,7 @@ int enqueue_job(adsbdec_b200 *h, int s, bool force_generic)
 		}
 	} else {
 		CU(launch_sort(h->rb[s], h->d_cands[s], h->d_ctr[s], h->cand_cap[s], j.n0, j.n1, h->st_res));
-		h->launches += 4;
+		h->launches += 5;
 	}
 	CU(cudaEventRecord(h->ev_b[s], h->st_res));
 	CU(cudaMemcpyAsync(h->h_ctr[s], h->d_ctr[s], sizeof(Counters), cudaMemcpyDeviceToHost, h->st_res));
@@ -576,12 +589,19 @@ int reserve_frames(adsbdec_b200 *h, size_t more)
 	while (cap < h->n_total + more)
 		cap *= 2;
 	adsbdec_b200_frame_t *p = nullptr;
+	unsigned long long *k = nullptr;
 	CU(cudaMallocHost(&p, cap * sizeof(adsbdec_b200_frame_t)));
-	if (h->n_total)
+	CU(cudaMallocHost(&k, cap * sizeof(unsigned long long)));
+	if (h->n_total) {
 		memcpy(p, h->frames, h->n_total * sizeof(adsbdec_b200_frame_t));
+		memcpy(k, h->fkeys, h->n_total * sizeof(unsigned long long));
+	}
 	if (h->frames)
 		cudaFreeHost(h->frames);
+	if (h->fkeys)
+		cudaFreeHost(h->fkeys);
 	h->frames = p;
+	h->fkeys = k;
 	h->frames_cap = cap;
 	return 0;
 }
@@ -687,13 +707,16 @@ int complete_job(adsbdec_b200 *h, int s)
 	const double t2 = now_ms();
 	if (n_res) {
 		RC(reserve_frames(h, n_res));
+		CU(cudaMemcpyAsync(h->fkeys + h->n_total, h->d_key[s], n_res * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+		                   h->st_d2h));
 		CU(cudaMemcpyAsync(h->frames + h->n_total, h->d_acc[s], n_res * sizeof(FrameRec), cudaMemcpyDeviceToHost,
 		                   h->st_d2h));
 		CU(cudaStreamSynchronize(h->st_d2h));
+		h->tr.mark("complete_job: fetched");
 		h->n_total += n_res;
 	}
-	h->n_vis = h->res->advance_frames(h->frames, h->n_vis, h->n_total, (uint64_t)std::max<int64_t>(j.n1, 0),
-	                                  (uint64_t)j.total_out);
+	h->n_vis = h->res->advance_keys(h->fkeys, h->n_vis, h->n_total, (uint64_t)std::max<int64_t>(j.n1, 0),
+	                                (uint64_t)j.total_out);
 	h->counted = h->n_vis;
 	// (Ok counters: the GPU counted the job's accepted frames per class; the few the call schedule has not
 	// reached yet are taken off again wherever the counters are read)
@@ -982,10 +1005,12 @@ void adsbdec_b200_close(adsbdec_b200_t *h)
 		if (h->d_ctr[s]) cudaFree(h->d_ctr[s]);
 		if (h->h_ctr[s]) cudaFreeHost(h->h_ctr[s]);
 		if (h->d_acc[s]) cudaFree(h->d_acc[s]);
+		if (h->d_key[s]) cudaFree(h->d_key[s]);
 		if (h->rb[s].sorted) cudaFree(h->rb[s].sorted);
 		if (h->rb[s].accept) cudaFree(h->rb[s].accept);
 		if (h->rb[s].cnt) cudaFree(h->rb[s].cnt);
-		if (h->rb[s].cur) cudaFree(h->rb[s].cur);
+		if (h->rb[s].keys) cudaFree(h->rb[s].keys);
+		if (h->rb[s].part) cudaFree(h->rb[s].part);
 		if (h->rb[s].off) cudaFree(h->rb[s].off);
 		if (h->rb[s].bacc) cudaFree(h->rb[s].bacc);
 		if (h->rb[s].bacc_x) cudaFree(h->rb[s].bacc_x);
@@ -1022,6 +1047,7 @@ void adsbdec_b200_close(adsbdec_b200_t *h)
 	if (h->st_res) cudaStreamDestroy(h->st_res);
 	if (h->st_stat) cudaStreamDestroy(h->st_stat);
 	if (h->frames) cudaFreeHost(h->frames);
+	if (h->fkeys) cudaFreeHost(h->fkeys);
 	delete h->res;
 	delete h;
 }
@@ -1334,7 +1360,7 @@ int adsbdec_b200_finish(adsbdec_b200_t *h)
 	// (air.c:243-244 drops it) is taken off the counters
 	// the last deqframe calls; what they do not reach is dropped (air.c:243-244) and comes off the Ok counters,
 	// which the GPU keeps for everything it accepted
-	h->n_vis = h->res->finish_frames(h->frames, h->n_vis, h->n_total);
+	h->n_vis = h->res->finish_keys(h->fkeys, h->n_vis, h->n_total);
 	for (size_t i = h->n_vis; i < h->n_total; i++) {
 		const int df = h->frames[i].bytes[0] >> 3;
 		h->stat_ok[df == 11 ? 0 : df == 17 ? 1 : 2]--;
@@ -1490,8 +1516,10 @@ void adsbdec_b200_clear_frames(adsbdec_b200_t *h)
 		return;
 	// every frame shown so far goes; the ones still in front of the call schedule move up
 	const size_t keep = h->n_total - h->n_vis;
-	if (keep)
+	if (keep) {
 		memmove(h->frames, h->frames + h->n_vis, keep * sizeof(adsbdec_b200_frame_t));
+		memmove(h->fkeys, h->fkeys + h->n_vis, keep * sizeof(unsigned long long));
+	}
 	h->n_total = keep;
 	h->n_vis = 0;
 	h->emitted = 0;

@@ -36,9 +36,9 @@
 //   shared-memory loads and atomics, and at the 20 warps per SM the FIR's registers allow they took
 //   half of the warps' time for a third of the instructions (profiles/r2a).
 //
-// k_gate (word-parallel, one lane per 32 offsets): preamble = P[n] & Q[n+30]; DF gate = five bits of B
+// k_gate (word-parallel, one lane per 128 offsets): preamble = P[n] & Q[n+30]; DF gate = five bits of B
 //   at stride 10; survivors ("tries", valid.c:46, :68) are compacted with a warp scan and one atomic
-//   per 1024 offsets into the try list.
+//   per few hundred tries into the try list.
 //
 // k_slice (four lanes per try): a lane loads the ten B words that hold its 28 frame bits once, shifts
 //   them so that its first bit leads, pulls 7 nibbles out at constant positions (funnel shift +
@@ -452,7 +452,7 @@ constexpr int GATE_STAGE = 512;  // tries staged per warp (2 KB), as 32-bit offs
 // The try list gets the bare offsets here; k_slice, which reads the first frame bits anyway, adds the DF
 // class (demod.c:46-81: 10001 = DF17, 10010 = DF18, 01011 = DF11) that the statistics pass wants.
 #ifndef ADSB_GATE_MINB
-#define ADSB_GATE_MINB 8
+#define ADSB_GATE_MINB 4
 #endif
 #ifndef ADSB_SLICE_MINB
 #define ADSB_SLICE_MINB 6
@@ -461,12 +461,11 @@ __global__ void __launch_bounds__(256, ADSB_GATE_MINB) k_gate(const GateParams p
 {
 	//@region gate
 	__shared__ uint32_t stage_all[8][GATE_STAGE];
-	__shared__ uint32_t cnt_all[8];
 	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t lt = (1u << lane) - 1u;
 	uint32_t *const stage = stage_all[threadIdx.x >> 5];
-	uint32_t *const cnt = &cnt_all[threadIdx.x >> 5];
 	const uint32_t warp = blockIdx.x * 8u + (threadIdx.x >> 5);
-	const uint32_t stride = gridDim.x * 8u * 32u;
+	const uint32_t stride = gridDim.x * 8u * 128u;  // words per step of the whole grid
 	// words that hold owned offsets (n0 < n1, j0 <= n0, fewer than 2^31 offsets per launch) and the masks of
 	// the two words the range may own only in part
 	const uint32_t r0 = (uint32_t)(p.n0 - p.j0), r1 = (uint32_t)(p.n1 - 1 - p.j0);
@@ -474,106 +473,147 @@ __global__ void __launch_bounds__(256, ADSB_GATE_MINB) k_gate(const GateParams p
 	const uint32_t m_first = 0xFFFFFFFFu >> (r0 & 31u);
 	const uint32_t m_last = 0xFFFFFFFFu << (31u - (r1 & 31u));
 	const uint32_t df18_mask = p.accept_df18 ? 0xFFFFFFFFu : 0u;
-	const unsigned int *__restrict__ bp = p.bits_p;
-	const unsigned int *__restrict__ bq = p.bits_q;
-	const unsigned int *__restrict__ bb = p.bits_b;
-	if (lane == 0)
-		*cnt = 0;
-	__syncwarp();
-	uint32_t staged = 0;  // == *cnt, warp-uniform
+	// a lane takes FOUR consecutive words (16-byte loads: five per lane and step instead of 24 four-byte ones)
+	const uint4 *__restrict__ const bp = reinterpret_cast<const uint4 *>(p.bits_p);
+	const uint4 *__restrict__ const bq = reinterpret_cast<const uint4 *>(p.bits_q);
+	const uint4 *__restrict__ const bb = reinterpret_cast<const uint4 *>(p.bits_b);
+	const unsigned int *__restrict__ const bq1 = p.bits_q;
+	unsigned long long *const tries = p.tries;
+	unsigned long long *const n_try = &p.ctr->n_try;
+	const unsigned long long try_cap = p.try_cap;
+	const long long j0 = p.j0;
+	uint32_t staged = 0;  // entries in `stage`, warp-uniform
 	bool ovf = false;
 
+	// `staged` entries go to the try list: one atomic per few hundred tries, coalesced stores
 	auto flush = [&]() {
+		__syncwarp();  // the staged entries were written by other lanes
 		unsigned long long base = 0;
 		if (lane == 0)
-			base = atomicAdd(&p.ctr->n_try, (unsigned long long)staged);
+			base = atomicAdd(n_try, (unsigned long long)staged);
 		base = __shfl_sync(FULL, base, 0);
 		for (uint32_t i = lane; i < staged; i += 32u) {
-			if (base + i < p.try_cap)
-				p.tries[base + i] = (unsigned long long)(p.j0 + (long long)stage[i]);
+			if (base + i < try_cap)
+				tries[base + i] = (unsigned long long)(j0 + (long long)stage[i]);
 			else
 				ovf = true;
 		}
-		__syncwarp();
-		if (lane == 0)
-			*cnt = 0;
-		__syncwarp();
+		__syncwarp();  // the stage may be overwritten
 		staged = 0;
 	};
 
-	// The six words of the NEXT step are requested before this step is worked on: the kernel is a chain of
-	// L2 loads -> a few logic ops -> shared-memory appends, and one step in flight per warp left the
-	// schedulers idle half of the time (profiles/r2c).
 	struct Words {
-		uint32_t p0, q0, q1, b2, b3, b4;
+		uint4 p, q, b0, b1;  // P[G..G+3], Q[G..G+3], B[G..G+3], B[G+4..G+7]
+		uint32_t q4;         // Q[G+4]
 	};
-	auto fetch = [&](uint32_t g) {
-		Words w = {0u, 0u, 0u, 0u, 0u, 0u};
-		if (g <= g_hi) {
-			w.p0 = bp[g];
-			w.q0 = bq[g];
-			w.q1 = bq[g + 1];
-			w.b2 = bb[g + 2];
-			w.b3 = bb[g + 3];
-			w.b4 = bb[g + 4];
+	// (words past g_hi are never owned; the arrays are allocated 16 words beyond the last one written)
+	auto fetch = [&](uint32_t G) {
+		Words w;
+		w.p = w.q = w.b0 = w.b1 = make_uint4(0u, 0u, 0u, 0u);
+		w.q4 = 0u;
+		if (G <= g_hi) {
+			w.p = bp[G >> 2];
+			w.q = bq[G >> 2];
+			w.q4 = bq1[G + 4];
+			w.b0 = bb[G >> 2];
+			w.b1 = bb[(G >> 2) + 1];
 		}
 		return w;
 	};
-	Words nxt = fetch(g_lo + warp * 32u + lane);
-	for (uint32_t g0 = g_lo + warp * 32u; g0 <= g_hi; g0 += stride) {
-		const uint32_t g = g0 + lane;
+	// The words of the NEXT step are requested before this step is worked on: the kernel is a chain of
+	// DRAM loads -> a few logic ops -> shared-memory appends.
+	uint32_t G = (g_lo & ~3u) + warp * 128u + 4u * lane;
+	Words nxt = fetch(G);
+	// (G - 4 lane <= g_hi: warp-uniform; the range holds fewer than 2^26 words, so G + stride cannot wrap)
+	for (; G - 4u * lane <= g_hi; G += stride) {
 		const Words w = nxt;
-		if (g0 + stride <= g_hi && g0 + stride > g0)
-			nxt = fetch(g + stride);
-		uint32_t any = 0;
-		{
-			// demod.c:107: p1 > 2*s1 at n, p2 > 2*s2 at n+30 (words past g_hi are zero)
-			uint32_t pre = w.p0 & __funnelshift_l(w.q1, w.q0, 30);
+		nxt = fetch(G + stride);
+		const uint32_t P[4] = {w.p.x, w.p.y, w.p.z, w.p.w};
+		const uint32_t Q[5] = {w.q.x, w.q.y, w.q.z, w.q.w, w.q4};
+		const uint32_t B[8] = {w.b0.x, w.b0.y, w.b0.z, w.b0.w, w.b1.x, w.b1.y, w.b1.z, w.b1.w};
+		uint32_t any[4];
+		uint32_t c = 0;
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const uint32_t g = G + (uint32_t)k;
+			// demod.c:107: p1 > 2*s1 at n, p2 > 2*s2 at n+30
+			uint32_t pre = P[k] & __funnelshift_l(Q[k + 1], Q[k], 30);
+			if (g < g_lo || g > g_hi)
+				pre = 0u;
 			if (g == g_lo)
 				pre &= m_first;
 			if (g == g_hi)
 				pre &= m_last;
 			// first five data bits sit at n+80, +90, +100, +110, +120 (demod.c:110, :46-81)
-			const uint32_t x7 = __funnelshift_l(w.b3, w.b2, 16);  // 80  = 64 + 16
-			const uint32_t x6 = __funnelshift_l(w.b3, w.b2, 26);  // 90  = 64 + 26
-			const uint32_t x5 = __funnelshift_l(w.b4, w.b3, 4);   // 100 = 96 + 4
-			const uint32_t x4 = __funnelshift_l(w.b4, w.b3, 14);  // 110 = 96 + 14
-			const uint32_t x3 = __funnelshift_l(w.b4, w.b3, 24);  // 120 = 96 + 24
+			const uint32_t b2 = B[k + 2], b3 = B[k + 3], b4 = B[k + 4];
+			const uint32_t x7 = __funnelshift_l(b3, b2, 16);  // 80  = 64 + 16
+			const uint32_t x6 = __funnelshift_l(b3, b2, 26);  // 90  = 64 + 26
+			const uint32_t x5 = __funnelshift_l(b4, b3, 4);   // 100 = 96 + 4
+			const uint32_t x4 = __funnelshift_l(b4, b3, 14);  // 110 = 96 + 14
+			const uint32_t x3 = __funnelshift_l(b4, b3, 24);  // 120 = 96 + 24
 			const uint32_t c0 = pre & ~x5;
 			const uint32_t lng = c0 & x7 & ~x6;
-			any = (lng & ~x4 & x3)                  // 10001
-			      | (lng & x4 & ~x3 & df18_mask)    // 10010 (only with -a, demod.c:59)
-			      | (c0 & ~x7 & x6 & x4 & x3);      // 01011
+			any[k] = (lng & ~x4 & x3)                  // 10001
+			         | (lng & x4 & ~x3 & df18_mask)    // 10010 (only with -a, demod.c:59)
+			         | (c0 & ~x7 & x6 & x4 & x3);      // 01011
+			c += (uint32_t)__popc(any[k]);
 		}
-		const uint32_t c = (uint32_t)__popc(any);
-		const uint32_t total = __reduce_add_sync(FULL, c);
+		// Where each lane's tries go in the stage: counts stay below 8 almost always, so the exclusive prefix
+		// over the lanes is three ballots and population counts (no shared-memory atomics, no scan).
+		const uint32_t v0 = __ballot_sync(FULL, c & 1u), v1 = __ballot_sync(FULL, c & 2u), v2 = __ballot_sync(FULL, c & 4u);
+		const uint32_t big = __ballot_sync(FULL, c > 7u);
+		uint32_t total, at;
+		if (big == 0u) {
+			total = (uint32_t)__popc(v0) + 2u * (uint32_t)__popc(v1) + 4u * (uint32_t)__popc(v2);
+			at = (uint32_t)__popc(v0 & lt) + 2u * (uint32_t)__popc(v1 & lt) + 4u * (uint32_t)__popc(v2 & lt);
+		} else {
+			uint32_t x = c;  // inclusive scan by shuffles
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const uint32_t y = __shfl_up_sync(FULL, x, d);
+				if ((int)lane >= d)
+					x += y;
+			}
+			total = __shfl_sync(FULL, x, 31);
+			at = x - c;
+		}
 		if (total == 0u)
 			continue;
-		if (staged + total > (uint32_t)GATE_STAGE)
-			flush();
-		uint32_t rel = g << 5;  // offset of bit 31 of this lane's word, relative to j0
+		const uint32_t rel = G << 5;  // offset of bit 31 of this lane's first word, relative to j0
 		if (total > (uint32_t)GATE_STAGE) {
-			// absurd density (more than half of 1024 offsets pass the gate): straight to the list
-			unsigned long long at = c ? atomicAdd(&p.ctr->n_try, (unsigned long long)c) : 0ull;
-			while (any) {
-				const int i = __clz(any);
-				any &= ~(0x80000000u >> i);
-				if (at < p.try_cap)
-					p.tries[at] = (unsigned long long)(p.j0 + (long long)(rel + (uint32_t)i));
-				else
-					ovf = true;
-				at++;
+			// absurd density (more than an eighth of 4096 offsets pass the gate): straight to the list
+			unsigned long long dst = 0;
+			if (lane == 0)
+				dst = atomicAdd(n_try, (unsigned long long)total);
+			dst = __shfl_sync(FULL, dst, 0) + at;
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				uint32_t m = any[k];
+				while (m) {
+					const int i = __clz(m);
+					m &= ~(0x80000000u >> i);
+					if (dst < try_cap)
+						tries[dst] = (unsigned long long)(j0 + (long long)(rel + 32u * (uint32_t)k + (uint32_t)i));
+					else
+						ovf = true;
+					dst++;
+				}
 			}
 			continue;
 		}
-		uint32_t at = c ? atomicAdd(cnt, c) : 0u;
-		while (any) {
-			const int i = __clz(any);
-			any &= ~(0x80000000u >> i);
-			stage[at++] = rel + (uint32_t)i;
+		if (staged + total > (uint32_t)GATE_STAGE)
+			flush();
+		at += staged;
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			uint32_t m = any[k];
+			while (m) {
+				const int i = __clz(m);
+				m &= ~(0x80000000u >> i);
+				stage[at++] = rel + 32u * (uint32_t)k + (uint32_t)i;
+			}
 		}
 		staged += total;
-		__syncwarp();
 	}
 	if (staged)
 		flush();
@@ -773,8 +813,9 @@ cudaError_t launch_gate(const GateParams &p, cudaStream_t st)
 	if (p.n1 <= p.n0)
 		return cudaSuccess;
 	const long long words = ((p.n1 - 1 - p.j0) >> 5) - ((p.n0 - p.j0) >> 5) + 1;
-	const long long want = (words + 255) / 256;  // one step of 8 warps
-	k_gate<<<(unsigned)(want < 148 * 8 ? want : 148 * 8), 256, 0, st>>>(p);
+	const long long want = (words + 1023) / 1024;  // one step of 8 warps: 128 words each
+	const long long most = 148 * ADSB_GATE_MINB;
+	k_gate<<<(unsigned)(want < most ? want : most), 256, 0, st>>>(p);
 	return cudaGetLastError();
 }
 

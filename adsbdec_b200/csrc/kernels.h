@@ -50,8 +50,10 @@ struct SlotResolve {         // per job, copied back to the host
 struct ResolveBuffers {      // per job slot scratch
 	CandRec *sorted;         // cand_cap entries
 	unsigned char *accept;   // cand_cap entries
-	unsigned int *cnt, *cur, *off, *bacc, *bacc_x;  // bucket arrays, nb_cap + 1 entries each
+	unsigned int *keys;      // cand_cap entries: offsets (relative to the job) grouped by bucket
+	unsigned int *cnt, *off, *bacc, *bacc_x;        // bucket arrays, nb_cap + 1 entries each (cnt: zero between jobs)
 	unsigned int *bdrift, *bdrift_x;                // sum(skip - 1) of the accepted frames per bucket / scanned
+	unsigned long long *part;                       // totals of the 4096-entry tiles of a bucket scan
 };
 
 int resolve_bucket_count(long long n0, long long n1);
@@ -59,7 +61,7 @@ cudaError_t launch_sort(const ResolveBuffers &rb, const CandRec *cands, const Co
                         long long n0, long long n1, cudaStream_t st);
 cudaError_t launch_resolve(const ResolveBuffers &rb, const CandRec *cands, const Counters *ctr, unsigned long long cap,
                            long long n0, long long n1, ResolveState *state, SlotResolve *slot, FrameRec *out,
-                           unsigned long long out_cap, cudaStream_t st);
+                           unsigned long long *keys_out, unsigned long long out_cap, cudaStream_t st);
 cudaError_t launch_set_state(ResolveState *state, unsigned long long carry_start, unsigned long long carry_pos,
                              unsigned long long drift, cudaStream_t st);
 cudaError_t launch_count_tries_frames(const unsigned long long *tries, const unsigned long long *n_tries_ptr,

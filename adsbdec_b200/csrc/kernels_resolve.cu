@@ -1,8 +1,9 @@
 // kernels_resolve.cu - the sequential half of demod.c:84-144, done on the GPU over the sparse
 // candidate list of one scan job, so that only ACCEPTED frames travel back to the host.
 //
-//   1. order:   counting sort of the candidates by offset (4096-offset buckets: histogram, scan,
-//               scatter, insertion sort inside each bucket); frame bits are repacked to bytes here;
+//   1. order:   counting sort of the candidates by offset (4096-offset buckets: histogram, scan, the
+//               bucket's offsets as keys, rank among them = final place); frame bits are repacked to bytes
+//               on the way;
 //   2. greedy:  demod.c:128/:134 - after an accepted frame the scan resumes behind it.  A candidate
 //               that starts >= 1200 samples after its predecessor is accepted whatever happened
 //               before (no frame is longer than 1200), so the list falls apart into independent
@@ -43,15 +44,13 @@ __global__ void k_hist(const CandRec *__restrict__ c, const Counters *ctr, unsig
 		atomicAdd(&cnt[(unsigned long long)((long long)c[i].n - n0) >> kBShift], 1u);
 }
 
-// Exclusive scan of bucket counts (nb entries in, nb+1 out), single block, three block barriers per
-// 36 Ki entries: every warp scans its 128-entry slice of each 4 Ki tile with shuffles and leaves the
-// slice totals in shared memory; nine warps scan those; every thread then reloads its four entries per
-// tile (coalesced 16-byte accesses, L2-resident) and writes them with the offsets added.  DUAL scans
-// two arrays at once (accepted frames and their timestamp drift per bucket) packed into one 64-bit
-// value: both totals stay below 2^32 (a job holds < 2^28 offsets).
-constexpr int kScanTile = 4 * kScanThreads;
-constexpr int kScanTiles = 9;  // per pass: a full-size job has 32 Ki + 2 buckets
-
+// Exclusive scan of bucket counts (nb entries in, nb+1 out) in two launches: k_scan_sums leaves the total of
+// every 4096-entry tile, k_scan_apply adds up the tiles in front of its own and scans it (one coalesced 16-byte
+// load per thread, shuffles inside the warps, two block barriers).  A single block walking the whole array
+// took 17-23 us of the 130 us a job's ordering chain needs; a thread-contiguous single-block variant was
+// slower still (uncoalesced loads on one SM's L1).  DUAL scans two arrays at once (accepted frames and their
+// timestamp drift per bucket) packed into one 64-bit value: both totals stay below 2^32 (a job holds
+// < 2^29 offsets).
 template <bool DUAL>
 __device__ __forceinline__ void scan_load4(const unsigned int *__restrict__ in_a, const unsigned int *__restrict__ in_b,
                                            int i0, int nb, unsigned long long v[4])
@@ -71,80 +70,101 @@ __device__ __forceinline__ void scan_load4(const unsigned int *__restrict__ in_a
 	}
 }
 
-template <bool DUAL>
-__global__ void __launch_bounds__(kScanThreads)
-k_scan_buckets_t(const unsigned int *__restrict__ in_a, const unsigned int *__restrict__ in_b,
-                 unsigned int *__restrict__ out_a, unsigned int *__restrict__ out_b, int nb)
+constexpr int kScanTile = 4 * kScanThreads;
+
+// Inclusive scan of one value per thread over the block; returns the block total in `total`.
+__device__ __forceinline__ unsigned long long block_scan_incl(unsigned long long x, unsigned long long *wsum,
+                                                              unsigned long long &total)
 {
 	typedef unsigned long long T;
-	__shared__ T wsum[kScanTiles][32];
-	const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-	T carry = 0;  // identical in every thread
-	for (int base = 0; base < nb; base += kScanTiles * kScanTile) {
-		T ex[kScanTiles];  // sum of the entries of this tile in front of this thread's, inside its warp
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
-		for (int tl = 0; tl < kScanTiles; tl++) {
-			T v[4];
-			scan_load4<DUAL>(in_a, in_b, base + tl * kScanTile + 4 * t, nb, v);
-			const T mine = v[0] + v[1] + v[2] + v[3];
-			T x = mine;
-#pragma unroll
-			for (int d = 1; d < 32; d <<= 1) {
-				const T y = __shfl_up_sync(0xFFFFFFFFu, x, d);
-				if (lane >= d)
-					x += y;
-			}
-			ex[tl] = x - mine;
-			if (lane == 31)
-				wsum[tl][w] = x;
-		}
-		__syncthreads();
-		if (w < kScanTiles) {  // warp w: inclusive scan of tile w's 32 slice totals
-			T s = wsum[w][lane];
-#pragma unroll
-			for (int d = 1; d < 32; d <<= 1) {
-				const T y = __shfl_up_sync(0xFFFFFFFFu, s, d);
-				if (lane >= d)
-					s += y;
-			}
-			wsum[w][lane] = s;
-		}
-		__syncthreads();
-#pragma unroll
-		for (int tl = 0; tl < kScanTiles; tl++) {
-			const int i0 = base + tl * kScanTile + 4 * t;
-			T v[4];
-			scan_load4<DUAL>(in_a, in_b, i0, nb, v);
-			T pre = carry + (w ? wsum[tl][w - 1] : 0ull) + ex[tl];
-			unsigned int oa[4], ob[4];
-#pragma unroll
-			for (int k = 0; k < 4; k++) {
-				oa[k] = (unsigned int)pre;
-				ob[k] = (unsigned int)(pre >> 32);
-				pre += v[k];
-			}
-			if (i0 + 4 <= nb) {
-				*reinterpret_cast<uint4 *>(out_a + i0) = make_uint4(oa[0], oa[1], oa[2], oa[3]);
-				if (DUAL)
-					*reinterpret_cast<uint4 *>(out_b + i0) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
-			} else {
-#pragma unroll
-				for (int k = 0; k < 4; k++)
-					if (i0 + k < nb) {
-						out_a[i0 + k] = oa[k];
-						if (DUAL)
-							out_b[i0 + k] = ob[k];
-					}
-			}
-			carry += wsum[tl][31];
-		}
-		__syncthreads();  // wsum is reused by the next pass
+	for (int d = 1; d < 32; d <<= 1) {
+		const T y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+		if (lane >= d)
+			x += y;
 	}
-	if (t == 0) {
-		out_a[nb] = (unsigned int)carry;
+	if (lane == 31)
+		wsum[w] = x;
+	__syncthreads();
+	if (w == 0) {
+		T sv = wsum[lane];
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const T y = __shfl_up_sync(0xFFFFFFFFu, sv, d);
+			if (lane >= d)
+				sv += y;
+		}
+		wsum[lane] = sv;
+	}
+	__syncthreads();
+	total = wsum[31];
+	return x + (w ? wsum[w - 1] : 0ull);
+}
+
+template <bool DUAL>
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_sums(const unsigned int *__restrict__ in_a, const unsigned int *__restrict__ in_b, int nb,
+            unsigned long long *__restrict__ part)
+{
+	__shared__ unsigned long long wsum[32];
+	unsigned long long v[4], total;
+	scan_load4<DUAL>(in_a, in_b, blockIdx.x * kScanTile + 4 * threadIdx.x, nb, v);
+	block_scan_incl(v[0] + v[1] + v[2] + v[3], wsum, total);
+	if (threadIdx.x == 0)
+		part[blockIdx.x] = total;
+}
+
+template <bool DUAL>
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_apply(const unsigned int *__restrict__ in_a, const unsigned int *__restrict__ in_b,
+             unsigned int *__restrict__ out_a, unsigned int *__restrict__ out_b, int nb,
+             const unsigned long long *__restrict__ part)
+{
+	typedef unsigned long long T;
+	__shared__ T wsum[32];
+	T base = 0;  // total of the tiles in front of this one (a few dozen at most)
+	for (int k = 0; k < (int)blockIdx.x; k++)
+		base += part[k];
+	const int i0 = blockIdx.x * kScanTile + 4 * threadIdx.x;
+	T v[4], total;
+	scan_load4<DUAL>(in_a, in_b, i0, nb, v);
+	const T mine = v[0] + v[1] + v[2] + v[3];
+	T pre = base + block_scan_incl(mine, wsum, total) - mine;
+	unsigned int oa[4], ob[4];
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		oa[k] = (unsigned int)pre;
+		ob[k] = (unsigned int)(pre >> 32);
+		pre += v[k];
+	}
+	if (i0 + 4 <= nb) {
+		*reinterpret_cast<uint4 *>(out_a + i0) = make_uint4(oa[0], oa[1], oa[2], oa[3]);
 		if (DUAL)
-			out_b[nb] = (unsigned int)(carry >> 32);
+			*reinterpret_cast<uint4 *>(out_b + i0) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+	} else {
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+			if (i0 + k < nb) {
+				out_a[i0 + k] = oa[k];
+				if (DUAL)
+					out_b[i0 + k] = ob[k];
+			}
 	}
+	if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+		out_a[nb] = (unsigned int)(base + total);
+		if (DUAL)
+			out_b[nb] = (unsigned int)((base + total) >> 32);
+	}
+}
+
+template <bool DUAL>
+void launch_scan(const unsigned int *in_a, const unsigned int *in_b, unsigned int *out_a, unsigned int *out_b, int nb,
+                 unsigned long long *part, cudaStream_t st)
+{
+	const int tiles = (nb + kScanTile - 1) / kScanTile;
+	k_scan_sums<DUAL><<<tiles, kScanThreads, 0, st>>>(in_a, in_b, nb, part);
+	k_scan_apply<DUAL><<<tiles, kScanThreads, 0, st>>>(in_a, in_b, out_a, out_b, nb, part);
 }
 
 __device__ __forceinline__ void repack(CandRec &o, const CandRec &c)
@@ -185,34 +205,39 @@ __device__ __forceinline__ void repack(CandRec &o, const CandRec &c)
 	o.bytes[15] = (uint8_t)nfix;
 }
 
-__global__ void k_scatter(const CandRec *__restrict__ c, const Counters *ctr, unsigned long long cap, long long n0,
-                          const unsigned int *__restrict__ off, unsigned int *cur, CandRec *__restrict__ sorted)
+// Ordering inside a bucket without moving records twice: the offsets of a bucket's candidates are dropped
+// into its slice of `keys` in whatever order the atomics fall (the counts of k_hist are used up again as
+// cursors and end at zero, ready for the next job), then every candidate counts the keys of its bucket
+// that are smaller than its own - a handful - and goes straight to its final place.  No two candidates
+// share an offset.
+__global__ void k_scatter_keys(const CandRec *__restrict__ c, const Counters *ctr, unsigned long long cap, long long n0,
+                               const unsigned int *__restrict__ off, unsigned int *cnt, unsigned int *__restrict__ keys)
 {
 	const unsigned long long m = job_count(ctr, cap);
 	for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < m;
 	     i += (unsigned long long)gridDim.x * blockDim.x) {
-		const unsigned long long b = (unsigned long long)((long long)c[i].n - n0) >> kBShift;
-		const unsigned int p = off[b] + atomicAdd(&cur[b], 1u);
-		CandRec r;
-		repack(r, c[i]);
-		sorted[p] = r;
+		const unsigned long long rel = (unsigned long long)((long long)c[i].n - n0);
+		const unsigned long long b = rel >> kBShift;
+		keys[off[b] + atomicSub(&cnt[b], 1u) - 1u] = (unsigned int)rel;
 	}
 }
 
-// Orders the few entries of each bucket (the scatter order inside a bucket is arbitrary).
-__global__ void k_bucket_sort(CandRec *sorted, const unsigned int *__restrict__ off, int nb)
+__global__ void k_rank_move(const CandRec *__restrict__ c, const Counters *ctr, unsigned long long cap, long long n0,
+                            const unsigned int *__restrict__ off, const unsigned int *__restrict__ keys,
+                            CandRec *__restrict__ sorted)
 {
-	for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
-		const unsigned int lo = off[b], hi = off[b + 1];
-		for (unsigned int i = lo + 1; i < hi; i++) {
-			const CandRec v = sorted[i];
-			unsigned int k = i;
-			while (k > lo && sorted[k - 1].n > v.n) {
-				sorted[k] = sorted[k - 1];
-				k--;
-			}
-			sorted[k] = v;
-		}
+	const unsigned long long m = job_count(ctr, cap);
+	for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < m;
+	     i += (unsigned long long)gridDim.x * blockDim.x) {
+		const unsigned long long rel = (unsigned long long)((long long)c[i].n - n0);
+		const unsigned long long b = rel >> kBShift;
+		const unsigned int lo = off[b], hi = off[b + 1], mine = (unsigned int)rel;
+		unsigned int rank = 0;
+		for (unsigned int q = lo; q < hi; q++)
+			rank += keys[q] < mine;
+		CandRec r;
+		repack(r, c[i]);
+		sorted[lo + rank] = r;
 	}
 }
 
@@ -283,7 +308,8 @@ __global__ void k_bucket_stats(const CandRec *__restrict__ sorted, const unsigne
 __global__ void k_compact(const CandRec *__restrict__ sorted, const unsigned char *__restrict__ accept,
                           const unsigned int *__restrict__ off, int nb, const unsigned int *__restrict__ bacc_x,
                           const unsigned int *__restrict__ bdrift_x, FrameRec *__restrict__ out,
-                          unsigned long long out_cap, ResolveState *st, SlotResolve *slot)
+                          unsigned long long *__restrict__ keys_out, unsigned long long out_cap, ResolveState *st,
+                          SlotResolve *slot)
 {
 	const unsigned long long drift0 = slot->drift0;
 	unsigned int ok[3] = {0, 0, 0};  // accepted frames per class (valid.c:53, :75), one atomic per warp at the end
@@ -311,6 +337,8 @@ __global__ void k_compact(const CandRec *__restrict__ sorted, const unsigned cha
 #pragma unroll
 					for (int k = 0; k < 5; k++)
 						o[k] = w[k];
+					// what the host's call schedule (air.c:94-99) looks at, 8 bytes instead of 40: start and length
+					keys_out[p] = (c.n << 1) | (c.len == 7 ? 0ull : 1ull);
 				}
 				drift += skip_of(c.len) - 1ull;
 				p++;
@@ -404,21 +432,18 @@ cudaError_t launch_sort(const ResolveBuffers &rb, const CandRec *cands, const Co
                         long long n0, long long n1, cudaStream_t st)
 {
 	const int nb = resolve_bucket_count(n0, n1);
-	cudaError_t e = cudaMemsetAsync(rb.cnt, 0, (size_t)(nb + 1) * sizeof(unsigned int), st);
-	if (e != cudaSuccess) return e;
-	e = cudaMemsetAsync(rb.cur, 0, (size_t)(nb + 1) * sizeof(unsigned int), st);
-	if (e != cudaSuccess) return e;
+	// (rb.cnt is all zero here: zeroed when it was allocated, counted back down to zero by every job)
 	k_hist<<<296, 256, 0, st>>>(cands, ctr, cap, n0, rb.cnt);
-	k_scan_buckets_t<false><<<1, kScanThreads, 0, st>>>(rb.cnt, nullptr, rb.off, nullptr, nb);
-	k_scatter<<<296, 256, 0, st>>>(cands, ctr, cap, n0, rb.off, rb.cur, rb.sorted);
-	k_bucket_sort<<<(nb + 127) / 128, 128, 0, st>>>(rb.sorted, rb.off, nb);
+	launch_scan<false>(rb.cnt, nullptr, rb.off, nullptr, nb, rb.part, st);
+	k_scatter_keys<<<296, 256, 0, st>>>(cands, ctr, cap, n0, rb.off, rb.cnt, rb.keys);
+	k_rank_move<<<296, 256, 0, st>>>(cands, ctr, cap, n0, rb.off, rb.keys, rb.sorted);
 	return cudaGetLastError();
 }
 
 // Sort + greedy + compaction: `out` receives the accepted candidates in order, slot->n_accept their number.
 cudaError_t launch_resolve(const ResolveBuffers &rb, const CandRec *cands, const Counters *ctr, unsigned long long cap,
                            long long n0, long long n1, ResolveState *state, SlotResolve *slot, FrameRec *out,
-                           unsigned long long out_cap, cudaStream_t st)
+                           unsigned long long *keys_out, unsigned long long out_cap, cudaStream_t st)
 {
 	const int nb = resolve_bucket_count(n0, n1);
 	cudaError_t e = launch_sort(rb, cands, ctr, cap, n0, n1, st);
@@ -426,9 +451,9 @@ cudaError_t launch_resolve(const ResolveBuffers &rb, const CandRec *cands, const
 	k_snapshot<<<1, 1, 0, st>>>(state, slot);
 	k_greedy<<<296, 256, 0, st>>>(rb.sorted, rb.off, nb, rb.accept, state, slot);
 	k_bucket_stats<<<(nb + 127) / 128, 128, 0, st>>>(rb.sorted, rb.accept, rb.off, nb, rb.bacc, rb.bdrift);
-	k_scan_buckets_t<true><<<1, kScanThreads, 0, st>>>(rb.bacc, rb.bdrift, rb.bacc_x, rb.bdrift_x, nb);
-	k_compact<<<(nb + 127) / 128, 128, 0, st>>>(rb.sorted, rb.accept, rb.off, nb, rb.bacc_x, rb.bdrift_x, out, out_cap,
-	                                             state, slot);
+	launch_scan<true>(rb.bacc, rb.bdrift, rb.bacc_x, rb.bdrift_x, nb, rb.part, st);
+	k_compact<<<(nb + 127) / 128, 128, 0, st>>>(rb.sorted, rb.accept, rb.off, nb, rb.bacc_x, rb.bdrift_x, out, keys_out,
+	                                             out_cap, state, slot);
 	return cudaGetLastError();
 }
 

@@ -9,8 +9,34 @@
 
 namespace adsb {
 
+// scan_to for advance_keys / finish_keys: only stamped frames exist, as keys (start << 1 | long).
+void Resolver::scan_keys_to(uint64_t cutoff)
+{
+	uint64_t pos = base_;
+	const unsigned long long *k = kin_;
+	const size_t n = fin_n_, i0 = fin_i_;
+	size_t i = i0;
+	if (i < n && (k[i] >> 1) < cutoff) {
+		const auto below = [cutoff](unsigned long long x, uint64_t) { return (x >> 1) < cutoff; };
+		const size_t w = std::min(n, i + 64);
+		size_t e = (size_t)(std::lower_bound(k + i, k + w, cutoff, below) - k);
+		if (e == w && w < n)
+			e = (size_t)(std::lower_bound(k + w, k + n, cutoff, below) - k);
+		i = e;
+	}
+	if (i > i0)
+		pos = (k[i - 1] >> 1) + ((k[i - 1] & 1ull) ? kSkipLong : kSkipShort);
+	fin_i_ = i;
+	base_ = std::max(cutoff, pos);  // deqframe returns idx; air.c:96-98 keeps the rest
+	scan_end_ = cutoff;
+}
+
 void Resolver::scan_to(uint64_t cutoff, std::vector<adsbdec_b200_frame_t> &accepted)
 {
+	if (kin_) {
+		scan_keys_to(cutoff);
+		return;
+	}
 	// One deqframe(ampbuff, len) call whose loop bound len-DECOFFSET is `cutoff` in absolute
 	// offsets (demod.c:89).  idx starts at ampbuff[0] = base_.  Candidates come from the few left
 	// over from earlier feeds (pending_) and then, in place, from the array being fed.
@@ -182,6 +208,41 @@ size_t Resolver::advance_frames(const adsbdec_b200_frame_t *f, size_t n_vis, siz
 	run_calls(none);
 	const size_t r = n_vis + fin_i_;
 	fin_ = nullptr;
+	fin_n_ = fin_i_ = fin_done_ = 0;
+	inplace_ = false;
+	return r;
+}
+
+size_t Resolver::advance_keys(const unsigned long long *k, size_t n_vis, size_t n_total, uint64_t scanned_upto,
+                              uint64_t total_out)
+{
+	std::vector<adsbdec_b200_frame_t> none;
+	inplace_ = true;
+	ok_ = nullptr;
+	kin_ = k + n_vis;
+	fin_n_ = n_total - n_vis;
+	fin_i_ = fin_done_ = 0;
+	scanned_upto_ = std::max(scanned_upto_, scanned_upto);
+	total_out_ = std::max(total_out_, total_out);
+	run_calls(none);
+	const size_t r = n_vis + fin_i_;
+	kin_ = nullptr;
+	fin_n_ = fin_i_ = fin_done_ = 0;
+	inplace_ = false;
+	return r;
+}
+
+size_t Resolver::finish_keys(const unsigned long long *k, size_t n_vis, size_t n_total)
+{
+	std::vector<adsbdec_b200_frame_t> none;
+	inplace_ = true;
+	ok_ = nullptr;
+	kin_ = k + n_vis;
+	fin_n_ = n_total - n_vis;
+	fin_i_ = fin_done_ = 0;
+	finish(none, nullptr);
+	const size_t r = n_vis + fin_i_;
+	kin_ = nullptr;
 	fin_n_ = fin_i_ = fin_done_ = 0;
 	inplace_ = false;
 	return r;

@@ -39,6 +39,11 @@ public:
 	size_t advance_frames(const adsbdec_b200_frame_t *f, size_t n_vis, size_t n_total, uint64_t scanned_upto,
 	                      uint64_t total_out);
 	size_t finish_frames(const adsbdec_b200_frame_t *f, size_t n_vis, size_t n_total);
+	// The same on a compact copy of what the schedule looks at: k[i] = f[i].n << 1 | (f[i].len == 14).  The host
+	// reads 8 bytes per frame instead of touching every cache line of the 40-byte records the GPU just wrote.
+	size_t advance_keys(const unsigned long long *k, size_t n_vis, size_t n_total, uint64_t scanned_upto,
+	                    uint64_t total_out);
+	size_t finish_keys(const unsigned long long *k, size_t n_vis, size_t n_total);
 
 	// DF11 / DF17 / DF18 frames fed as stamped frames that the call schedule has not reached yet.
 	void count_pending(uint32_t out[3]) const;
@@ -51,6 +56,7 @@ public:
 private:
 	void run_calls(std::vector<adsbdec_b200_frame_t> &accepted);
 	void scan_to(uint64_t cutoff, std::vector<adsbdec_b200_frame_t> &accepted);
+	void scan_keys_to(uint64_t cutoff);
 	void flush_stamped(std::vector<adsbdec_b200_frame_t> &accepted);
 
 	bool emulate_tail_;
@@ -67,6 +73,7 @@ private:
 	std::vector<adsbdec_b200_frame_t> fpending_;    // stamped frames the call schedule has not reached
 	size_t fhead_ = 0, fdone_ = 0;                  // [fdone_, fhead_) consumed but not copied out yet
 	const adsbdec_b200_frame_t *fin_ = nullptr;
+	const unsigned long long *kin_ = nullptr;       // advance_keys / finish_keys: the compact form of fin_
 	size_t fin_n_ = 0, fin_i_ = 0, fin_done_ = 0;
 	uint32_t *ok_ = nullptr;  // where scan_to counts the stamped frames it accepts
 };

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Step time of the resident bench under the development knobs of api.cu.
-for ts in 0 1; do for sms in 8 16; do
-  echo "== ADSB_B200_TAIL_SPLIT=$ts ADSB_B200_RESOLVE_SMS=$sms"
-  ADSB_B200_TAIL_SPLIT=$ts ADSB_B200_RESOLVE_SMS=$sms timeout 120 python tools/run_resident.py 60 6 2>&1 | tail -4 | grep -E "wall|step" | tail -2 | cut -c1-120
-done; done
+for sms in ${SMS_LIST:-2 4 8 12 16}; do
+  echo "== ADSB_B200_RESOLVE_SMS=$sms"
+  ADSB_B200_RESOLVE_SMS=$sms timeout 120 python tools/run_resident.py 60 6 2>&1 | tail -4 | grep -E "wall|step" | tail -2 | cut -c1-150
+done

@@ -43,6 +43,31 @@ __global__ void __launch_bounds__(640, 1) k(float *out, uint32_t seed)
 			if (MODE == 14) f[i] = __fmaf_rn(f[i], f[(i + 1) & 7], f[(i + 2) & 7]); // FFMA 3 distinct regs
 			if (MODE == 15) g[i] = __ffma2_rn(g[i], g[(i + 1) & 7], g[(i + 2) & 7]); // FFMA2 3 distinct reg pairs
 		}
+		if (MODE == 16) {  // the same 8 FFMA2 + 8 FFMA as mode 8, but in two blocks instead of alternating
+#pragma unroll
+			for (int i = 0; i < 8; i++) g[i] = __ffma2_rn(g[i], c12, c22);
+#pragma unroll
+			for (int i = 0; i < 8; i++) f[i] = __fmaf_rn(f[i], c1, c2);
+		}
+		if (MODE == 17) {  // 8 FFMA2 + 8 FFMA in groups of two
+#pragma unroll
+			for (int i = 0; i < 8; i += 2) {
+				g[i] = __ffma2_rn(g[i], c12, c22); g[i + 1] = __ffma2_rn(g[i + 1], c12, c22);
+				f[i] = __fmaf_rn(f[i], c1, c2); f[i + 1] = __fmaf_rn(f[i + 1], c1, c2);
+			}
+		}
+		if (MODE == 18) {  // squares as k_fused has them: FMUL + FFMA (scalar) per FFMA2 x 7
+#pragma unroll
+			for (int i = 0; i < 8; i++) {
+				g[i] = __ffma2_rn(g[i], c12, c22);
+				if (i == 7) { f[0] = __fmul_rn(f[0], c1); f[1] = __fmaf_rn(f[1], c1, c2); }
+			}
+		}
+		if (MODE == 19) {  // the same with one packed pair instead of the two scalars
+#pragma unroll
+			for (int i = 0; i < 8; i++)
+				g[i] = __ffma2_rn(g[i], c12, c22);
+		}
 	}
 	float acc = 0;
 #pragma unroll
@@ -94,5 +119,9 @@ int main()
 	run<10>("FADD -> SHF (dependent)", 2, d);
 	run<12>("FFMA2 + PRMT", 2, d);
 	run<13>("FFMA2 + FADD2", 2, d);
+	run<16>("8 FFMA2 then 8 FFMA", 2, d);
+	run<17>("FFMA2 x2, FFMA x2", 2, d);
+	run<18>("7 FFMA2 + FMUL + FFMA", 1, d);
+	run<19>("8 FFMA2", 1, d);
 	return 0;
 }
