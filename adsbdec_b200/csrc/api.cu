@@ -76,7 +76,8 @@ constexpr int64_t kBulkRead = 16ll << 20;  // decode_file: samples fetched per p
 constexpr int64_t kPackSlice = 32ll << 20; // push_packed12: samples uploaded and unpacked per step
 constexpr unsigned long long kPendCap = 1ull << 18;
 constexpr int kSlots = 3;                  // scan jobs in flight: three keep the GPU busy while the host hands frames out
-constexpr int kResolveSMs = 8;             // SMs k_fused leaves to the resolve chain of the previous job
+constexpr int kResolveSMs = 0;             // SMs k_fused leaves free: none - the resolve chain of the previous job runs in blocks of
+                                           // 128 threads x 32 registers, which fit BESIDE k_fused on every SM (kernels_resolve.cu)
 
 __global__ void k_reset_counters(Counters *c)
 {
@@ -328,7 +329,7 @@ int ensure_buckets(adsbdec_b200 *h, int s, int nb)
 	}
 	if (rb.part) cudaFree(rb.part);
 	rb.part = nullptr;
-	CU(cudaMalloc(&rb.part, (size_t)(cap / 4096 + 2) * sizeof(unsigned long long)));
+	CU(cudaMalloc(&rb.part, (size_t)(cap / 512 + 2) * sizeof(unsigned long long)));
 	// the bucket counts are zero between jobs: the scatter counts them back down (kernels_resolve.cu)
 	CU(cudaMemset(rb.cnt, 0, (size_t)cap * sizeof(unsigned int)));
 	h->nb_cap[s] = cap;
@@ -1278,21 +1279,29 @@ int adsbdec_b200_push_device(adsbdec_b200_t *h, const void *dev_samples, size_t 
 	if (piece_u0 == 0 && !h->job[0].active && !h->job[1].active && !h->job[2].active)  // a fresh stream: nothing refers to the lists yet
 		for (int s = 0; s < kSlots; s++)
 			RC(presize_lists(h, s, per / 2));
-	// (cutting the last job in two, so that less of its resolve chain and hand-over is exposed, measured no
-	// gain: 1.55 ms per 60 s capture either way, profiles/README.md)
-	int tail_split = 0;
-	if (const char *e = getenv("ADSB_B200_TAIL_SPLIT"))  // development knob
-		tail_split = atoi(e);
-	for (int64_t end = piece_u0; end < piece_u1;) {
-		int64_t step = per;
-		if (tail_split && piece_u1 - end <= per && piece_u1 - end > (8 << 20)) {
-			step = align_down((piece_u1 - end) / 2 + 7, 8);
-			tail_split = 0;  // once
+	// development knob: the piece cut at these percentages instead of into equal jobs, e.g. "25,50,25"
+	std::vector<int64_t> ends;
+	if (const char *e = getenv("ADSB_B200_JOB_SPLIT")) {
+		double acc = 0;
+		for (const char *q = e; *q;) {
+			char *nx = nullptr;
+			acc += strtod(q, &nx);
+			if (nx == q)
+				break;
+			ends.push_back(std::min(piece_u1, piece_u0 + align_down((int64_t)((double)total * acc / 100.0) + 7, 8)));
+			q = *nx ? nx + 1 : nx;
 		}
-		end = std::min(piece_u1, end + step);
+		if (ends.empty() || ends.back() != piece_u1)
+			ends.push_back(piece_u1);
+	} else {
+		for (int64_t end = piece_u0; end < piece_u1;)
+			ends.push_back(end = std::min(piece_u1, end + per));
+	}
+	for (const int64_t end : ends) {
 		// window: from the FIR history of the next owned offset to `end`, inside the caller's memory
 		const int64_t w0 = std::max<int64_t>(piece_u0, align_down(2 * h->own_next - kCarryBack, 8));
-		RC(submit_window(h, src + (w0 - piece_u0), w0, end));
+		if (end > w0)
+			RC(submit_window(h, src + (w0 - piece_u0), w0, end));
 	}
 	RC(complete_all(h));  // the caller's memory is no longer needed after this ...
 	h->dev_fill = 0;

@@ -125,7 +125,8 @@ __global__ void k_fill_pw(const uint16_t *__restrict__ raw, long long u_raw0, un
 
 // The same for ACCEPTED frames (the stream path): a third of the candidates survive the greedy rule, so the
 // signal level is only worked out for those, behind the compaction.
-__global__ void k_fill_pw_frames(const uint16_t *__restrict__ raw, long long u_raw0, unsigned long long phase_origin,
+// (128 threads x 32 registers: fits beside k_fused of the next job, see kernels_resolve.cu)
+__global__ void __launch_bounds__(128, 16) k_fill_pw_frames(const uint16_t *__restrict__ raw, long long u_raw0, unsigned long long phase_origin,
                                  FrameRec *frames, const unsigned long long *n_ptr, unsigned long long cap)
 {
 	unsigned long long n_fr = *n_ptr;
@@ -291,7 +292,7 @@ cudaError_t launch_fill_pw(const uint16_t *raw, long long u_raw0, unsigned long 
 cudaError_t launch_fill_pw_frames(const uint16_t *raw, long long u_raw0, unsigned long long origin, FrameRec *frames,
                                   const unsigned long long *n_ptr, unsigned long long cap, cudaStream_t st)
 {
-	k_fill_pw_frames<<<296, 256, 0, st>>>(raw, u_raw0, origin, frames, n_ptr, cap);
+	k_fill_pw_frames<<<592, 128, 0, st>>>(raw, u_raw0, origin, frames, n_ptr, cap);
 	return cudaGetLastError();
 }
 

@@ -27,7 +27,24 @@ namespace adsb {
 namespace {
 
 constexpr int kBShift = 12;  // bucket = 4096 offsets
+
+// Footprint of the chain's kernels.  They run on their own stream beside k_fused of the NEXT job, which holds
+// 640 threads x 96 registers on every SM: 4096 registers, 62 KB of shared memory and 44 warp slots are left
+// there, i.e. room for exactly one block of 128 threads x 32 registers.  Built that way (ADSB_CHAIN_SMALL)
+// the chain needs no SMs of its own; otherwise k_fused leaves it some (api.cu: kResolveSMs).
+#ifndef ADSB_CHAIN_SMALL
+#define ADSB_CHAIN_SMALL 1
+#endif
+#if ADSB_CHAIN_SMALL
+#define ADSB_CHAIN_BOUNDS __launch_bounds__(128, 16)
+constexpr int kChainThreads = 128;
+constexpr int kScanThreads = 128;
+#else
+#define ADSB_CHAIN_BOUNDS
+constexpr int kChainThreads = 256;
 constexpr int kScanThreads = 1024;
+#endif
+constexpr int kChainBlocks = 296 * 256 / kChainThreads;
 
 __device__ __forceinline__ unsigned long long job_count(const Counters *ctr, unsigned long long cap)
 {
@@ -35,7 +52,7 @@ __device__ __forceinline__ unsigned long long job_count(const Counters *ctr, uns
 	return n < cap ? n : cap;
 }
 
-__global__ void k_hist(const CandRec *__restrict__ c, const Counters *ctr, unsigned long long cap, long long n0,
+__global__ void ADSB_CHAIN_BOUNDS k_hist(const CandRec *__restrict__ c, const Counters *ctr, unsigned long long cap, long long n0,
                        unsigned int *cnt)
 {
 	const unsigned long long m = job_count(ctr, cap);
@@ -88,7 +105,7 @@ __device__ __forceinline__ unsigned long long block_scan_incl(unsigned long long
 		wsum[w] = x;
 	__syncthreads();
 	if (w == 0) {
-		T sv = wsum[lane];
+		T sv = lane < kScanThreads / 32 ? wsum[lane] : 0ull;
 #pragma unroll
 		for (int d = 1; d < 32; d <<= 1) {
 			const T y = __shfl_up_sync(0xFFFFFFFFu, sv, d);
@@ -210,7 +227,7 @@ __device__ __forceinline__ void repack(CandRec &o, const CandRec &c)
 // cursors and end at zero, ready for the next job), then every candidate counts the keys of its bucket
 // that are smaller than its own - a handful - and goes straight to its final place.  No two candidates
 // share an offset.
-__global__ void k_scatter_keys(const CandRec *__restrict__ c, const Counters *ctr, unsigned long long cap, long long n0,
+__global__ void ADSB_CHAIN_BOUNDS k_scatter_keys(const CandRec *__restrict__ c, const Counters *ctr, unsigned long long cap, long long n0,
                                const unsigned int *__restrict__ off, unsigned int *cnt, unsigned int *__restrict__ keys)
 {
 	const unsigned long long m = job_count(ctr, cap);
@@ -222,7 +239,7 @@ __global__ void k_scatter_keys(const CandRec *__restrict__ c, const Counters *ct
 	}
 }
 
-__global__ void k_rank_move(const CandRec *__restrict__ c, const Counters *ctr, unsigned long long cap, long long n0,
+__global__ void ADSB_CHAIN_BOUNDS k_rank_move(const CandRec *__restrict__ c, const Counters *ctr, unsigned long long cap, long long n0,
                             const unsigned int *__restrict__ off, const unsigned int *__restrict__ keys,
                             CandRec *__restrict__ sorted)
 {
@@ -254,7 +271,7 @@ __global__ void k_snapshot(const ResolveState *st, SlotResolve *slot)
 }
 
 // Greedy acceptance.  Thread i walks the segment that starts at candidate i (if one does).
-__global__ void k_greedy(const CandRec *__restrict__ sorted, const unsigned int *__restrict__ off, int nb,
+__global__ void ADSB_CHAIN_BOUNDS k_greedy(const CandRec *__restrict__ sorted, const unsigned int *__restrict__ off, int nb,
                          unsigned char *__restrict__ accept, ResolveState *st, const SlotResolve *slot)
 {
 	const unsigned long long m = off[nb];
@@ -288,7 +305,7 @@ __global__ void k_greedy(const CandRec *__restrict__ sorted, const unsigned int 
 	}
 }
 
-__global__ void k_bucket_stats(const CandRec *__restrict__ sorted, const unsigned char *__restrict__ accept,
+__global__ void ADSB_CHAIN_BOUNDS k_bucket_stats(const CandRec *__restrict__ sorted, const unsigned char *__restrict__ accept,
                                const unsigned int *__restrict__ off, int nb, unsigned int *bacc, unsigned int *bdrift)
 {
 	for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
@@ -305,7 +322,7 @@ __global__ void k_bucket_stats(const CandRec *__restrict__ sorted, const unsigne
 
 // Writes the accepted frames, in offset order, as the API hands them out.  ts counts the loop
 // iterations of deqframe (demod.c:86, :99): every accepted frame before this one saved skip-1 of them.
-__global__ void k_compact(const CandRec *__restrict__ sorted, const unsigned char *__restrict__ accept,
+__global__ void ADSB_CHAIN_BOUNDS k_compact(const CandRec *__restrict__ sorted, const unsigned char *__restrict__ accept,
                           const unsigned int *__restrict__ off, int nb, const unsigned int *__restrict__ bacc_x,
                           const unsigned int *__restrict__ bdrift_x, FrameRec *__restrict__ out,
                           unsigned long long *__restrict__ keys_out, unsigned long long out_cap, ResolveState *st,
@@ -362,7 +379,7 @@ __global__ void k_compact(const CandRec *__restrict__ sorted, const unsigned cha
 // Try statistics (valid.c:46, :68 as the sequential scan sees them) against the accepted frames
 // of this job, which are still on the device.  The bucket prefix counts of the compaction tell
 // where the frames near a try sit, so no search is needed.
-__global__ void k_count_tries_frames(const unsigned long long *__restrict__ tries,
+__global__ void ADSB_CHAIN_BOUNDS k_count_tries_frames(const unsigned long long *__restrict__ tries,
                                      const unsigned long long *__restrict__ n_tries_ptr, unsigned long long cap,
                                      const FrameRec *__restrict__ frames, const SlotResolve *slot,
                                      unsigned long long frames_cap, const unsigned int *__restrict__ bacc_x,
@@ -433,10 +450,10 @@ cudaError_t launch_sort(const ResolveBuffers &rb, const CandRec *cands, const Co
 {
 	const int nb = resolve_bucket_count(n0, n1);
 	// (rb.cnt is all zero here: zeroed when it was allocated, counted back down to zero by every job)
-	k_hist<<<296, 256, 0, st>>>(cands, ctr, cap, n0, rb.cnt);
+	k_hist<<<kChainBlocks, kChainThreads, 0, st>>>(cands, ctr, cap, n0, rb.cnt);
 	launch_scan<false>(rb.cnt, nullptr, rb.off, nullptr, nb, rb.part, st);
-	k_scatter_keys<<<296, 256, 0, st>>>(cands, ctr, cap, n0, rb.off, rb.cnt, rb.keys);
-	k_rank_move<<<296, 256, 0, st>>>(cands, ctr, cap, n0, rb.off, rb.keys, rb.sorted);
+	k_scatter_keys<<<kChainBlocks, kChainThreads, 0, st>>>(cands, ctr, cap, n0, rb.off, rb.cnt, rb.keys);
+	k_rank_move<<<kChainBlocks, kChainThreads, 0, st>>>(cands, ctr, cap, n0, rb.off, rb.keys, rb.sorted);
 	return cudaGetLastError();
 }
 
@@ -449,7 +466,7 @@ cudaError_t launch_resolve(const ResolveBuffers &rb, const CandRec *cands, const
 	cudaError_t e = launch_sort(rb, cands, ctr, cap, n0, n1, st);
 	if (e != cudaSuccess) return e;
 	k_snapshot<<<1, 1, 0, st>>>(state, slot);
-	k_greedy<<<296, 256, 0, st>>>(rb.sorted, rb.off, nb, rb.accept, state, slot);
+	k_greedy<<<kChainBlocks, kChainThreads, 0, st>>>(rb.sorted, rb.off, nb, rb.accept, state, slot);
 	k_bucket_stats<<<(nb + 127) / 128, 128, 0, st>>>(rb.sorted, rb.accept, rb.off, nb, rb.bacc, rb.bdrift);
 	launch_scan<true>(rb.bacc, rb.bdrift, rb.bacc_x, rb.bdrift_x, nb, rb.part, st);
 	k_compact<<<(nb + 127) / 128, 128, 0, st>>>(rb.sorted, rb.accept, rb.off, nb, rb.bacc_x, rb.bdrift_x, out, keys_out,
@@ -480,7 +497,7 @@ cudaError_t launch_count_tries_frames(const unsigned long long *tries, const uns
                                       cudaStream_t st)
 {
 	const int nb = n1 > n0 ? resolve_bucket_count(n0, n1) : 0;
-	k_count_tries_frames<<<592, 256, 0, st>>>(tries, n_tries_ptr, cap, frames, slot, frames_cap, rb.bacc_x, n0, nb,
+	k_count_tries_frames<<<2 * kChainBlocks, kChainThreads, 0, st>>>(tries, n_tries_ptr, cap, frames, slot, frames_cap, rb.bacc_x, n0, nb,
 	                                         scan_end, pend_out, n_pend_out, pend_cap, stt);
 	return cudaGetLastError();
 }

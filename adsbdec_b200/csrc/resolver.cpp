@@ -16,14 +16,14 @@ void Resolver::scan_keys_to(uint64_t cutoff)
 	const unsigned long long *k = kin_;
 	const size_t n = fin_n_, i0 = fin_i_;
 	size_t i = i0;
-	if (i < n && (k[i] >> 1) < cutoff) {
-		const auto below = [cutoff](unsigned long long x, uint64_t) { return (x >> 1) < cutoff; };
-		const size_t w = std::min(n, i + 64);
-		size_t e = (size_t)(std::lower_bound(k + i, k + w, cutoff, below) - k);
-		if (e == w && w < n)
-			e = (size_t)(std::lower_bound(k + w, k + n, cutoff, below) - k);
-		i = e;
-	}
+	// a call covers ~40 k offsets - a dozen frames of a dense capture: walk them (one predictable branch each);
+	// search only what a long walk has not reached
+	const unsigned long long kc = (unsigned long long)cutoff << 1;  // k < kc  <=>  start < cutoff
+	const size_t w = std::min(n, i + 48);
+	while (i < w && k[i] < kc)
+		i++;
+	if (i == w && i < n && k[i] < kc)
+		i = (size_t)(std::lower_bound(k + i, k + n, kc) - k);
 	if (i > i0)
 		pos = (k[i - 1] >> 1) + ((k[i - 1] & 1ull) ? kSkipLong : kSkipShort);
 	fin_i_ = i;
