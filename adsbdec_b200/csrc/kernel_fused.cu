@@ -455,7 +455,7 @@ constexpr int GATE_STAGE = 512;  // tries staged per warp (2 KB), as 32-bit offs
 #define ADSB_GATE_MINB 4
 #endif
 #ifndef ADSB_SLICE_MINB
-#define ADSB_SLICE_MINB 6
+#define ADSB_SLICE_MINB 5
 #endif
 __global__ void __launch_bounds__(256, ADSB_GATE_MINB) k_gate(const GateParams p)
 {
@@ -696,10 +696,20 @@ __global__ void __launch_bounds__(256, ADSB_SLICE_MINB) k_slice(const SliceParam
 	};
 
 	// whole warps iterate together (the ballot below needs every lane)
+	// (the entry of the NEXT pass is requested a pass ahead: list entry -> frame bits -> syndrome is a chain of
+	// dependent trips to the L2, and this kernel waits for them ten cycles of eleven)
+	unsigned long long e_next = 0;
+	{
+		const uint32_t t = blockIdx.x * 256u + threadIdx.x;
+		if (t < count)
+			e_next = tries[t];
+	}
 	for (uint32_t t0 = blockIdx.x * 256u + (threadIdx.x & ~31u); t0 < count; t0 += stride) {
 		const uint32_t t = t0 + lane;
 		const bool have = t < count;
-		const long long n_abs = have ? (long long)(tries[t] & kTryMask) : p.j0;
+		const long long n_abs = have ? (long long)(e_next & kTryMask) : p.j0;
+		if (t + stride < count && t + stride > t)
+			e_next = tries[t + stride];
 		// frame bit b sits at n + 80 + 10 b; the first one tells 10001 / 10010 (112 bits) from 01011 (56 bits,
 		// the tail of the syndrome table: rows 14..27)
 		const uint32_t pb = (uint32_t)(n_abs - p.j0) + 80u;
