@@ -90,6 +90,8 @@ __global__ void k_reset_counters(Counters *c)
 
 __global__ void k_zero_u64(unsigned long long *p) { *p = 0; }
 
+__global__ void k_mark_cands(Counters *c) { c->cand_mark = c->n_cand; }
+
 // Builds the span table of one fused launch on the device and marks where its tries will begin.
 // Span i covers envelope samples [j0 + i*per, j0 + (i+1)*per) = bit words [i*per/32, (i+1)*per/32), cut off at
 // `words` (per is a multiple of 224: FIR phase 0 and a bit-word boundary at every span start).
@@ -100,6 +102,8 @@ __global__ void k_make_spans(FusedSpan *sp, int *ticket, Counters *ctr, int n_sp
 	if (i == 0) {
 		*ticket = 0;
 		ctr->try_mark = ctr->n_try;
+		ctr->cand_mark = ctr->n_cand;
+		ctr->n_ap = 0;
 	}
 	if (i >= n_sp)
 		return;
@@ -251,6 +255,11 @@ struct adsbdec_b200 {
 	cudaEvent_t ev_pk[2] = {nullptr, nullptr};
 	int pk_i = 0;
 	int fix_level = 0;
+	// EXTENSION, off by default: DF4/5/20/21 accepted against the addresses announced so far
+	bool ap_mode = false;
+	unsigned long long *d_first_seen = nullptr;     // [2^24] by ICAO address: offset of its first announcement
+	unsigned long long *d_aptries[kSlots] = {};     // DF4/5/20/21 tries of the fused range being worked on
+	unsigned long long ap_cap[kSlots] = {};
 
 	// parity taps of the fused kernel (adsbdec_b200_debug_fused)
 	float *dbg_amp = nullptr;
@@ -297,6 +306,13 @@ int alloc_slot_outputs(adsbdec_b200 *h, int s, unsigned long long cand_cap, unsi
 		h->try_cap[s] = 0;
 		CU(cudaMalloc(&h->d_tries[s], try_cap * sizeof(unsigned long long)));
 		h->try_cap[s] = try_cap;
+		if (h->ap_mode) {  // four bit patterns pass that gate where three pass the reference's
+			if (h->d_aptries[s]) cudaFree(h->d_aptries[s]);
+			h->d_aptries[s] = nullptr;
+			h->ap_cap[s] = 0;
+			CU(cudaMalloc(&h->d_aptries[s], 2 * try_cap * sizeof(unsigned long long)));
+			h->ap_cap[s] = 2 * try_cap;
+		}
 	}
 	return 0;
 }
@@ -356,9 +372,22 @@ int launch_generic(adsbdec_b200 *h, int s, const Job &j, int64_t n0, int64_t n1)
 	for (int64_t c0 = n0; c0 < n1; c0 += kAmpChunk) {
 		const int64_t cnt = std::min(kAmpChunk, n1 - c0);
 		CU(launch_envelope_generic(j.buf, j.u0, j.origin, c0, cnt + kLookahead, h->d_amp, h->st));
+		if (h->ap_mode) {
+			k_mark_cands<<<1, 1, 0, h->st>>>(h->d_ctr[s]);
+			CU(cudaGetLastError());
+		}
 		CU(launch_scan_generic(h->d_amp, c0, c0, cnt, h->cfg.accept_df18, h->cfg.collect_stats, h->d_cands[s],
-		                       h->cand_cap[s], h->d_tries[s], h->try_cap[s], h->d_ctr[s], h->d_fix, h->fix_level, h->st));
+		                       h->cand_cap[s], h->d_tries[s], h->try_cap[s], h->d_ctr[s], h->d_fix, h->fix_level,
+		                       nullptr, h->st));
 		h->launches += 2;
+		if (h->ap_mode) {
+			// extension: the chunk's clean DF11/17/18 candidates announce their addresses, then a second pass
+			// takes the DF4/5/20/21 frames whose address has been announced at an earlier offset
+			CU(launch_note_addresses(h->d_cands[s], h->cand_cap[s], h->d_ctr[s], h->d_first_seen, h->st));
+			CU(launch_scan_generic(h->d_amp, c0, c0, cnt, h->cfg.accept_df18, 0, h->d_cands[s], h->cand_cap[s],
+			                       h->d_tries[s], h->try_cap[s], h->d_ctr[s], nullptr, 0, h->d_first_seen, h->st));
+			h->launches += 3;
+		}
 	}
 	return 0;
 }
@@ -484,6 +513,26 @@ int launch_fused_range(adsbdec_b200 *h, int s, const Job &j, int64_t n0, int64_t
 	CU(launch_slice(sl, h->st));
 	CU(cudaEventRecord(h->ev_fc[s], h->st));
 	h->launches += 4;
+	if (h->ap_mode) {
+		// extension: addresses announced by this range's clean candidates, then the DF4/5/20/21 tries of the
+		// range against the table (same bit arrays, a list of their own)
+		CU(launch_note_addresses(h->d_cands[s], h->cand_cap[s], h->d_ctr[s], h->d_first_seen, h->st));
+		GateParams ga = g;
+		ga.tries = h->d_aptries[s];
+		ga.try_cap = h->ap_cap[s];
+		CU(launch_gate_ap(ga, h->st));
+		AddressParityParams ap;
+		ap.bits_b = bb;
+		ap.j0 = j0;
+		ap.ap_tries = h->d_aptries[s];
+		ap.ap_cap = h->ap_cap[s];
+		ap.cands = h->d_cands[s];
+		ap.cand_cap = h->cand_cap[s];
+		ap.ctr = h->d_ctr[s];
+		ap.first_seen = h->d_first_seen;
+		CU(launch_slice_ap(ap, h->st));
+		h->launches += 3;
+	}
 	h->fused_launches += 1;
 	h->fused_samples += (uint64_t)(2 * (n1 - n0));
 	return 0;
@@ -569,7 +618,8 @@ void emit_new_frames(adsbdec_b200 *h)
 		const adsbdec_b200_frame_t &f = h->frames[h->emitted];
 		if (h->emitted >= h->counted) {
 			const int df = f.bytes[0] >> 3;
-			h->stat_ok[df == 11 ? 0 : df == 17 ? 1 : 2]++;  // valid.c:53, :75
+			if (ok_class(df) >= 0)
+				h->stat_ok[ok_class(df)]++;  // valid.c:53, :75
 			h->counted = h->emitted + 1;
 		}
 		if (h->sink)
@@ -665,7 +715,7 @@ int complete_job(adsbdec_b200 *h, int s)
 			if (j.used_fused && c.wide) {
 				// samples beyond 12 bits: exact generic kernels
 				force_generic = true;
-			} else if (!(c.overflow & 3u)) {
+			} else if (!(c.overflow & 7u)) {
 				break;
 			}
 			if (attempt >= 8)
@@ -677,9 +727,9 @@ int complete_job(adsbdec_b200 *h, int s)
 			if (j.resolve)
 				CU(launch_set_state(h->d_state, h->h_slot[s]->span0_start, h->h_slot[s]->span0_end,
 				                    h->h_slot[s]->drift0, h->st_res));
-			if (c.overflow & 3u)
+			if (c.overflow & 7u)  // bit 2: the list of address/parity tries, sized with the try list
 				RC(alloc_slot_outputs(h, s, (c.overflow & 1u) ? h->cand_cap[s] * 4 : h->cand_cap[s],
-				                      (c.overflow & 2u) ? h->try_cap[s] * 4 : h->try_cap[s]));
+				                      (c.overflow & 6u) ? h->try_cap[s] * 4 : h->try_cap[s]));
 			RC(enqueue_job(h, s, force_generic));
 			for (int t = next_of(s); t != s; t = next_of(t))  // the newer jobs, oldest first
 				if (h->job[t].active)
@@ -942,6 +992,7 @@ int adsbdec_b200_open(const adsbdec_b200_config_t *cfg, adsbdec_b200_t **out)
 		    cfg->reserved[0] ? cfg->reserved[0] : std::min<unsigned long long>(1ull << 18, std::max<unsigned long long>(4096, (unsigned long long)h->batch / 128));
 		const unsigned long long tc =
 		    cfg->reserved[1] ? cfg->reserved[1] : std::min<unsigned long long>(1ull << 20, std::max<unsigned long long>(16384, (unsigned long long)h->batch / 32));
+		h->ap_mode = (cfg->reserved[3] & 0x100u) != 0;  // (sizes a list of its own below)
 		for (int s = 0; s < kSlots && !rc; s++)
 			rc = alloc_slot_outputs(h, s, cc, tc);
 		if (rc) break;
@@ -960,11 +1011,19 @@ int adsbdec_b200_open(const adsbdec_b200_config_t *cfg, adsbdec_b200_t **out)
 			h->fused_ctas = per_sm * sms;
 		}
 		// reserved[3]: opt-in error repair (repair.h) - 0 = the reference's behaviour
-		if (cfg->reserved[3] > 2) {
-			rc = fail(ADSB_B200_EINVAL, "repair level must be 0, 1 or 2");
+		if ((cfg->reserved[3] & 0xFFu) > 2 || (cfg->reserved[3] & ~0x1FFull)) {
+			rc = fail(ADSB_B200_EINVAL, "reserved[3]: repair level 0, 1 or 2, plus 0x100 for address/parity frames");
 			break;
 		}
-		h->fix_level = (int)cfg->reserved[3];
+		h->fix_level = (int)(cfg->reserved[3] & 0xFFu);
+		h->ap_mode = (cfg->reserved[3] & 0x100u) != 0;
+		if (h->ap_mode) {
+			if (cudaMalloc(&h->d_first_seen, sizeof(unsigned long long) << 24) != cudaSuccess ||
+			    cudaMemset(h->d_first_seen, 0xFF, sizeof(unsigned long long) << 24) != cudaSuccess) {
+				rc = fail(ADSB_B200_ECUDA, "address table: %s", cudaGetErrorString(cudaGetLastError()));
+				break;
+			}
+		}
 		if (h->fix_level > 0) {
 			std::vector<unsigned long long> tab(kFixSlots);
 			fix_build_table(tab.data());
@@ -1047,6 +1106,9 @@ void adsbdec_b200_close(adsbdec_b200_t *h)
 	if (h->st_d2h) cudaStreamDestroy(h->st_d2h);
 	if (h->st_res) cudaStreamDestroy(h->st_res);
 	if (h->st_stat) cudaStreamDestroy(h->st_stat);
+	if (h->d_first_seen) cudaFree(h->d_first_seen);
+	for (int s = 0; s < kSlots; s++)
+		if (h->d_aptries[s]) cudaFree(h->d_aptries[s]);
 	if (h->frames) cudaFreeHost(h->frames);
 	if (h->fkeys) cudaFreeHost(h->fkeys);
 	delete h->res;
@@ -1088,6 +1150,8 @@ int adsbdec_b200_reset(adsbdec_b200_t *h, uint64_t start_sample)
 	CU(cudaMemset(h->d_state, 0, sizeof(ResolveState)));
 	for (int s = 0; s < kSlots; s++)
 		CU(cudaMemset(h->d_slot[s], 0, sizeof(SlotResolve)));
+	if (h->d_first_seen)  // a new stream: nothing has been announced
+		CU(cudaMemset(h->d_first_seen, 0xFF, sizeof(unsigned long long) << 24));
 	return 0;
 }
 
@@ -1372,7 +1436,8 @@ int adsbdec_b200_finish(adsbdec_b200_t *h)
 	h->n_vis = h->res->finish_keys(h->fkeys, h->n_vis, h->n_total);
 	for (size_t i = h->n_vis; i < h->n_total; i++) {
 		const int df = h->frames[i].bytes[0] >> 3;
-		h->stat_ok[df == 11 ? 0 : df == 17 ? 1 : 2]--;
+		if (ok_class(df) >= 0)
+			h->stat_ok[ok_class(df)]--;
 	}
 	h->n_total = h->n_vis;
 	h->counted = h->n_vis;
@@ -1505,7 +1570,8 @@ int adsbdec_b200_stats(adsbdec_b200_t *h, uint32_t try_[3], uint32_t ok[3])
 	uint32_t pend[3] = {0, 0, 0};  // frames the GPU has accepted but the deqframe call schedule has not reached
 	for (size_t k = h->n_vis; k < h->n_total; k++) {
 		const int df = h->frames[k].bytes[0] >> 3;
-		pend[df == 11 ? 0 : df == 17 ? 1 : 2]++;
+		if (ok_class(df) >= 0)
+			pend[ok_class(df)]++;
 	}
 	for (int i = 0; i < 3; i++) {
 		if (try_) try_[i] = h->h_stats->stat_try[i];
@@ -1620,6 +1686,8 @@ int64_t adsbdec_b200_chunk_candidates(adsbdec_b200_t *h, const void *dev_samples
 {
 	if (!h || !dev_samples || (!out && cap))
 		return fail(ADSB_B200_EINVAL, "null argument");
+	if (h->ap_mode)  // a chunk does not know which addresses earlier chunks announced
+		return fail(ADSB_B200_EINVAL, "address/parity frames (extension) are a stream-mode feature");
 	if (own_end < own_begin || (own_end + kLookahead) * 2 > n_samples)
 		return fail(ADSB_B200_EINVAL, "owned range needs 1200 envelope samples of look-ahead in the chunk");
 	if (((uintptr_t)dev_samples % 16) != 0 || start_sample % 4)

@@ -9,7 +9,8 @@
 // block on stderr at exit (valid.c:84-101); a file that cannot be opened prints stats and exits 0
 // (air.c:225-228).  Deliberately NOT kept: stdout beast output truncated by strlen() (output.c:331
 // - we write the full packet) and the frames the reference loses in its EOF race (output.c:287).
-// Extra: -D n selects the CUDA device, -G forces the generic kernels, -R 1|2 switches on the error
+// Extra: -D n selects the CUDA device, -G forces the generic kernels, -P accepts address/parity frames
+// (DF4/5/20/21), -R 1|2 switches on the error
 // repair extension (repair.h; the reference has none, so the default output is the reference's).
 #include <arpa/inet.h>
 #include <netdb.h>
@@ -44,6 +45,7 @@ void usage()
 	printf("\t-l addr[:port] : listen on addr:port and send output via TCP to the first client (default port : 30002)\n");
 	printf("\t-D n : CUDA device ordinal\n");
 	printf("\t-R 1|2 : extension, not in adsbdec : repair 1 (2) flipped bits by CRC syndrome\n");
+	printf("\t-P : extension, not in adsbdec : also DF4/5/20/21 of aircraft announced earlier (address/parity)\n");
 }
 
 // -s: connect to a server; -l: bind, wait for ONE client ("listening" / "connected" on stderr), then
@@ -149,7 +151,7 @@ int main(int argc, char **argv)
 	adsbdec_b200_config_t cfg;
 	adsbdec_b200_default_config(&cfg);
 	int c;
-	while ((c = getopt(argc, argv, "cf:s:l:g:aembD:GR:")) != EOF) {
+	while ((c = getopt(argc, argv, "cf:s:l:g:aembD:GR:P")) != EOF) {
 		switch (c) {
 		case 'f': filename = optarg; break;
 		case 's': addr = optarg; listener = false; break;  // main.c: outmode 1
@@ -160,7 +162,8 @@ int main(int argc, char **argv)
 		case 'b': g_format = 2; break;
 		case 'D': cfg.device = atoi(optarg); break;
 		case 'G': cfg.kernel = 1; break;
-		case 'R': cfg.reserved[3] = (uint64_t)atoi(optarg); break;
+		case 'R': cfg.reserved[3] = (cfg.reserved[3] & 0x100u) | (uint64_t)(atoi(optarg) & 0xFF); break;
+		case 'P': cfg.reserved[3] |= 0x100u; break;
 		default:  // -c, -e and anything unknown
 			usage();
 			return 1;

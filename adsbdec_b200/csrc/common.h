@@ -16,6 +16,9 @@ constexpr int kSkipLong = 80 + 80 * 14;
 
 // DF classes in print_stats order (valid.c:88-97)
 enum : uint32_t { kClsDF11 = 0, kClsDF17 = 1, kClsDF18 = 2 };
+// Index of a frame's DF in the Ok counters (valid.c:53, :75), -1 for the frames of the address/parity
+// extension (DF4/5/20/21), which the reference's statistics do not know.
+__host__ __device__ inline int ok_class(int df) { return df == 11 ? 0 : df == 17 ? 1 : df == 18 ? 2 : -1; }
 
 // One CRC-valid candidate as written by the kernels (32 bytes).
 struct alignas(16) CandRec {
@@ -51,7 +54,9 @@ struct Counters {
 	unsigned int overflow;          // bit0: candidate list full, bit1: try list full
 	unsigned int wide;              // a sample outside 0..4095 was seen by the fused kernel
 	unsigned long long try_mark;    // n_try when the current fused range began: k_slice starts here
-	unsigned int pad_[8];
+	unsigned long long cand_mark;   // n_cand when the current range began (address/parity extension)
+	unsigned long long n_ap;        // entries in the range's list of address/parity tries (extension)
+	unsigned int pad_[4];
 };
 static_assert(sizeof(Counters) == 64, "Counters layout");
 

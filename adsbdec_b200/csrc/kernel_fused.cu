@@ -457,6 +457,9 @@ constexpr int GATE_STAGE = 512;  // tries staged per warp (2 KB), as 32-bit offs
 #ifndef ADSB_SLICE_MINB
 #define ADSB_SLICE_MINB 5
 #endif
+// AP (address/parity extension, off by default): the same kernel lists the offsets whose first five bits read
+// 0010x / 1010x (DF4, DF5, DF20, DF21) in a list of their own (counter Counters::n_ap, overflow bit 2).
+template <bool AP>
 __global__ void __launch_bounds__(256, ADSB_GATE_MINB) k_gate(const GateParams p)
 {
 	//@region gate
@@ -479,7 +482,7 @@ __global__ void __launch_bounds__(256, ADSB_GATE_MINB) k_gate(const GateParams p
 	const uint4 *__restrict__ const bb = reinterpret_cast<const uint4 *>(p.bits_b);
 	const unsigned int *__restrict__ const bq1 = p.bits_q;
 	unsigned long long *const tries = p.tries;
-	unsigned long long *const n_try = &p.ctr->n_try;
+	unsigned long long *const n_try = AP ? &p.ctr->n_ap : &p.ctr->n_try;
 	const unsigned long long try_cap = p.try_cap;
 	const long long j0 = p.j0;
 	uint32_t staged = 0;  // entries in `stage`, warp-uniform
@@ -551,11 +554,15 @@ __global__ void __launch_bounds__(256, ADSB_GATE_MINB) k_gate(const GateParams p
 			const uint32_t x5 = __funnelshift_l(b4, b3, 4);   // 100 = 96 + 4
 			const uint32_t x4 = __funnelshift_l(b4, b3, 14);  // 110 = 96 + 14
 			const uint32_t x3 = __funnelshift_l(b4, b3, 24);  // 120 = 96 + 24
-			const uint32_t c0 = pre & ~x5;
-			const uint32_t lng = c0 & x7 & ~x6;
-			any[k] = (lng & ~x4 & x3)                  // 10001
-			         | (lng & x4 & ~x3 & df18_mask)    // 10010 (only with -a, demod.c:59)
-			         | (c0 & ~x7 & x6 & x4 & x3);      // 01011
+			if (AP) {
+				any[k] = pre & x5 & ~x6 & ~x4;           // 0010x, 1010x (extension)
+			} else {
+				const uint32_t c0 = pre & ~x5;
+				const uint32_t lng = c0 & x7 & ~x6;
+				any[k] = (lng & ~x4 & x3)                  // 10001
+				         | (lng & x4 & ~x3 & df18_mask)    // 10010 (only with -a, demod.c:59)
+				         | (c0 & ~x7 & x6 & x4 & x3);      // 01011
+			}
 			c += (uint32_t)__popc(any[k]);
 		}
 		// Where each lane's tries go in the stage: counts stay below 8 almost always, so the exclusive prefix
@@ -618,7 +625,7 @@ __global__ void __launch_bounds__(256, ADSB_GATE_MINB) k_gate(const GateParams p
 	if (staged)
 		flush();
 	if (ovf)
-		atomicOr(&p.ctr->overflow, 2u);
+		atomicOr(&p.ctr->overflow, AP ? 4u : 2u);
 }
 
 // ============================================================================================
@@ -770,6 +777,75 @@ __global__ void __launch_bounds__(256, ADSB_SLICE_MINB) k_slice(const SliceParam
 		atomicOr(&p.ctr->overflow, 1u);
 }
 
+// ============================================================================================
+// EXTENSION (off by default, not in the reference): address/parity frames
+// ============================================================================================
+// A clean DF11 / DF17 / DF18 candidate announces its AA field (frame bits 8..31) at its offset.
+__global__ void k_note_addresses(const CandRec *__restrict__ cands, unsigned long long cand_cap, const Counters *ctr,
+                                 unsigned long long *first_seen)
+{
+	unsigned long long last = ctr->n_cand;
+	if (last > cand_cap)
+		last = cand_cap;
+	for (unsigned long long i = ctr->cand_mark + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < last;
+	     i += (unsigned long long)gridDim.x * blockDim.x) {
+		const CandRec c = cands[i];
+		uint32_t aa;
+		if (c.len & kCandNibbleWords) {
+			uint32_t w[2];
+			memcpy(w, c.bytes, 8);
+			if (w[0] >> 28)  // repaired by the other extension: not a clean announcement
+				continue;
+			aa = ((w[0] & 0xFFFFFu) << 4) | ((w[1] >> 24) & 0xFu);
+		} else {
+			if (c.bytes[15])
+				continue;
+			aa = (uint32_t)c.bytes[1] << 16 | (uint32_t)c.bytes[2] << 8 | c.bytes[3];
+		}
+		atomicMin(&first_seen[aa], (unsigned long long)c.n);
+	}
+}
+
+// One lane per DF4/5/20/21 try: the syndrome of the frame bits IS the address the sender overlaid on the parity
+// field; the frame is a candidate when that address was announced at an earlier offset.
+__global__ void __launch_bounds__(256) k_slice_ap(const AddressParityParams p)
+{
+	__shared__ uint32_t lut[28 * 16];
+	for (int e = threadIdx.x; e < 28 * 16; e += 256)
+		lut[e] = g_lut[e];
+	__syncthreads();
+	unsigned long long count = p.ctr->n_ap;
+	if (count > p.ap_cap)
+		count = p.ap_cap;
+	bool ovf = false;
+	for (unsigned long long t = blockIdx.x * 256ull + threadIdx.x; t < count; t += (unsigned long long)gridDim.x * 256ull) {
+		const long long n_abs = (long long)p.ap_tries[t];
+		const uint32_t pb = (uint32_t)(n_abs - p.j0) + 80u;
+		const bool is_long = ((p.bits_b[pb >> 5] << (pb & 31u)) >> 31) != 0u;
+		const char *lutp = reinterpret_cast<const char *>(lut) + (is_long ? 0 : 14 * 64);
+		uint32_t acc = 0, w0, w1, w2 = 0, w3 = 0;
+		w0 = slice28(p.bits_b, pb, lutp, acc);
+		w1 = slice28(p.bits_b, pb + 280u, lutp + 7 * 64, acc);
+		if (is_long) {
+			w2 = slice28(p.bits_b, pb + 560u, lutp + 14 * 64, acc);
+			w3 = slice28(p.bits_b, pb + 840u, lutp + 21 * 64, acc);
+		}
+		if (acc == 0u || p.first_seen[acc] >= (unsigned long long)n_abs)
+			continue;
+		const unsigned long long k = atomicAdd(&p.ctr->n_cand, 1ull);
+		if (k >= p.cand_cap) {
+			ovf = true;
+			continue;
+		}
+		uint4 *rec = reinterpret_cast<uint4 *>(p.cands + k);
+		rec[0] = make_uint4((uint32_t)n_abs, (uint32_t)((unsigned long long)n_abs >> 32), 0u,
+		                    (is_long ? 14u : 7u) | kCandNibbleWords);
+		rec[1] = make_uint4(w0, w1, w2, w3);
+	}
+	if (ovf)
+		atomicOr(&p.ctr->overflow, 1u);
+}
+
 int fused_block_outputs() { return S; }
 int fused_span_quantum() { return QUANTUM; }
 int fused_threads() { return NT; }
@@ -825,7 +901,31 @@ cudaError_t launch_gate(const GateParams &p, cudaStream_t st)
 	const long long words = ((p.n1 - 1 - p.j0) >> 5) - ((p.n0 - p.j0) >> 5) + 1;
 	const long long want = (words + 1023) / 1024;  // one step of 8 warps: 128 words each
 	const long long most = 148 * ADSB_GATE_MINB;
-	k_gate<<<(unsigned)(want < most ? want : most), 256, 0, st>>>(p);
+	k_gate<false><<<(unsigned)(want < most ? want : most), 256, 0, st>>>(p);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_gate_ap(const GateParams &p, cudaStream_t st)
+{
+	if (p.n1 <= p.n0)
+		return cudaSuccess;
+	const long long words = ((p.n1 - 1 - p.j0) >> 5) - ((p.n0 - p.j0) >> 5) + 1;
+	const long long want = (words + 1023) / 1024;
+	const long long most = 148 * ADSB_GATE_MINB;
+	k_gate<true><<<(unsigned)(want < most ? want : most), 256, 0, st>>>(p);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_note_addresses(const CandRec *cands, unsigned long long cand_cap, const Counters *ctr,
+                                  unsigned long long *first_seen, cudaStream_t st)
+{
+	k_note_addresses<<<148, 256, 0, st>>>(cands, cand_cap, ctr, first_seen);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_slice_ap(const AddressParityParams &p, cudaStream_t st)
+{
+	k_slice_ap<<<148 * 4, 256, 0, st>>>(p);
 	return cudaGetLastError();
 }
 

@@ -23,7 +23,7 @@ cudaError_t launch_scan_generic(const float *amp, long long j_amp0, long long n0
                                 int accept_df18, int want_tries, CandRec *cands,
                                 unsigned long long cand_cap, unsigned long long *tries,
                                 unsigned long long try_cap, Counters *ctr, const unsigned long long *fix_tab,
-                                int fix_level, cudaStream_t st);
+                                int fix_level, const unsigned long long *first_seen, cudaStream_t st);
 
 // Packed 12-bit samples (libairspy layout, 8 samples per 12 bytes) -> u16 samples.  n_samples % 8 == 0,
 // `packed` 4-byte and `out` 8-byte aligned.
@@ -112,6 +112,22 @@ struct GateParams {
 	unsigned long long *tries;
 	unsigned long long try_cap;
 	Counters *ctr;
+	// address/parity extension (launch_gate_ap): the list above is the one of DF4/5/20/21 tries then
+};
+
+// EXTENSION (off by default): DF4 / DF5 / DF20 / DF21 carry CRC ^ ICAO address in their parity field.
+// `first_seen[address]` (2^24 entries) is the smallest offset at which a clean DF11/17/18 candidate announces the
+// address (~0: never); a frame of the four classes is a candidate when its syndrome is an address announced at
+// an earlier offset.
+struct AddressParityParams {
+	const unsigned int *bits_b;
+	long long j0;
+	const unsigned long long *ap_tries;   // entries [0, ctr->n_ap)
+	unsigned long long ap_cap;
+	CandRec *cands;
+	unsigned long long cand_cap;
+	Counters *ctr;
+	unsigned long long *first_seen;
 };
 
 struct SliceParams {
@@ -135,6 +151,12 @@ size_t fused_smem_bytes();
 int fused_prepare(int device);
 cudaError_t launch_fused(const FusedParams &p, int workers, cudaStream_t st);
 cudaError_t launch_gate(const GateParams &p, cudaStream_t st);
+// extension: notes the addresses of candidates [ctr->cand_mark, ctr->n_cand), lists the DF4/5/20/21 tries of the
+// range (launch_gate_ap, GateParams::tries = that list) and slices them against the address table
+cudaError_t launch_note_addresses(const CandRec *cands, unsigned long long cand_cap, const Counters *ctr,
+                                  unsigned long long *first_seen, cudaStream_t st);
+cudaError_t launch_gate_ap(const GateParams &p, cudaStream_t st);
+cudaError_t launch_slice_ap(const AddressParityParams &p, cudaStream_t st);
 cudaError_t launch_slice(const SliceParams &p, cudaStream_t st);
 
 }  // namespace adsb

@@ -162,8 +162,9 @@ __global__ void k_scan_generic(const float *__restrict__ amp, long long j_amp0, 
                                long long count, int accept_df18, int want_tries, CandRec *cands,
                                unsigned long long cand_cap, unsigned long long *tries,
                                unsigned long long try_cap, Counters *ctr, const unsigned long long *fix_tab,
-                               int fix_level)
+                               int fix_level, const unsigned long long *first_seen)
 {
+	// first_seen != null: the pass of the address/parity extension - only DF4/5/20/21, no tries
 	long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
 	if (i >= count)
 		return;
@@ -184,7 +185,10 @@ __global__ void k_scan_generic(const float *__restrict__ amp, long long j_amp0, 
 	     b3 = ppm(a, d + 40);
 	int len = 0;
 	uint32_t cls = 0;
-	if (b7 && !b6 && !b5) {
+	if (first_seen) {
+		if (b5 && !b6 && !b4)
+			len = b7 ? 14 : 7;  // 1010x: DF20, DF21; 0010x: DF4, DF5
+	} else if (b7 && !b6 && !b5) {
 		if (b4 && !b3 && accept_df18) {
 			len = 14;
 			cls = kClsDF18;
@@ -198,7 +202,7 @@ __global__ void k_scan_generic(const float *__restrict__ amp, long long j_amp0, 
 	}
 	if (!len)
 		return;
-	if (want_tries) {
+	if (want_tries && !first_seen) {
 		unsigned long long k = atomicAdd(&ctr->n_try, 1ull);
 		if (k < try_cap)
 			tries[k] = ((unsigned long long)cls << kTryClsShift) | (unsigned long long)n;
@@ -218,7 +222,11 @@ __global__ void k_scan_generic(const float *__restrict__ amp, long long j_amp0, 
 	crc = (crc & 0xFFFFFFu) ^ ((uint32_t)msg[len - 3] << 16 | (uint32_t)msg[len - 2] << 8 |
 	                           (uint32_t)msg[len - 1]);  // crc.h:40-42
 	uint32_t nfix = 0;
-	if (crc != 0) {  // valid.c:52, :74
+	if (first_seen) {
+		// the syndrome is the address overlaid on the parity field: announced at an earlier offset?
+		if (crc == 0 || first_seen[crc] >= (unsigned long long)n)
+			return;
+	} else if (crc != 0) {  // valid.c:52, :74
 		if (fix_level <= 0)
 			return;
 		// extension (repair.h): the syndrome of one or two flipped bits
@@ -300,13 +308,14 @@ cudaError_t launch_scan_generic(const float *amp, long long j_amp0, long long n0
                                 int accept_df18, int want_tries, CandRec *cands,
                                 unsigned long long cand_cap, unsigned long long *tries,
                                 unsigned long long try_cap, Counters *ctr, const unsigned long long *fix_tab,
-                                int fix_level, cudaStream_t st)
+                                int fix_level, const unsigned long long *first_seen, cudaStream_t st)
 {
 	if (count <= 0)
 		return cudaSuccess;
 	const int bs = 256;
 	k_scan_generic<<<(unsigned)((count + bs - 1) / bs), bs, 0, st>>>(
-	    amp, j_amp0, n0, count, accept_df18, want_tries, cands, cand_cap, tries, try_cap, ctr, fix_tab, fix_level);
+	    amp, j_amp0, n0, count, accept_df18, want_tries, cands, cand_cap, tries, try_cap, ctr, fix_tab, fix_level,
+	    first_seen);
 	return cudaGetLastError();
 }
 

@@ -360,7 +360,8 @@ __global__ void ADSB_CHAIN_BOUNDS k_compact(const CandRec *__restrict__ sorted, 
 				drift += skip_of(c.len) - 1ull;
 				p++;
 				const int df = c.bytes[0] >> 3;
-				ok[df == 11 ? 0 : df == 17 ? 1 : 2]++;
+				if (ok_class(df) >= 0)
+					ok[ok_class(df)]++;
 			}
 	}
 #pragma unroll

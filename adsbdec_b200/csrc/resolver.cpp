@@ -61,7 +61,8 @@ void Resolver::scan_to(uint64_t cutoff, std::vector<adsbdec_b200_frame_t> &accep
 			if (ok_)
 				for (size_t k = i0; k < i; k++) {
 					const int df = f[k].bytes[0] >> 3;
-					ok_[df == 11 ? 0 : df == 17 ? 1 : 2]++;
+					if (ok_class(df) >= 0)
+						ok_[ok_class(df)]++;
 				}
 			pos = f[i - 1].n + (f[i - 1].len == 7 ? kSkipShort : kSkipLong);
 		}
@@ -122,7 +123,8 @@ void Resolver::count_pending(uint32_t out[3]) const
 	out[0] = out[1] = out[2] = 0;
 	for (size_t k = fhead_; k < fpending_.size(); k++) {
 		const int df = fpending_[k].bytes[0] >> 3;
-		out[df == 11 ? 0 : df == 17 ? 1 : 2]++;
+		if (ok_class(df) >= 0)
+			out[ok_class(df)]++;
 	}
 }
 

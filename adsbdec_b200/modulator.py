@@ -33,7 +33,7 @@ def crc24(data: bytes) -> int:
 
 
 def make_frame(df: int, rng: np.random.Generator, *, ca: int | None = None,
-               overlay: int = 0) -> bytes:
+               overlay: int = 0, aa: int | None = None) -> bytes:
     """A 56-bit (DF<16) or 112-bit frame with valid parity.
 
     ``overlay`` is XORed onto the parity field: 0 gives the syndrome-0 frames the
@@ -43,6 +43,8 @@ def make_frame(df: int, rng: np.random.Generator, *, ca: int | None = None,
     nbytes = 7 if df < 16 else 14
     body = bytearray(rng.integers(0, 256, nbytes - 3, dtype=np.uint8).tobytes())
     body[0] = ((df & 0x1F) << 3) | ((int(rng.integers(0, 8)) if ca is None else ca) & 7)
+    if aa is not None:          # the AA field of DF11 / DF17 / DF18: bytes 1..3
+        body[1:4] = int(aa).to_bytes(3, "big")
     par = crc24(bytes(body)) ^ overlay
     return bytes(body) + par.to_bytes(3, "big")
 
@@ -142,4 +144,30 @@ def synth_capture(seconds: float, n_frames: int, *, snr_db: float = 20.0, sigma:
             fr = flip_bits(fr, rng.choice(8 * len(fr), bit_errors, replace=False))
         bursts.append(Burst(int(s), fr, amp * float(rng.uniform(0.7, 1.4)),
                             float(rng.uniform(0, 2 * np.pi))))
+    return Capture(render(n_samples, bursts, sigma, rng, pad=pad), bursts, seed)
+
+
+def synth_fleet_capture(seconds: float, n_frames: int, n_aircraft: int, *, snr_db: float = 20.0, sigma: float = 25.0,
+                        seed: int = 0, strangers: float = 0.15, pad: int = PAD_SAMPLES) -> Capture:
+    """Traffic of a fleet: every aircraft has an ICAO address, announces it in DF11 / DF17 / DF18 frames (AA field,
+    plain parity) and answers interrogations with DF4 / DF5 / DF20 / DF21 frames whose parity field is overlaid
+    with that address.  A share ``strangers`` of the address/parity frames comes from aircraft that never announce
+    themselves.  For the address/parity extension; ``Burst.frame`` keeps what was sent."""
+    rng = np.random.default_rng(seed)
+    n_samples = int(round(seconds * FS))
+    n_samples -= n_samples % 8
+    fleet = rng.choice(np.arange(1, 1 << 24), n_aircraft, replace=False)
+    amp = amplitude_for_snr(snr_db, sigma)
+    starts = np.sort(rng.integers(0, max(1, n_samples - 2600), n_frames))
+    bursts = []
+    for s in starts:
+        icao = int(rng.choice(fleet))
+        kind = rng.random()
+        if kind < 0.45:
+            fr = make_frame(int(rng.choice([11, 17, 17, 18])), rng, aa=icao, ca=(0 if kind < 0.1 else None))
+        else:
+            if rng.random() < strangers:
+                icao = int(rng.integers(1, 1 << 24))
+            fr = make_frame(int(rng.choice([4, 5, 20, 21])), rng, overlay=icao)
+        bursts.append(Burst(int(s), fr, amp * float(rng.uniform(0.7, 1.4)), float(rng.uniform(0, 2 * np.pi))))
     return Capture(render(n_samples, bursts, sigma, rng, pad=pad), bursts, seed)

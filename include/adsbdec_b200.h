@@ -89,7 +89,11 @@ typedef struct {
 	                                    file with (0 = up to 12, 1 = the calling thread only),
 	                                    [3]: EXTENSION, error repair by syndrome lookup: 0 = off = the
 	                                    reference (valid.c:52,:74 want syndrome 0), 1 = one flipped bit,
-	                                    2 = also two flipped bits of a 112-bit frame; never the DF field */
+	                                    2 = also two flipped bits of a 112-bit frame; never the DF field;
+	                                    | 0x100: EXTENSION, address/parity frames: DF4 / DF5 / DF20 / DF21, whose
+	                                    parity field carries CRC ^ ICAO address, are accepted when a clean DF11 /
+	                                    DF17 / DF18 frame announced that address at an earlier offset of the
+	                                    stream (stream mode only; the Try/Ok counters do not count them) */
 } adsbdec_b200_config_t;
 
 /* Fills *cfg with defaults (device 0, reference-compatible behaviour). */

@@ -32,6 +32,8 @@ struct oracle_ctx {
 	int accept_df18;
 	int fma_contract;
 	int repair;                 /* EXTENSION, 0 = the reference: see try_repair() */
+	int ap;                     /* EXTENSION, 0 = the reference: see oracle_set_address_parity() */
+	uint64_t *first_seen;       /* [2^24], by ICAO address: where it was first announced (~0: never) */
 	/* front end state (air.c:33-34, 49-50) */
 	float ring[NTAPS];
 	uint32_t ring_pos;
@@ -169,6 +171,12 @@ static int scan(oracle_ctx *c, const float *a, int have)
 		} else if (!b7 && b6 && !b5 && b4 && b3) {
 			len = 7;            /* DF11 */
 		}
+		int ap = 0;
+		if (!len && c->ap && b5 && !b6 && !b4) {
+			/* EXTENSION: 00100 / 00101 (DF4, DF5: 56 bits), 10100 / 10101 (DF20, DF21: 112 bits) */
+			len = b7 ? 14 : 7;
+			ap = 1;
+		}
 		if (!len) {
 			at++;
 			continue;
@@ -183,6 +191,19 @@ static int scan(oracle_ctx *c, const float *a, int have)
 		int df = msg[0] >> 3;
 		c->tried[df]++;                                            /* valid.c:46, 68 */
 		int fixed = 0;
+		if (ap) {
+			/* EXTENSION: the parity field carries CRC ^ address; the frame counts if that address was
+			 * announced by a clean DF11/17/18 frame that starts earlier in the stream */
+			uint32_t addr = syndrome(msg, len);
+			if (addr != 0 && c->first_seen[addr] < c->amp_base + (uint64_t)at) {
+				c->passed[df]++;
+				emit(c, msg, len, (uint32_t)((p1 + p2) / 4), c->amp_base + (uint64_t)at, 0);
+				at = d + 80 * len;
+				continue;
+			}
+			at++;
+			continue;
+		}
 		if (syndrome(msg, len) == 0 || (c->repair > 0 && (fixed = try_repair(c, msg, len)) > 0)) {
 			c->passed[df]++;
 			emit(c, msg, len, (uint32_t)((p1 + p2) / 4), c->amp_base + (uint64_t)at, fixed);
@@ -304,6 +325,76 @@ oracle_ctx *oracle_new(int accept_df18, int fma_contract)
 
 void oracle_set_repair(oracle_ctx *c, int level) { c->repair = level; }
 
+/* ---- EXTENSION: address/parity frames (not in the reference) ---------------------------
+ * DF4, DF5 (56 bits) and DF20, DF21 (112 bits) carry CRC ^ ICAO address in their parity field, so their
+ * syndrome is an address, not zero, and the reference (valid.c:52, :74) never accepts them.  With this mode on
+ * such a frame is accepted when its address has been ANNOUNCED before it: by a DF11 / DF17 / (with -a) DF18
+ * frame with syndrome 0 whose AA field (bytes 1..3) is that address and which starts at an earlier offset of
+ * the stream.  "Starts at an offset" means: the preamble test, the DF gate and the CRC hold there - whether or
+ * not the sequential scan visits that offset (it skips the inside of accepted frames).  That makes the set of
+ * announcements a property of the capture alone, which a parallel decoder can establish without the scan.
+ * Everything sequential (greedy skip, ts, tail) treats an accepted address/parity frame like any other; the
+ * Try/Ok statistics (DF11/17/18) do not count them.  oracle_address_prepass() has to see the whole capture
+ * before it is decoded. */
+static int regular_candidate_at(const oracle_ctx *c, const float *a, uint8_t *msg)
+{
+	int p1 = (int)(a[0] + a[2 * PULSE]), s1 = (int)(a[PULSE] + a[3 * PULSE]);
+	int p2 = (int)(a[7 * PULSE] + a[9 * PULSE]), s2 = (int)(a[6 * PULSE] + a[8 * PULSE]);
+	if (!(p1 > 2 * s1 && p2 > 2 * s2))
+		return 0;
+	const int d = 16 * PULSE;
+	int b7 = ppm_bit(a, d), b6 = ppm_bit(a, d + 10), b5 = ppm_bit(a, d + 20);
+	int b4 = ppm_bit(a, d + 30), b3 = ppm_bit(a, d + 40);
+	int len = 0;
+	if (b7 && !b6 && !b5) {
+		if (b4 && !b3 && c->accept_df18)
+			len = 14;
+		else if (!b4 && b3)
+			len = 14;
+	} else if (!b7 && b6 && !b5 && b4 && b3) {
+		len = 7;
+	}
+	if (!len)
+		return 0;
+	for (int i = 0; i < len; i++) {
+		int v = 0;
+		for (int k = 0; k < 8; k++)
+			v = (v << 1) | ppm_bit(a, d + 80 * i + 10 * k);
+		msg[i] = (uint8_t)v;
+	}
+	return syndrome(msg, len) == 0 ? len : 0;
+}
+
+void oracle_set_address_parity(oracle_ctx *c, int on)
+{
+	c->ap = on;
+	if (on && !c->first_seen) {
+		c->first_seen = malloc(sizeof(uint64_t) << 24);
+		memset(c->first_seen, 0xFF, sizeof(uint64_t) << 24);
+	}
+}
+
+void oracle_address_prepass(oracle_ctx *c, const void *data, size_t nbytes)
+{
+	/* the envelope of the whole capture, through a second context with the same front-end state */
+	size_t n_amp = nbytes / 4 * 2 + 8;
+	float *amp = malloc(n_amp * sizeof *amp);
+	oracle_ctx *t = oracle_new(c->accept_df18, c->fma_contract);
+	t->ring_pos = c->ring_pos;
+	oracle_record_amp(t, amp, n_amp);
+	oracle_decode_memory(t, data, nbytes);
+	size_t have = t->tap_n < n_amp ? t->tap_n : n_amp;
+	oracle_free(t);
+	uint8_t msg[14];
+	for (size_t at = 0; at + LOOKAHEAD < have; at++)
+		if (regular_candidate_at(c, amp + at, msg)) {
+			uint32_t aa = (uint32_t)msg[1] << 16 | (uint32_t)msg[2] << 8 | msg[3];
+			if (c->first_seen[aa] > (uint64_t)at)
+				c->first_seen[aa] = (uint64_t)at;
+		}
+	free(amp);
+}
+
 void oracle_set_origin(oracle_ctx *c, uint64_t origin)
 {
 	c->ring_pos = (uint32_t)origin;
@@ -313,6 +404,7 @@ void oracle_free(oracle_ctx *c)
 {
 	if (c) {
 		free(c->frames);
+		free(c->first_seen);
 		free(c);
 	}
 }

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from helpers import DF_MIX_ALL, capture_basic, frames_key
-from adsbdec_b200.modulator import synth_capture
+from adsbdec_b200.modulator import synth_capture, synth_fleet_capture
 
 pytestmark = pytest.mark.gpu
 
@@ -662,3 +662,55 @@ def test_repair_is_off_by_default(adsb, oracle):
     d.close()
     with pytest.raises(adsb.AdsbError):
         adsb.Decoder(repair=3)
+
+
+@pytest.mark.parametrize("kernel", [1, 0], ids=["generic", "fused"])
+@pytest.mark.parametrize("batch", [0, 1 << 20], ids=["one_job", "many_jobs"])
+def test_address_parity_extension_matches_oracle(adsb, oracle, kernel, batch):
+    """EXTENSION, off by default (the reference rejects every frame with a non-zero syndrome): DF4 / DF5 / DF20 /
+    DF21 carry CRC ^ ICAO address in their parity field and are accepted when a clean DF11 / DF17 / DF18 frame has
+    announced that address at an earlier offset.  The GPU (address table updated job by job, a gate and a slicer
+    pass of their own) against the oracle's sequential statement of the same rule: frames, timestamps (an accepted
+    frame takes part in the greedy skip), Try/Ok (which do not count the new classes)."""
+    cap = synth_fleet_capture(0.3, 400, 15, snr_db=22, seed=70, pad=1 << 16)
+    ref = oracle.decode(cap.samples, accept_df18=True, address_parity=True)
+    d = adsb.decode(cap.samples, accept_df18=True, kernel=kernel, address_parity=True, batch_samples=batch)
+    got, st = d.frames, d.stats()
+    d.close()
+    assert_same(ref, got, st)
+    plain = oracle.decode(cap.samples, accept_df18=True)
+    dfs = [f.data[0] >> 3 for f in ref.frames]
+    assert len(ref.frames) > len(plain.frames) + 60 and {4, 5, 20, 21} <= set(dfs)
+    # nobody is accepted before being announced, strangers never
+    first = {}
+    for f in ref.frames:
+        df = f.data[0] >> 3
+        if df in (11, 17, 18):
+            first.setdefault(bytes(f.data[1:4]), f.n)
+    sent = {bytes(b.frame): b for b in cap.bursts}
+    for f in ref.frames:
+        if (f.data[0] >> 3) in (4, 5, 20, 21):
+            assert bytes(f.data) in sent
+
+
+def test_cli_address_parity_flag(adsb, oracle, tmp_path):
+    """-P (extension; the reference has no such flag and rejects these frames): same bytes as the oracle's text."""
+    cap = synth_fleet_capture(0.2, 250, 10, snr_db=22, seed=72, pad=1 << 21)
+    f = tmp_path / "fleet.bin"
+    cap.samples.astype("<u2").tofile(f)
+    r = subprocess.run([str(adsb.CLI_PATH), "-a", "-P", "-m", "-f", str(f)], capture_output=True)
+    assert r.returncode == 0
+    assert r.stdout == oracle.decode(cap.samples, accept_df18=True, address_parity=True).text(1)
+    r = subprocess.run([str(adsb.CLI_PATH), "-a", "-m", "-f", str(f)], capture_output=True)
+    assert r.stdout == oracle.decode(cap.samples, accept_df18=True).text(1)
+
+
+def test_address_parity_is_off_by_default(adsb, oracle):
+    cap = synth_fleet_capture(0.2, 200, 10, snr_db=22, seed=71, pad=1 << 16)
+    d = adsb.decode(cap.samples, accept_df18=True)
+    ref = oracle.decode(cap.samples, accept_df18=True)
+    assert_same(ref, d.frames, d.stats())
+    assert not ({f.data[0] >> 3 for f in d.frames} & {4, 5, 20, 21})
+    d.close()
+    with pytest.raises(adsb.AdsbError):
+        adsb.Decoder(address_parity=True).chunk_candidates(16, 1 << 16, 0, 0, 100)

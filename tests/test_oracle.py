@@ -198,3 +198,26 @@ def test_oracle_empty_and_tiny_inputs(oracle, tmp_path):
         g = tmp_path / "tiny.bin"
         cap.tofile(g)
         assert oracle.run_ref(g, binary=binary).stdout == b""
+
+
+def test_address_parity_extension_of_the_oracle(oracle):
+    """EXTENSION (no reference behaviour to pin it to: the reference rejects these frames).  The oracle's own
+    statement of the rule, checked for what must hold by construction: off by default, every accepted
+    DF4/5/20/21 frame is one that was sent, its address was announced by an earlier DF11/17/18 frame of the
+    capture, and an aircraft that never announces itself is never accepted."""
+    from adsbdec_b200.modulator import crc24, synth_fleet_capture
+    cap = synth_fleet_capture(0.3, 400, 15, snr_db=22, seed=70, pad=1 << 16)
+    plain = oracle.decode(cap.samples, accept_df18=True)
+    ref = oracle.decode(cap.samples, accept_df18=True, address_parity=True)
+    assert not ({f.data[0] >> 3 for f in plain.frames} & {4, 5, 20, 21})
+    sent = {bytes(b.frame) for b in cap.bursts}
+    announced_at = {}
+    for b in cap.bursts:
+        if (b.frame[0] >> 3) in (11, 17, 18):
+            announced_at.setdefault(bytes(b.frame[1:4]), b.start)
+    extra = [f for f in ref.frames if (f.data[0] >> 3) in (4, 5, 20, 21)]
+    assert len(extra) > 60
+    for f in extra:
+        assert bytes(f.data) in sent
+        addr = (crc24(bytes(f.data[:-3])) ^ int.from_bytes(f.data[-3:], "big")).to_bytes(3, "big")
+        assert addr in announced_at and announced_at[addr] // 2 < f.n
