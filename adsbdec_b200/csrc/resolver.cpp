@@ -20,6 +20,8 @@ void Resolver::scan_keys_to(uint64_t cutoff)
 	// search only what a long walk has not reached
 	const unsigned long long kc = (unsigned long long)cutoff << 1;  // k < kc  <=>  start < cutoff
 	const size_t w = std::min(n, i + 48);
+	while (i + 4 <= w && k[i + 3] < kc)  // (four at a time: the walk is a chain of dependent loads otherwise)
+		i += 4;
 	while (i < w && k[i] < kc)
 		i++;
 	if (i == w && i < n && k[i] < kc)
