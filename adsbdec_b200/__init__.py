@@ -302,6 +302,17 @@ class Decoder:
         return np.frombuffer(buf, dtype=FRAME_DTYPE).copy()
 
     @property
+    def frames_view(self) -> np.ndarray:
+        """The frame store itself (adsbdec_b200_frames()), not a copy: page-locked host memory the GPU has written
+        the accepted frames into.  Valid until the next push / finish / reset / clear_frames / close."""
+        L = lib()
+        n = L.adsbdec_b200_num_frames(self._h)
+        if n == 0:
+            return np.zeros(0, dtype=FRAME_DTYPE)
+        buf = (C.c_uint8 * (n * FRAME_DTYPE.itemsize)).from_address(L.adsbdec_b200_frames(self._h))
+        return np.frombuffer(buf, dtype=FRAME_DTYPE)
+
+    @property
     def num_frames(self) -> int:
         return int(lib().adsbdec_b200_num_frames(self._h))
 

@@ -602,7 +602,10 @@ def main():
             dec.reset()
             dec.push(host_np)
             dec.finish()
-            fa = dec.frames_array          # the step's result, on the host
+            # the step's result is on the host when finish() returns (the library fetches the accepted frames into
+            # its page-locked store): read it where it lies - a copy into a fresh numpy array cost 3 ms per step
+            fa = dec.frames_view
+            assert int(fa["n"][-1]) > int(fa["n"][0])
             return len(fa), fa.nbytes
 
         step_e2e()
@@ -637,7 +640,7 @@ def main():
                 dec.push_packed12(pk_np, n8)
                 dec.push(host_np[n8:])
                 dec.finish()
-                nfp = len(dec.frames_array)
+                nfp = len(dec.frames_view)
                 dt = time.perf_counter() - tp
                 best = dt if best is None else min(best, dt)
             assert nfp == frames, (nfp, frames)

@@ -714,3 +714,13 @@ def test_address_parity_is_off_by_default(adsb, oracle):
     d.close()
     with pytest.raises(adsb.AdsbError):
         adsb.Decoder(address_parity=True).chunk_candidates(16, 1 << 16, 0, 0, 100)
+
+
+def test_frames_view_is_the_store_itself(adsb, oracle):
+    """Decoder.frames_view hands out adsbdec_b200_frames() without a copy (what bench.py's end-to-end leg reads)."""
+    cap = capture_basic(seed=73)
+    d = adsb.decode(cap.samples, accept_df18=True)
+    v, a = d.frames_view, d.frames_array
+    assert len(v) == d.num_frames == len(oracle.decode(cap.samples, accept_df18=True).frames)
+    assert v.tobytes() == a.tobytes() and not v.flags.owndata
+    d.close()
