@@ -91,9 +91,9 @@ def test_tail_and_tiny_inputs(adsb, oracle, n_samples):
 @pytest.mark.parametrize("kernel", [1, 0], ids=["generic", "fused"])
 def test_saturated_traffic_is_one_long_greedy_chain(adsb, oracle, kernel):
     """Short frames back to back (one every 713 offsets, each 640 long): no two candidates are a full frame
-    (1200 offsets) apart, so the greedy rule (demod.c:128, :134) links the whole capture into ONE chain,
-    which k_greedy walks with a single thread.  Slow by design (the walk is the reference's own sequential
-    dependency) - but exact."""
+    (1200 offsets) apart, so the greedy rule (demod.c:128, :134) links the whole capture into ONE chain - the
+    reference's own sequential dependency.  k_greedy hands such a chain from the thread that found it to its
+    warp (32 candidates per load, the rule applied out of registers)."""
     cap = synth_capture(0.1, 1400, snr_db=22, seed=61, df_mix=((11, 1.0),), pad=1 << 16, poisson=False)
     ref = oracle.decode(cap.samples, accept_df18=True)
     d = adsb.decode(cap.samples, accept_df18=True, kernel=kernel)
