@@ -204,6 +204,8 @@ struct adsbdec_b200 {
 	cudaEvent_t ev_dev_free[2] = {nullptr, nullptr};  // last reader of dev[i] (job + carry copy) done
 	cudaEvent_t ev_pin_free[2] = {nullptr, nullptr};  // last upload out of pin[i] done
 	cudaEvent_t ev_h2d = nullptr;
+	// a job's results on their way to the host (st_d2h): its keys have arrived / its frames have arrived
+	cudaEvent_t ev_keys = nullptr, ev_frm = nullptr;
 	int cur = 0;
 	int64_t win_u0 = 0;      // local index of the first sample held in dev[cur] (carry start)
 	int64_t win_off = 0;     // element offset in dev[cur] where local sample win_u0 sits
@@ -233,6 +235,7 @@ struct adsbdec_b200 {
 	int fspan_cap[kSlots] = {};
 	int *d_ticket[kSlots] = {};
 	cudaEvent_t ev_done[kSlots] = {};
+	cudaEvent_t tr_ref = nullptr;    // ADSB_B200_TRACE: the event the GPU timeline is printed against
 	cudaEvent_t ev_a[kSlots] = {}, ev_b[kSlots] = {};
 	cudaEvent_t ev_fa[kSlots] = {}, ev_fb[kSlots] = {};
 	cudaEvent_t ev_fc[kSlots] = {};     // behind k_gate + k_slice of the slot's last fused range
@@ -726,6 +729,18 @@ int complete_job(adsbdec_b200 *h, int s)
 				h->fused_ms += ms;
 				cudaEventElapsedTime(&ms, h->ev_fb[s], h->ev_fc[s]);
 				h->gate_ms += ms;
+				if (h->tr.on) {  // GPU timeline of the job relative to the start of the first job in flight's scan
+					float t_fa = 0, t_fb = 0, t_fc = 0, t_b = 0;
+					cudaEvent_t ref = h->tr_ref ? h->tr_ref : h->ev_a[s];
+					if (!h->tr_ref)
+						h->tr_ref = h->ev_a[s];
+					cudaEventElapsedTime(&t_fa, ref, h->ev_fa[s]);
+					cudaEventElapsedTime(&t_fb, ref, h->ev_fb[s]);
+					cudaEventElapsedTime(&t_fc, ref, h->ev_fc[s]);
+					cudaEventElapsedTime(&t_b, ref, h->ev_b[s]);
+					fprintf(stderr, "  [trace-gpu] slot %d: k_fused %.3f..%.3f, gate+slice ..%.3f, chain done %.3f ms\n", s, t_fa,
+					        t_fb, t_fc, t_b);
+				}
 			}
 			const Counters &c = *h->h_ctr[s];
 			if (j.used_fused && c.wide) {
@@ -774,17 +789,22 @@ int complete_job(adsbdec_b200 *h, int s)
 	const double t2 = now_ms();
 	if (n_res) {
 		RC(reserve_frames(h, n_res));
+		// keys first: the call schedule below reads nothing else, and runs while the 40-byte records follow
 		CU(cudaMemcpyAsync(h->fkeys + h->n_total, h->d_key[s], n_res * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
 		                   h->st_d2h));
+		CU(cudaEventRecord(h->ev_keys, h->st_d2h));
 		CU(cudaMemcpyAsync(h->frames + h->n_total, h->d_acc[s], n_res * sizeof(FrameRec), cudaMemcpyDeviceToHost,
 		                   h->st_d2h));
-		CU(cudaStreamSynchronize(h->st_d2h));
-		h->tr.mark("complete_job: fetched");
+		CU(cudaEventRecord(h->ev_frm, h->st_d2h));
+		CU(cudaEventSynchronize(h->ev_keys));
+		h->tr.mark("complete_job: keys fetched");
 		h->n_total += n_res;
 	}
 	h->n_vis = h->res->advance_keys(h->fkeys, h->n_vis, h->n_total, (uint64_t)std::max<int64_t>(j.n1, 0),
 	                                (uint64_t)j.total_out);
 	h->counted = h->n_vis;
+	if (n_res)
+		CU(cudaEventSynchronize(h->ev_frm));  // the frames themselves have landed
 	// (Ok counters: the GPU counted the job's accepted frames per class; the few the call schedule has not
 	// reached yet are taken off again wherever the counters are read)
 	if (scanned)
@@ -971,6 +991,8 @@ int adsbdec_b200_open(const adsbdec_b200_config_t *cfg, adsbdec_b200_t **out)
 		          cudaStreamCreateWithFlags(&h->st_res, cudaStreamNonBlocking) == cudaSuccess &&
 		          cudaStreamCreateWithFlags(&h->st_stat, cudaStreamNonBlocking) == cudaSuccess &&
 		          cudaEventCreateWithFlags(&h->ev_h2d, cudaEventDisableTiming) == cudaSuccess &&
+		          cudaEventCreateWithFlags(&h->ev_keys, cudaEventDisableTiming) == cudaSuccess &&
+		          cudaEventCreateWithFlags(&h->ev_frm, cudaEventDisableTiming) == cudaSuccess &&
 		          cudaMalloc(&h->d_stats, sizeof(StreamStats)) == cudaSuccess &&
 		          cudaMalloc(&h->d_state, sizeof(ResolveState)) == cudaSuccess &&
 		          cudaMemset(h->d_state, 0, sizeof(ResolveState)) == cudaSuccess &&
@@ -1117,6 +1139,8 @@ void adsbdec_b200_close(adsbdec_b200_t *h)
 	if (h->h_stats) cudaFreeHost(h->h_stats);
 	if (h->d_amp) cudaFree(h->d_amp);
 	if (h->ev_h2d) cudaEventDestroy(h->ev_h2d);
+	if (h->ev_keys) cudaEventDestroy(h->ev_keys);
+	if (h->ev_frm) cudaEventDestroy(h->ev_frm);
 	if (h->st) cudaStreamDestroy(h->st);
 	if (h->st_copy) cudaStreamDestroy(h->st_copy);
 	if (h->st_d2h) cudaStreamDestroy(h->st_d2h);
@@ -1157,6 +1181,7 @@ int adsbdec_b200_reset(adsbdec_b200_t *h, uint64_t start_sample)
 		h->job[s].active = false;
 	delete h->res;
 	h->res = new Resolver(h->cfg.emulate_reference_tail != 0);
+	h->tr_ref = nullptr;
 	h->n_total = h->n_vis = 0;  // the store keeps its capacity
 	h->emitted = 0;
 	h->counted = 0;

@@ -297,10 +297,20 @@ cudaError_t launch_fill_pw(const uint16_t *raw, long long u_raw0, unsigned long 
 	return cudaGetLastError();
 }
 
+static int fill_blocks()
+{
+	static const int n = [] {
+		const char *e = getenv("ADSB_B200_CHAIN_BLOCKS");  // development knob, see kernels_resolve.cu
+		const int v = e ? atoi(e) : 0;
+		return v > 0 ? v : 592;
+	}();
+	return n;
+}
+
 cudaError_t launch_fill_pw_frames(const uint16_t *raw, long long u_raw0, unsigned long long origin, FrameRec *frames,
                                   const unsigned long long *n_ptr, unsigned long long cap, cudaStream_t st)
 {
-	k_fill_pw_frames<<<592, 128, 0, st>>>(raw, u_raw0, origin, frames, n_ptr, cap);
+	k_fill_pw_frames<<<fill_blocks(), 128, 0, st>>>(raw, u_raw0, origin, frames, n_ptr, cap);
 	return cudaGetLastError();
 }
 

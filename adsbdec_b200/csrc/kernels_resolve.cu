@@ -17,6 +17,7 @@
 // timestamp (demod.c:99) and the deqframe call schedule (air.c:94-99) that decides where the scan ends.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/adsbdec_b200.h"
 #include "common.h"
@@ -44,7 +45,17 @@ constexpr int kScanThreads = 128;
 constexpr int kChainThreads = 256;
 constexpr int kScanThreads = 1024;
 #endif
-constexpr int kChainBlocks = 296 * 256 / kChainThreads;
+// Blocks of the grid-stride kernels (development knob ADSB_B200_CHAIN_BLOCKS).
+static int chain_blocks()
+{
+	static const int n = [] {
+		const char *e = getenv("ADSB_B200_CHAIN_BLOCKS");
+		const int v = e ? atoi(e) : 0;
+		return v > 0 ? v : 296 * 256 / kChainThreads;
+	}();
+	return n;
+}
+#define kChainBlocks chain_blocks()
 
 __device__ __forceinline__ unsigned long long job_count(const Counters *ctr, unsigned long long cap)
 {
@@ -556,7 +567,7 @@ cudaError_t launch_count_tries_frames(const unsigned long long *tries, const uns
                                       cudaStream_t st)
 {
 	const int nb = n1 > n0 ? resolve_bucket_count(n0, n1) : 0;
-	k_count_tries_frames<<<2 * kChainBlocks, kChainThreads, 0, st>>>(tries, n_tries_ptr, cap, frames, slot, frames_cap, rb.bacc_x, n0, nb,
+	k_count_tries_frames<<<4 * kChainBlocks, kChainThreads, 0, st>>>(tries, n_tries_ptr, cap, frames, slot, frames_cap, rb.bacc_x, n0, nb,
 	                                         scan_end, pend_out, n_pend_out, pend_cap, stt);
 	return cudaGetLastError();
 }
