@@ -803,8 +803,6 @@ int complete_job(adsbdec_b200 *h, int s)
 	h->n_vis = h->res->advance_keys(h->fkeys, h->n_vis, h->n_total, (uint64_t)std::max<int64_t>(j.n1, 0),
 	                                (uint64_t)j.total_out);
 	h->counted = h->n_vis;
-	if (n_res)
-		CU(cudaEventSynchronize(h->ev_frm));  // the frames themselves have landed
 	// (Ok counters: the GPU counted the job's accepted frames per class; the few the call schedule has not
 	// reached yet are taken off again wherever the counters are read)
 	if (scanned)
@@ -812,11 +810,13 @@ int complete_job(adsbdec_b200 *h, int s)
 			h->stat_ok[c] += h->h_slot[s]->ok[c];
 	const double t3 = now_ms();
 	h->tr.mark("complete_job: frames fed");
-	if (scanned) {
+	if (scanned) {  // (needs the scan end the schedule has just reached, nothing of the frames on the host)
 		RC(stats_pass(h, s, true));
 		h->last_slot = s;
 	}
 	const double t4 = now_ms();
+	if (n_res)
+		CU(cudaEventSynchronize(h->ev_frm));  // the frames themselves have landed
 	emit_new_frames(h);
 	h->tel.resolve_ms += t3 - t2;
 	h->tel.stats_issue_ms += t4 - t3;
