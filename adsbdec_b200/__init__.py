@@ -197,7 +197,7 @@ class Decoder:
     def __init__(self, *, device: int = 0, accept_df18: bool = False, emulate_reference_tail: bool = True,
                  collect_stats: bool = True, kernel: int = 0, batch_samples: int = 0, start_sample: int = 0,
                  sink=None, initial_caps: tuple[int, int] = (0, 0), reader_threads: int = 0, repair: int = 0,
-                 address_parity: bool = False):
+                 address_parity: bool = False, iq: bool = False):
         L = lib()
         cfg = Config()
         L.adsbdec_b200_default_config(C.byref(cfg))
@@ -212,7 +212,8 @@ class Decoder:
         cfg.reserved[2] = reader_threads  # decode_file: 0 = up to 12, 1 = the calling thread only
         # EXTENSIONS (not in the reference): repair 1 = fix one bit, 2 = two bits; 0x100 = accept DF4/5/20/21
         # whose address/parity field names an aircraft announced earlier in the stream
-        cfg.reserved[3] = repair | (0x100 if address_parity else 0)
+        # 0x200 = the samples are signed I/Q pairs at 10 MS/s (complex baseband) instead of real samples at 20 MS/s
+        cfg.reserved[3] = repair | (0x100 if address_parity else 0) | (0x200 if iq else 0)
         self._h = C.c_void_p()
         self._cb = None
         _check(L.adsbdec_b200_open(C.byref(cfg), C.byref(self._h)))

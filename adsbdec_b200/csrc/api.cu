@@ -276,6 +276,7 @@ struct adsbdec_b200 {
 	int fix_level = 0;
 	// EXTENSION, off by default: DF4/5/20/21 accepted against the addresses announced so far
 	bool ap_mode = false;
+	bool iq_mode = false;  // EXTENSION: the stream is signed 16-bit I/Q pairs at 10 MS/s, not real samples
 	unsigned long long *d_first_seen = nullptr;     // [2^24] by ICAO address: offset of its first announcement
 	unsigned long long *d_aptries[kSlots] = {};     // DF4/5/20/21 tries of the fused range being worked on
 	unsigned long long ap_cap[kSlots] = {};
@@ -390,7 +391,7 @@ int launch_generic(adsbdec_b200 *h, int s, const Job &j, int64_t n0, int64_t n1)
 		CU(cudaMalloc(&h->d_amp, (size_t)(kAmpChunk + kLookahead) * sizeof(float)));
 	for (int64_t c0 = n0; c0 < n1; c0 += kAmpChunk) {
 		const int64_t cnt = std::min(kAmpChunk, n1 - c0);
-		CU(launch_envelope_generic(j.buf, j.u0, j.origin, c0, cnt + kLookahead, h->d_amp, h->st));
+		CU(launch_envelope_generic(j.buf, j.u0, j.origin, c0, cnt + kLookahead, h->d_amp, h->iq_mode ? 1 : 0, h->st));
 		if (h->ap_mode) {
 			k_mark_cands<<<1, 1, 0, h->st>>>(h->d_ctr[s]);
 			CU(cudaGetLastError());
@@ -569,7 +570,7 @@ int enqueue_job(adsbdec_b200 *h, int s, bool force_generic)
 	// the statistics pass of the job that used this slot before reads its lists on a stream of its own
 	CU(cudaStreamWaitEvent(h->st, h->ev_stats[s], 0));
 	CU(cudaStreamWaitEvent(h->st_res, h->ev_stats[s], 0));
-	force_generic = force_generic || h->cfg.kernel == 1 || h->fused_ctas <= 0;
+	force_generic = force_generic || h->cfg.kernel == 1 || h->fused_ctas <= 0 || h->iq_mode;  // (no FIR in front of I/Q)
 	k_reset_counters<<<1, 1, 0, h->st>>>(h->d_ctr[s]);
 	CU(cudaGetLastError());
 	CU(cudaEventRecord(h->ev_a[s], h->st));
@@ -1049,12 +1050,14 @@ int adsbdec_b200_open(const adsbdec_b200_config_t *cfg, adsbdec_b200_t **out)
 			h->fused_ctas = per_sm * sms;
 		}
 		// reserved[3]: opt-in error repair (repair.h) - 0 = the reference's behaviour
-		if ((cfg->reserved[3] & 0xFFu) > 2 || (cfg->reserved[3] & ~0x1FFull)) {
-			rc = fail(ADSB_B200_EINVAL, "reserved[3]: repair level 0, 1 or 2, plus 0x100 for address/parity frames");
+		if ((cfg->reserved[3] & 0xFFu) > 2 || (cfg->reserved[3] & ~0x3FFull)) {
+			rc = fail(ADSB_B200_EINVAL,
+			          "reserved[3]: repair level 0, 1 or 2, plus 0x100 for address/parity frames, 0x200 for I/Q input");
 			break;
 		}
 		h->fix_level = (int)(cfg->reserved[3] & 0xFFu);
 		h->ap_mode = (cfg->reserved[3] & 0x100u) != 0;
+		h->iq_mode = (cfg->reserved[3] & 0x200u) != 0;
 		if (h->ap_mode) {
 			if (cudaMalloc(&h->d_first_seen, sizeof(unsigned long long) << 24) != cudaSuccess ||
 			    cudaMemset(h->d_first_seen, 0xFF, sizeof(unsigned long long) << 24) != cudaSuccess) {
@@ -1712,7 +1715,7 @@ int adsbdec_b200_envelope(int device, const void *samples, size_t n_samples, int
 	}
 	cudaError_t e = cudaMalloc(&d_amp, std::max<size_t>(count, 1) * sizeof(float));
 	if (e == cudaSuccess)
-		e = launch_envelope_generic(raw, 0, start_sample, 0, (long long)count, d_amp, 0);
+		e = launch_envelope_generic(raw, 0, start_sample, 0, (long long)count, d_amp, 0, 0);
 	if (e == cudaSuccess)
 		e = cudaMemcpy(amp_out, d_amp, count * sizeof(float), cudaMemcpyDeviceToHost);
 	if (d_raw) cudaFree(d_raw);

@@ -46,6 +46,7 @@ void usage()
 	printf("\t-D n : CUDA device ordinal\n");
 	printf("\t-R 1|2 : extension, not in adsbdec : repair 1 (2) flipped bits by CRC syndrome\n");
 	printf("\t-P : extension, not in adsbdec : also DF4/5/20/21 of aircraft announced earlier (address/parity)\n");
+	printf("\t-I : extension, not in adsbdec : the file holds signed 16-bit I/Q pairs at 10 MS/s\n");
 }
 
 // -s: connect to a server; -l: bind, wait for ONE client ("listening" / "connected" on stderr), then
@@ -151,7 +152,7 @@ int main(int argc, char **argv)
 	adsbdec_b200_config_t cfg;
 	adsbdec_b200_default_config(&cfg);
 	int c;
-	while ((c = getopt(argc, argv, "cf:s:l:g:aembD:GR:P")) != EOF) {
+	while ((c = getopt(argc, argv, "cf:s:l:g:aembD:GR:PI")) != EOF) {
 		switch (c) {
 		case 'f': filename = optarg; break;
 		case 's': addr = optarg; listener = false; break;  // main.c: outmode 1
@@ -164,6 +165,7 @@ int main(int argc, char **argv)
 		case 'G': cfg.kernel = 1; break;
 		case 'R': cfg.reserved[3] = (cfg.reserved[3] & 0x100u) | (uint64_t)(atoi(optarg) & 0xFF); break;
 		case 'P': cfg.reserved[3] |= 0x100u; break;
+		case 'I': cfg.reserved[3] |= 0x200u; break;
 		default:  // -c, -e and anything unknown
 			usage();
 			return 1;

@@ -10,7 +10,7 @@ namespace adsb {
 // ---- generic path (kernels_generic.cu) -----------------------------------
 
 cudaError_t launch_envelope_generic(const uint16_t *raw, long long u_raw0, unsigned long long origin,
-                                    long long j0, long long n, float *amp, cudaStream_t st);
+                                    long long j0, long long n, float *amp, int iq, cudaStream_t st);
 
 cudaError_t launch_fill_pw(const uint16_t *raw, long long u_raw0, unsigned long long origin, CandRec *cands,
                            const unsigned long long *n_cand_ptr, unsigned long long cap, cudaStream_t st);

@@ -87,11 +87,19 @@ __device__ float envelope_at(const uint16_t *__restrict__ raw, long long u_raw0,
 
 __global__ void k_envelope_generic(const uint16_t *__restrict__ raw, long long u_raw0,
                                    unsigned long long phase_origin, long long j0, long long n,
-                                   float *__restrict__ amp)
+                                   float *__restrict__ amp, int iq)
 {
 	long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
 	if (i >= n)
 		return;
+	if (iq) {
+		// EXTENSION: the stream is complex baseband, one signed 16-bit I/Q pair per envelope
+		// sample; the envelope is |z|^2 in the form of air.c:76
+		const long long u = 2 * (j0 + i) - u_raw0;
+		const float I = (float)(int16_t)raw[u], Q = (float)(int16_t)raw[u + 1];
+		amp[i] = __fmaf_rn(I, I, __fmul_rn(Q, Q));
+		return;
+	}
 	amp[i] = envelope_at(raw, u_raw0, phase_origin, j0 + i);
 }
 
@@ -281,12 +289,12 @@ __global__ void k_unpack12(const uint32_t *__restrict__ in, uint16_t *__restrict
 // ---- launch wrappers -----------------------------------------------------
 
 cudaError_t launch_envelope_generic(const uint16_t *raw, long long u_raw0, unsigned long long origin,
-                                    long long j0, long long n, float *amp, cudaStream_t st)
+                                    long long j0, long long n, float *amp, int iq, cudaStream_t st)
 {
 	if (n <= 0)
 		return cudaSuccess;
 	const int bs = 256;
-	k_envelope_generic<<<(unsigned)((n + bs - 1) / bs), bs, 0, st>>>(raw, u_raw0, origin, j0, n, amp);
+	k_envelope_generic<<<(unsigned)((n + bs - 1) / bs), bs, 0, st>>>(raw, u_raw0, origin, j0, n, amp, iq);
 	return cudaGetLastError();
 }
 

@@ -171,3 +171,47 @@ def synth_fleet_capture(seconds: float, n_frames: int, n_aircraft: int, *, snr_d
             fr = make_frame(int(rng.choice([4, 5, 20, 21])), rng, overlay=icao)
         bursts.append(Burst(int(s), fr, amp * float(rng.uniform(0.7, 1.4)), float(rng.uniform(0, 2 * np.pi))))
     return Capture(render(n_samples, bursts, sigma, rng, pad=pad), bursts, seed)
+
+
+def synth_iq_capture(seconds: float, n_frames: int, *, snr_db: float = 20.0, sigma: float = 40.0, seed: int = 0,
+                     df_mix=((17, 1.0),), pad: int = PAD_SAMPLES, fleet: int = 0) -> Capture:
+    """The same traffic as complex baseband: signed 16-bit I/Q pairs at 10 MS/s (what libairspy hands out as
+    INT16_IQ: it does the fs/4 translation and the decimation itself).  ``samples`` holds the interleaved pairs
+    reinterpreted as uint16 - one pair per envelope sample - ready for ``Decoder(iq=True).push``.  ``fleet`` > 0:
+    frames of that many aircraft as in synth_fleet_capture (for the address/parity extension).  ``Burst.start`` is in
+    16-bit values, like everywhere else (two per envelope sample)."""
+    rng = np.random.default_rng(seed)
+    n_pairs = int(round(seconds * FS / 2))
+    n_pairs -= n_pairs % 4
+    dfs = np.array([d for d, _ in df_mix])
+    w = np.array([x for _, x in df_mix], dtype=np.float64)
+    w /= w.sum()
+    amp = amplitude_for_snr(snr_db, sigma)
+    aircraft = rng.choice(np.arange(1, 1 << 24), fleet, replace=False) if fleet else None
+    starts = np.sort(rng.integers(0, max(1, n_pairs - 1300), n_frames))
+    z = np.zeros(n_pairs, dtype=np.complex64)
+    bursts = []
+    for s in starts:
+        if fleet:
+            icao = int(rng.choice(aircraft))
+            if rng.random() < 0.45:
+                fr = make_frame(int(rng.choice([11, 17, 17, 18])), rng, aa=icao, ca=(0 if rng.random() < 0.2 else None))
+            else:
+                fr = make_frame(int(rng.choice([4, 5, 20, 21])), rng, overlay=icao)
+        else:
+            fr = make_frame(int(rng.choice(dfs, p=w)), rng)
+        a = amp * float(rng.uniform(0.7, 1.4))
+        ph = float(rng.uniform(0, 2 * np.pi))
+        env = envelope(fr)[::2]                 # 20 MS/s pulse shape -> 10 MS/s (5 samples per half microsecond)
+        end = min(int(s) + env.size, n_pairs)
+        z[int(s):end] += np.complex64(a * np.exp(1j * ph)) * env[:end - int(s)]
+        bursts.append(Burst(2 * int(s), fr, a, ph))
+    if sigma > 0:
+        z += (rng.standard_normal(n_pairs, dtype=np.float32) + 1j * rng.standard_normal(n_pairs, dtype=np.float32)) \
+            * np.float32(sigma)
+    iq = np.empty(2 * n_pairs, dtype=np.int16)
+    iq[0::2] = np.clip(np.rint(z.real), -8191, 8191)
+    iq[1::2] = np.clip(np.rint(z.imag), -8191, 8191)
+    if pad:
+        iq = np.concatenate([iq, np.zeros(pad, dtype=np.int16)])
+    return Capture(iq.view("<u2"), bursts, seed)

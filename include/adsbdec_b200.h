@@ -93,7 +93,11 @@ typedef struct {
 	                                    | 0x100: EXTENSION, address/parity frames: DF4 / DF5 / DF20 / DF21, whose
 	                                    parity field carries CRC ^ ICAO address, are accepted when a clean DF11 /
 	                                    DF17 / DF18 frame announced that address at an earlier offset of the
-	                                    stream (stream mode only; the Try/Ok counters do not count them) */
+	                                    stream (stream mode only; the Try/Ok counters do not count them);
+	                                    | 0x200: EXTENSION, I/Q input: the pushed 16-bit values are SIGNED I/Q pairs
+	                                    of a complex baseband stream at 10 MS/s (libairspy's INT16_IQ sample type)
+	                                    instead of real samples at 20 MS/s: one pair per envelope sample, envelope
+	                                    = I*I + Q*Q, no fs/4 mixer or FIR; everything behind the envelope as usual */
 } adsbdec_b200_config_t;
 
 /* Fills *cfg with defaults (device 0, reference-compatible behaviour). */

@@ -33,6 +33,7 @@ struct oracle_ctx {
 	int fma_contract;
 	int repair;                 /* EXTENSION, 0 = the reference: see try_repair() */
 	int ap;                     /* EXTENSION, 0 = the reference: see oracle_set_address_parity() */
+	int iq;                     /* EXTENSION, 0 = the reference: see oracle_set_iq() */
 	uint64_t *first_seen;       /* [2^24], by ICAO address: where it was first announced (~0: never) */
 	/* front end state (air.c:33-34, 49-50) */
 	float ring[NTAPS];
@@ -258,6 +259,24 @@ static inline void amp_put(oracle_ctx *c, float v)
 
 void oracle_push(oracle_ctx *c, const uint16_t *buf, int len)
 {
+	if (c->iq) {
+		/* EXTENSION: signed I/Q pairs, one per envelope sample, |z|^2 in the form of air.c:76; the
+		 * buffer schedule (air.c:94-99: a look every two envelope samples) is the reference's */
+		for (int i = 0; i < len; i += 4) {
+			for (int k = 0; k < 4; k += 2) {
+				float fi = (float)(int16_t)buf[i + k], fq = (float)(int16_t)buf[i + k + 1];
+				amp_put(c, c->fma_contract ? fmaf(fi, fi, fq * fq) : fi * fi + fq * fq);
+			}
+			if (c->amp_fill >= AMP_FLUSH) {
+				int used = scan(c, c->amp, (int)c->amp_fill);
+				if ((uint32_t)used < c->amp_fill)
+					memmove(c->amp, c->amp + used, (c->amp_fill - (uint32_t)used) * sizeof(float));
+				c->amp_fill -= (uint32_t)used;
+				c->amp_base += (uint64_t)used;
+			}
+		}
+		return;
+	}
 	for (int i = 0; i < len; i += 4) {
 		/* air.c:64-67, 79-82: centre on mid-scale; the second pair of every
 		 * four is negated (fs/4 mixer). */
@@ -325,6 +344,12 @@ oracle_ctx *oracle_new(int accept_df18, int fma_contract)
 
 void oracle_set_repair(oracle_ctx *c, int level) { c->repair = level; }
 
+/* EXTENSION (not in the reference, which only asks the airspy for real samples, air.c:128-152): the input is
+ * complex baseband - signed 16-bit I/Q pairs at 10 MS/s, libairspy's INT16_IQ sample type, for which the library
+ * does the fs/4 translation and the decimation itself.  One pair per envelope sample, envelope = I*I + Q*Q;
+ * demod.c / valid.c behind it unchanged.  Integer sums as in demod.c:102-105: exact for |I|, |Q| <= 8191. */
+void oracle_set_iq(oracle_ctx *c, int on) { c->iq = on; }
+
 /* ---- EXTENSION: address/parity frames (not in the reference) ---------------------------
  * DF4, DF5 (56 bits) and DF20, DF21 (112 bits) carry CRC ^ ICAO address in their parity field, so their
  * syndrome is an address, not zero, and the reference (valid.c:52, :74) never accepts them.  With this mode on
@@ -381,6 +406,7 @@ void oracle_address_prepass(oracle_ctx *c, const void *data, size_t nbytes)
 	float *amp = malloc(n_amp * sizeof *amp);
 	oracle_ctx *t = oracle_new(c->accept_df18, c->fma_contract);
 	t->ring_pos = c->ring_pos;
+	t->iq = c->iq;
 	oracle_record_amp(t, amp, n_amp);
 	oracle_decode_memory(t, data, nbytes);
 	size_t have = t->tap_n < n_amp ? t->tap_n : n_amp;

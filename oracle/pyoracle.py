@@ -63,6 +63,7 @@ def lib():
         L.oracle_set_origin.argtypes = [C.c_void_p, C.c_uint64]
         L.oracle_set_repair.argtypes = [C.c_void_p, C.c_int]
         L.oracle_set_address_parity.argtypes = [C.c_void_p, C.c_int]
+        L.oracle_set_iq.argtypes = [C.c_void_p, C.c_int]
         L.oracle_address_prepass.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.oracle_push.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.oracle_decode_file.argtypes = [C.c_void_p, C.c_char_p]
@@ -106,7 +107,8 @@ def format_frame(f: Frame, fmt: int) -> bytes:
 
 
 def decode(samples: np.ndarray, *, accept_df18: bool = False, fma: bool = True,
-           want_amp: bool = False, origin: int = 0, repair: int = 0, address_parity: bool = False) -> Result:
+           want_amp: bool = False, origin: int = 0, repair: int = 0, address_parity: bool = False,
+           iq: bool = False) -> Result:
     """Run the sequential restatement over a whole capture (file semantics)."""
     L = lib()
     samples = np.ascontiguousarray(samples, dtype="<u2")
@@ -117,6 +119,8 @@ def decode(samples: np.ndarray, *, accept_df18: bool = False, fma: bool = True,
             L.oracle_set_origin(ctx, origin)
         if repair:
             L.oracle_set_repair(ctx, repair)   # extension, see oracle.h
+        if iq:                                 # extension, see oracle.h
+            L.oracle_set_iq(ctx, 1)
         if address_parity:                     # extension, see oracle.h
             L.oracle_set_address_parity(ctx, 1)
             L.oracle_address_prepass(ctx, samples.ctypes.data, samples.nbytes)

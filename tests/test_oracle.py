@@ -221,3 +221,19 @@ def test_address_parity_extension_of_the_oracle(oracle):
         assert bytes(f.data) in sent
         addr = (crc24(bytes(f.data[:-3])) ^ int.from_bytes(f.data[-3:], "big")).to_bytes(3, "big")
         assert addr in announced_at and announced_at[addr] // 2 < f.n
+
+
+def test_iq_input_extension_of_the_oracle(oracle):
+    """EXTENSION (the reference has no I/Q path): complex baseband pairs, envelope = I*I + Q*Q.  What must hold by
+    construction: read as real samples the capture decodes to nothing, read as I/Q it returns frames that were
+    sent, most of them, with timestamps in order."""
+    from adsbdec_b200.modulator import synth_iq_capture
+    cap = synth_iq_capture(0.3, 300, snr_db=20, seed=80, df_mix=((17, 0.6), (11, 0.3), (18, 0.1)), pad=1 << 16)
+    assert len(oracle.decode(cap.samples, accept_df18=True).frames) == 0
+    ref = oracle.decode(cap.samples, accept_df18=True, iq=True)
+    sent = {bytes(b.frame) for b in cap.bursts}
+    assert len(ref.frames) > 200 and all(bytes(f.data) in sent for f in ref.frames)
+    ts = [f.ts for f in ref.frames]
+    assert ts == sorted(ts)
+    starts = {b.start // 2 for b in cap.bursts}
+    assert sum(f.n in starts or f.n + 1 in starts or f.n - 1 in starts for f in ref.frames) > 0.9 * len(ref.frames)
