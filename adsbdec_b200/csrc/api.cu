@@ -182,10 +182,10 @@ struct adsbdec_b200 {
 	int device = 0;
 	cudaStream_t st = nullptr;       // kernels + result copies
 	cudaStream_t st_copy = nullptr;  // uploads of sample batches
-	cudaStream_t st_d2h = nullptr;   // the rest of a job's results when the speculative copy fell short
+	cudaStream_t st_d2h = nullptr;   // a finished job's keys and frames on their way to the host store
 	// Ordering / greedy / compaction / statistics of a job's candidates: a chain of small kernels that runs
-	// BESIDE the next job's scan.  k_fused leaves kResolveSMs SMs free for it (a persistent CTA holds a
-	// whole SM's registers, so nothing else fits next to one).
+	// BESIDE the next job's scan, in blocks of 128 threads x 32 registers - what is left on an SM next to a
+	// k_fused block (kernels_resolve.cu).
 	cudaStream_t st_res = nullptr;
 	cudaStream_t st_stat = nullptr;  // the Try statistics passes (they only read a finished job's lists)
 	cudaEvent_t ev_scan[kSlots] = {};   // the slot's scan kernels are done (recorded on st)
@@ -1041,7 +1041,8 @@ int adsbdec_b200_open(const adsbdec_b200_config_t *cfg, adsbdec_b200_t **out)
 				rc = fail(ADSB_B200_ENODEV, "fused kernel cannot be configured on device %d", cfg->device);
 				break;
 			}
-			// leave a few SMs to the resolve chain of the previous job (see st_res)
+			// (development knob: SMs left free for the resolve chain of the previous job; none by default, the
+			// chain's blocks fit beside k_fused - see kResolveSMs)
 			int reserve = kResolveSMs;
 			if (const char *e = getenv("ADSB_B200_RESOLVE_SMS"))  // development knob
 				reserve = atoi(e);
