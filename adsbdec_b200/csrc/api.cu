@@ -173,6 +173,7 @@ struct Job {
 	unsigned long long origin = 0;
 	bool used_fused = false;
 	bool resolve = true;            // feed the stream resolver on completion
+	bool gpu_idle_after = false;    // nothing is queued behind this job's scan: its ordering chain runs alone
 };
 
 }  // namespace
@@ -276,6 +277,7 @@ struct adsbdec_b200 {
 	int fix_level = 0;
 	// EXTENSION, off by default: DF4/5/20/21 accepted against the addresses announced so far
 	bool ap_mode = false;
+	bool next_job_is_last = false;  // set around the submit of a resident push's last job (Job::gpu_idle_after)
 	bool iq_mode = false;  // EXTENSION: the stream is signed 16-bit I/Q pairs at 10 MS/s, not real samples
 	unsigned long long *d_first_seen = nullptr;     // [2^24] by ICAO address: offset of its first announcement
 	unsigned long long *d_aptries[kSlots] = {};     // DF4/5/20/21 tries of the fused range being worked on
@@ -608,15 +610,15 @@ int enqueue_job(adsbdec_b200 *h, int s, bool force_generic)
 	CU(cudaStreamWaitEvent(h->st_res, h->ev_scan[s], 0));
 	if (j.resolve) {
 		CU(launch_resolve(h->rb[s], h->d_cands[s], h->d_ctr[s], h->cand_cap[s], j.n0, j.n1, h->d_state, h->d_slot[s],
-		                  h->d_acc[s], h->d_key[s], h->cand_cap[s], h->st_res));
+		                  h->d_acc[s], h->d_key[s], h->cand_cap[s], j.gpu_idle_after, h->st_res));
 		h->launches += 11;
 		if (j.used_fused) {  // demod.c:127: the signal level, for the frames that were accepted
 			CU(launch_fill_pw_frames(j.buf, j.u0, j.origin, h->d_acc[s], &h->d_slot[s]->n_accept, h->cand_cap[s],
-			                         h->st_res));
+			                         j.gpu_idle_after, h->st_res));
 			h->launches += 1;
 		}
 	} else {
-		CU(launch_sort(h->rb[s], h->d_cands[s], h->d_ctr[s], h->cand_cap[s], j.n0, j.n1, h->st_res));
+		CU(launch_sort(h->rb[s], h->d_cands[s], h->d_ctr[s], h->cand_cap[s], j.n0, j.n1, false, h->st_res));
 		h->launches += 5;
 	}
 	CU(cudaEventRecord(h->ev_b[s], h->st_res));
@@ -848,6 +850,7 @@ int submit_window(adsbdec_b200 *h, const uint16_t *buf, int64_t u0, int64_t u1)
 	j.n1 = std::max<int64_t>(h->own_next, j.total_out - kLookahead);
 	j.origin = h->origin;
 	j.resolve = true;
+	j.gpu_idle_after = h->next_job_is_last;
 	j.active = true;
 	h->own_next = j.n1;
 	h->tr.mark("submit: enqueue");
@@ -1408,8 +1411,10 @@ int adsbdec_b200_push_device(adsbdec_b200_t *h, const void *dev_samples, size_t 
 	for (const int64_t end : ends) {
 		// window: from the FIR history of the next owned offset to `end`, inside the caller's memory
 		const int64_t w0 = std::max<int64_t>(piece_u0, align_down(2 * h->own_next - kCarryBack, 8));
-		if (end > w0)
-			RC(submit_window(h, src + (w0 - piece_u0), w0, end));
+		h->next_job_is_last = end == piece_u1;  // (we wait for it below: nothing runs beside its chain)
+		const int rc = end > w0 ? submit_window(h, src + (w0 - piece_u0), w0, end) : 0;
+		h->next_job_is_last = false;
+		RC(rc);
 	}
 	// The tail the next push needs is copied while the last jobs still run (behind their scan kernels on the same
 	// stream, into the window buffer no job of this push reads), so that the wait below finds it done.
@@ -1750,6 +1755,7 @@ int64_t adsbdec_b200_chunk_candidates(adsbdec_b200_t *h, const void *dev_samples
 	j.n1 = (int64_t)own_end;
 	j.origin = start_sample;
 	j.resolve = false;
+	j.gpu_idle_after = false;
 	j.active = true;
 	RC(presize_lists(h, s, j.n1 - j.n0));
 	RC(enqueue_job(h, s, false));

@@ -17,7 +17,7 @@ cudaError_t launch_fill_pw(const uint16_t *raw, long long u_raw0, unsigned long 
 
 // pw for the n accepted frames of a job (*n_ptr, read on the device)
 cudaError_t launch_fill_pw_frames(const uint16_t *raw, long long u_raw0, unsigned long long origin, FrameRec *frames,
-                                  const unsigned long long *n_ptr, unsigned long long cap, cudaStream_t st);
+                                  const unsigned long long *n_ptr, unsigned long long cap, bool wide, cudaStream_t st);
 
 cudaError_t launch_scan_generic(const float *amp, long long j_amp0, long long n0, long long count,
                                 int accept_df18, int want_tries, CandRec *cands,
@@ -57,11 +57,12 @@ struct ResolveBuffers {      // per job slot scratch
 };
 
 int resolve_bucket_count(long long n0, long long n1);
+// wide: the chain will have the GPU to itself (four times the blocks of the grid-stride kernels)
 cudaError_t launch_sort(const ResolveBuffers &rb, const CandRec *cands, const Counters *ctr, unsigned long long cap,
-                        long long n0, long long n1, cudaStream_t st);
+                        long long n0, long long n1, bool wide, cudaStream_t st);
 cudaError_t launch_resolve(const ResolveBuffers &rb, const CandRec *cands, const Counters *ctr, unsigned long long cap,
                            long long n0, long long n1, ResolveState *state, SlotResolve *slot, FrameRec *out,
-                           unsigned long long *keys_out, unsigned long long out_cap, cudaStream_t st);
+                           unsigned long long *keys_out, unsigned long long out_cap, bool wide, cudaStream_t st);
 cudaError_t launch_set_state(ResolveState *state, unsigned long long carry_start, unsigned long long carry_pos,
                              unsigned long long drift, cudaStream_t st);
 cudaError_t launch_count_tries_frames(const unsigned long long *tries, const unsigned long long *n_tries_ptr,

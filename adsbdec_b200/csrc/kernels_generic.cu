@@ -316,9 +316,9 @@ static int fill_blocks()
 }
 
 cudaError_t launch_fill_pw_frames(const uint16_t *raw, long long u_raw0, unsigned long long origin, FrameRec *frames,
-                                  const unsigned long long *n_ptr, unsigned long long cap, cudaStream_t st)
+                                  const unsigned long long *n_ptr, unsigned long long cap, bool wide, cudaStream_t st)
 {
-	k_fill_pw_frames<<<fill_blocks(), 128, 0, st>>>(raw, u_raw0, origin, frames, n_ptr, cap);
+	k_fill_pw_frames<<<fill_blocks() * (wide ? 4 : 1), 128, 0, st>>>(raw, u_raw0, origin, frames, n_ptr, cap);
 	return cudaGetLastError();
 }
 

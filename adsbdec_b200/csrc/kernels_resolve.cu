@@ -55,7 +55,9 @@ static int chain_blocks()
 	}();
 	return n;
 }
-#define kChainBlocks chain_blocks()
+// (a job whose chain will have the GPU to itself - the last one of a resident push - gets four times the blocks:
+// the kernels wait for memory, and the one-block-per-SM slot beside k_fused is not what limits them then)
+#define kChainBlocks (chain_blocks() * (wide ? 4 : 1))
 
 __device__ __forceinline__ unsigned long long job_count(const Counters *ctr, unsigned long long cap)
 {
@@ -516,7 +518,7 @@ int resolve_bucket_count(long long n0, long long n1) { return (int)(((n1 - n0) >
 
 // Sort only (chunk mode): rb.sorted = candidates in offset order, bytes repacked, count in off[nb].
 cudaError_t launch_sort(const ResolveBuffers &rb, const CandRec *cands, const Counters *ctr, unsigned long long cap,
-                        long long n0, long long n1, cudaStream_t st)
+                        long long n0, long long n1, bool wide, cudaStream_t st)
 {
 	const int nb = resolve_bucket_count(n0, n1);
 	// (rb.cnt is all zero here: zeroed when it was allocated, counted back down to zero by every job)
@@ -530,10 +532,10 @@ cudaError_t launch_sort(const ResolveBuffers &rb, const CandRec *cands, const Co
 // Sort + greedy + compaction: `out` receives the accepted candidates in order, slot->n_accept their number.
 cudaError_t launch_resolve(const ResolveBuffers &rb, const CandRec *cands, const Counters *ctr, unsigned long long cap,
                            long long n0, long long n1, ResolveState *state, SlotResolve *slot, FrameRec *out,
-                           unsigned long long *keys_out, unsigned long long out_cap, cudaStream_t st)
+                           unsigned long long *keys_out, unsigned long long out_cap, bool wide, cudaStream_t st)
 {
 	const int nb = resolve_bucket_count(n0, n1);
-	cudaError_t e = launch_sort(rb, cands, ctr, cap, n0, n1, st);
+	cudaError_t e = launch_sort(rb, cands, ctr, cap, n0, n1, wide, st);
 	if (e != cudaSuccess) return e;
 	k_snapshot<<<1, 1, 0, st>>>(state, slot);
 	k_greedy<<<kChainBlocks, kChainThreads, 0, st>>>(rb.sorted, rb.off, nb, rb.accept, state, slot);
@@ -567,6 +569,7 @@ cudaError_t launch_count_tries_frames(const unsigned long long *tries, const uns
                                       cudaStream_t st)
 {
 	const int nb = n1 > n0 ? resolve_bucket_count(n0, n1) : 0;
+	const bool wide = false;
 	k_count_tries_frames<<<4 * kChainBlocks, kChainThreads, 0, st>>>(tries, n_tries_ptr, cap, frames, slot, frames_cap, rb.bacc_x, n0, nb,
 	                                         scan_end, pend_out, n_pend_out, pend_cap, stt);
 	return cudaGetLastError();
