@@ -34,6 +34,7 @@ EXPORTS = [
     "adsbdec_b200_format_packet", "adsbdec_b200_format_frames",
     "adsbdec_b200_envelope", "adsbdec_b200_resolver_new", "adsbdec_b200_resolver_free",
     "adsbdec_b200_resolver_feed", "adsbdec_b200_resolver_feed_frames", "adsbdec_b200_resolver_finish",
+    "adsbdec_b200_resolver_advance_keys",
     "adsbdec_b200_resolver_scan_end", "adsbdec_b200_resolver_num_frames", "adsbdec_b200_resolver_frames",
     "adsbdec_b200_chunk_candidates", "adsbdec_b200_debug_fused", "adsbdec_b200_last_error",
     "adsbdec_b200_version",
@@ -145,6 +146,8 @@ def lib():
         L.adsbdec_b200_resolver_feed.argtypes = [vp, vp, C.c_size_t, u64, u64, SINK_FN, vp]
         L.adsbdec_b200_resolver_feed_frames.argtypes = [vp, vp, C.c_size_t, u64, u64, u32p, SINK_FN, vp]
         L.adsbdec_b200_resolver_finish.argtypes = [vp, SINK_FN, vp]
+        L.adsbdec_b200_resolver_advance_keys.argtypes = [vp, vp, C.c_size_t, C.c_size_t, u64, u64, C.c_int]
+        L.adsbdec_b200_resolver_advance_keys.restype = C.c_int64
         L.adsbdec_b200_resolver_scan_end.argtypes = [vp]
         L.adsbdec_b200_resolver_scan_end.restype = u64
         L.adsbdec_b200_chunk_candidates.argtypes = [vp, vp, C.c_size_t, u64, u64, u64, vp, C.c_size_t, u32p]
@@ -458,6 +461,13 @@ class Resolver:
         _check(lib().adsbdec_b200_resolver_feed_frames(self._r, f.ctypes.data, f.size, scanned_upto, total_out,
                                                        ok, self._cb, None))
         return tuple(ok)
+
+    def advance_keys(self, keys: np.ndarray, n_vis: int, scanned_upto: int, total_out: int, finish: bool = False) -> int:
+        """The in-place schedule of the stream decoder: keys[i] = start << 1 | long for ALL stamped frames so far,
+        the first n_vis of them reached before.  Returns the new n_vis."""
+        k = np.ascontiguousarray(keys, dtype=np.uint64)
+        return _check(int(lib().adsbdec_b200_resolver_advance_keys(self._r, k.ctypes.data, n_vis, k.size, scanned_upto,
+                                                                  total_out, int(finish))))
 
     def finish(self) -> None:
         _check(lib().adsbdec_b200_resolver_finish(self._r, self._cb, None))

@@ -1878,6 +1878,18 @@ int adsbdec_b200_resolver_feed_frames(adsbdec_b200_resolver_t *r, const adsbdec_
 	return 0;
 }
 
+int64_t adsbdec_b200_resolver_advance_keys(adsbdec_b200_resolver_t *r, const uint64_t *keys, size_t n_vis,
+                                           size_t n_total, uint64_t scanned_upto, uint64_t total_out, int finish)
+{
+	if (!r || (!keys && n_total) || n_vis > n_total)
+		return fail(ADSB_B200_EINVAL, "bad argument");
+	static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "key type");
+	const unsigned long long *k = reinterpret_cast<const unsigned long long *>(keys);
+	if (finish)
+		return (int64_t)r->r.finish_keys(k, n_vis, n_total);
+	return (int64_t)r->r.advance_keys(k, n_vis, n_total, scanned_upto, total_out);
+}
+
 int adsbdec_b200_resolver_finish(adsbdec_b200_resolver_t *r, adsbdec_b200_sink_fn fn, void *user)
 {
 	if (!r)

@@ -239,6 +239,13 @@ int adsbdec_b200_resolver_feed(adsbdec_b200_resolver_t *r, const adsbdec_b200_ca
 int adsbdec_b200_resolver_feed_frames(adsbdec_b200_resolver_t *r, const adsbdec_b200_frame_t *f, size_t count,
                                       uint64_t scanned_upto, uint64_t total_out, uint32_t ok[3],
                                       adsbdec_b200_sink_fn fn, void *user);
+/* The in-place form the stream decoder itself runs (api.cu, complete_job): the caller keeps ALL stamped frames of
+ * the stream in one array and hands in only what the call schedule looks at, keys[i] = frame i's start << 1 |
+ * (frame i has 112 bits).  keys[0 .. n_vis) have been reached by the schedule before, keys[n_vis .. n_total) are new
+ * or still in front of it.  Returns the new n_vis (finish != 0: the last calls at the end of the stream,
+ * air.c:243-244), or < 0.  Nothing is copied, no sink is called; do not mix with feed / feed_frames on one resolver. */
+int64_t adsbdec_b200_resolver_advance_keys(adsbdec_b200_resolver_t *r, const uint64_t *keys, size_t n_vis,
+                                           size_t n_total, uint64_t scanned_upto, uint64_t total_out, int finish);
 int adsbdec_b200_resolver_finish(adsbdec_b200_resolver_t *r, adsbdec_b200_sink_fn fn, void *user);
 /* Number of spans accepted so far / copy them ([start, start+skip) pairs). */
 uint64_t adsbdec_b200_resolver_scan_end(const adsbdec_b200_resolver_t *r);

@@ -176,6 +176,42 @@ def test_resolver_stamped_frames_path(adsb, oracle, cut):
         assert tuple(ok) == ref.ok == tuple(int(x) for x in ok2)
 
 
+def test_resolver_in_place_schedule_on_keys(adsb, oracle):
+    """The form the stream decoder runs in production (api.cu complete_job -> Resolver::advance_keys): all stamped
+    frames stay in one array, the call schedule only sees 8-byte keys (start << 1 | long) and returns how many
+    frames it has reached.  Same answer as feeding the frames themselves, job by job and at the end of the stream;
+    dense traffic, so that both the short walk and the search behind it run."""
+    from adsbdec_b200.modulator import synth_capture
+    cap = synth_capture(0.12, 1500, snr_db=22, seed=34, df_mix=((11, 0.6), (17, 0.4)), pad=0, poisson=False)
+    ref = oracle.decode(cap.samples, accept_df18=True, want_amp=True)
+    cands, _ = all_offset_candidates(ref.amp, True)
+    total_out = ref.amp.size
+    stamped, pos, drift = [], 0, 0
+    for c in cands:                       # demod.c:99, :128, :134 over the sparse list
+        if c["n"] < pos or c["n"] >= total_out - 1200:
+            continue
+        skip = 640 if c["len"] == 7 else 1200
+        stamped.append((int(c["n"]) + 1 - drift, int(c["n"]), int(c["pw"]), int(c["len"]), c["bytes"][:14], (0, 0)))
+        pos, drift = int(c["n"]) + skip, drift + skip - 1
+    stamped = np.array(stamped, dtype=adsb.FRAME_DTYPE)
+    keys = (stamped["n"].astype(np.uint64) << np.uint64(1)) | (stamped["len"] == 14).astype(np.uint64)
+    a, b = adsb.Resolver(True), adsb.Resolver(True)
+    n_vis, fed, step = 0, 0, 250_000      # "jobs" of 250 k offsets
+    for upto in range(step, total_out + step, step):
+        upto = min(upto, total_out)
+        scanned = max(0, upto - 1200)
+        have = int(np.searchsorted(stamped["n"], scanned))      # frames of the jobs so far
+        a.feed_frames(stamped[fed:have], scanned, upto)
+        fed = have
+        n_vis = b.advance_keys(keys[:have], n_vis, scanned, upto)
+        assert n_vis == len(a.out) and b.scan_end == a.scan_end
+    a.finish()
+    n_vis = b.advance_keys(keys[:fed], n_vis, 0, 0, finish=True)
+    assert n_vis == len(a.out) == len(ref.frames) > 500
+    assert [(f.ts, f.data) for f in a.out] == [(f.ts, f.data) for f in ref.frames]
+    assert [int(x) for x in stamped["ts"][:n_vis]] == [f.ts for f in ref.frames]
+
+
 def test_resolver_non_emulated_tail_scans_everything(adsb, oracle):
     cap = capture_basic(seed=32, seconds=0.03, n_frames=40, pad=0)
     ref = oracle.decode(cap.samples, want_amp=True)
