@@ -26,3 +26,26 @@ for kernel in (0, 1):
     print("kernel", kernel, "repair=2 packed12 frames", len(d.frames), "== oracle:", ok,
           [int(x) for x in d.frames_array["pad"][:, 0]] == ref2.fixed)
     d.close()
+
+# the extensions of round 2 and the long-chain path of k_greedy
+from adsbdec_b200.modulator import synth_fleet_capture, synth_iq_capture
+key = lambda fr: [(f.n, f.ts, f.pw, f.data) for f in fr]
+fleet = synth_fleet_capture(0.2, 250, 10, snr_db=22, seed=70, pad=1 << 16)
+ref3 = pyoracle.decode(fleet.samples, accept_df18=True, address_parity=True)
+for kernel in (0, 1):
+    d = A.Decoder(accept_df18=True, kernel=kernel, batch_samples=1 << 20, address_parity=True)
+    d.push(fleet.samples); d.finish()
+    print("kernel", kernel, "address/parity frames", len(d.frames), "== oracle:", key(d.frames) == key(ref3.frames))
+    d.close()
+iq = synth_iq_capture(0.2, 200, snr_db=20, seed=80, df_mix=((17, .6), (11, .4)), pad=1 << 16)
+ref4 = pyoracle.decode(iq.samples, accept_df18=True, iq=True)
+d = A.Decoder(accept_df18=True, iq=True, batch_samples=1 << 20)
+d.push(iq.samples); d.finish()
+print("I/Q input frames", len(d.frames), "== oracle:", key(d.frames) == key(ref4.frames))
+d.close()
+sat = synth_capture(0.1, 1400, snr_db=22, seed=61, df_mix=((11, 1.0),), pad=1 << 16, poisson=False)
+ref5 = pyoracle.decode(sat.samples, accept_df18=True)
+d = A.Decoder(accept_df18=True)
+d.push(sat.samples); d.finish()
+print("saturated traffic (one greedy chain) frames", len(d.frames), "== oracle:", key(d.frames) == key(ref5.frames))
+d.close()
