@@ -1269,6 +1269,8 @@ int adsbdec_b200_push_packed12(adsbdec_b200_t *h, const void *packed, size_t n)
 		return fail(ADSB_B200_EINVAL, "packed pushes come in groups of 8 samples (12 bytes)");
 	if (((uintptr_t)packed) % 4)
 		return fail(ADSB_B200_EINVAL, "packed samples must be 4-byte aligned");
+	if (h->iq_mode)
+		return fail(ADSB_B200_EINVAL, "packed 12-bit samples are real samples: not on a stream opened for I/Q input");
 	if (h->finished)
 		return fail(ADSB_B200_ESTATE, "push after finish");
 	if (n == 0)

@@ -746,6 +746,8 @@ def test_iq_input_extension_matches_oracle(adsb, oracle, batch, tmp_path):
     assert_same(ref, d.frames, d.stats())
     d.close()
     assert {4, 5, 20, 21} <= {f.data[0] >> 3 for f in ref.frames}
+    with pytest.raises(adsb.AdsbError):      # packed 12-bit samples are real samples
+        adsb.Decoder(iq=True).push_packed12(np.zeros(12, np.uint32), 32)
     if batch == 0:
         f = tmp_path / "iq.bin"
         np.concatenate([cap.samples, np.zeros(1 << 21, np.uint16)]).astype("<u2").tofile(f)
