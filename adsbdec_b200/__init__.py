@@ -212,7 +212,7 @@ class Decoder:
         cfg.batch_samples = batch_samples
         cfg.start_sample = start_sample
         cfg.reserved[0], cfg.reserved[1] = initial_caps
-        cfg.reserved[2] = reader_threads  # decode_file: 0 = up to 12, 1 = the calling thread only
+        cfg.reserved[2] = reader_threads  # decode_file: 0 = up to 16, 1 = the calling thread only
         # EXTENSIONS (not in the reference): repair 1 = fix one bit, 2 = two bits; 0x100 = accept DF4/5/20/21
         # whose address/parity field names an aircraft announced earlier in the stream
         # 0x200 = the samples are signed I/Q pairs at 10 MS/s (complex baseband) instead of real samples at 20 MS/s

@@ -1525,12 +1525,12 @@ int adsbdec_b200_decode_file(adsbdec_b200_t *h, const char *path)
 		off_t pos = 0;
 		bool had_full_read = false;
 		// every read but the last returns 2 MiB whatever the order it is issued in: fetch those in
-		// parallel (readpool.h); reserved[2] = reader threads, 0 = up to 12, 1 = this thread alone
+		// parallel (readpool.h); reserved[2] = reader threads, 0 = up to 16, 1 = this thread alone
 		int64_t bulk_left = (int64_t)(sb.st_size / (off_t)(kReadSamples * sizeof(uint16_t))) * kReadSamples;
 		if (!rc && bulk_left > 0 && !h->readers) {
 			int nthr = (int)h->cfg.reserved[2];
 			if (nthr <= 0)
-				nthr = std::max(1, std::min(12, (int)std::thread::hardware_concurrency() * 3 / 4));
+				nthr = std::max(1, std::min(16, (int)std::thread::hardware_concurrency()));  // (16 threads: 22.7 G samples/s, 12: 19.9)
 			h->readers.reset(new (std::nothrow) ReadPool(std::min(nthr, 64) - 1));
 			if (!h->readers)
 				rc = fail(ADSB_B200_ENOMEM, "out of memory");

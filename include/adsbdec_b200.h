@@ -86,7 +86,7 @@ typedef struct {
 	                                    FIR rotation / fidx wrap (air.c:34,65) line up)           */
 	uint64_t reserved[4];            /* [0], [1]: initial candidate / try list capacities (0 = default;
 	                                    lists regrow on demand), [2]: threads decode_file reads a regular
-	                                    file with (0 = up to 12, 1 = the calling thread only),
+	                                    file with (0 = up to 16, 1 = the calling thread only),
 	                                    [3]: EXTENSION, error repair by syndrome lookup: 0 = off = the
 	                                    reference (valid.c:52,:74 want syndrome 0), 1 = one flipped bit,
 	                                    2 = also two flipped bits of a 112-bit frame; never the DF field;
