@@ -212,6 +212,50 @@ def test_resolver_in_place_schedule_on_keys(adsb, oracle):
     assert [int(x) for x in stamped["ts"][:n_vis]] == [f.ts for f in ref.frames]
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_resolver_schedule_against_a_python_statement(adsb, seed):
+    """air.c:94-99 as three lines of Python against Resolver::advance_keys: deqframe is called at the first even
+    sample count that leaves 40 980 envelope samples queued, scans up to 1200 before the end of what it was given and
+    returns where it stopped - behind a frame if one straddles that point.  Random frame lists from empty to
+    saturated, fed in random pieces."""
+    rng = np.random.default_rng(seed)
+    total = int(rng.integers(100_000, 3_000_000))
+    gap = [3000, 700, 50_000, 1300, 641, 200_000][seed]
+    starts, lens, n = [], [], int(rng.integers(0, 2000))
+    while n < total - 1200:
+        ln = 14 if rng.random() < 0.5 else 7
+        starts.append(n)
+        lens.append(ln)
+        n += (1200 if ln == 14 else 640) + int(rng.integers(0, gap))
+    starts, lens = np.array(starts, dtype=np.uint64), np.array(lens)
+    keys = (starts << np.uint64(1)) | (lens == 14).astype(np.uint64)
+
+    def model(state, n_have, scanned_upto, total_out):
+        base, n_vis = state
+        while True:
+            call_at = base + 40980
+            call_at += call_at & 1
+            if call_at > total_out or call_at - 1200 > scanned_upto:
+                return base, n_vis
+            cutoff = call_at - 1200
+            i = n_vis
+            while i < n_have and int(starts[i]) < cutoff:
+                i += 1
+            pos = int(starts[i - 1]) + (1200 if lens[i - 1] == 14 else 640) if i > n_vis else base
+            base, n_vis = max(cutoff, pos), i
+
+    r = adsb.Resolver(True)
+    state, n_vis, upto = (0, 0), 0, 0
+    while upto < total:
+        upto = min(total, upto + int(rng.integers(1, 400_000)))
+        scanned = max(0, upto - 1200)
+        have = int(np.searchsorted(starts, scanned))
+        state = model(state, have, scanned, upto)
+        n_vis = r.advance_keys(keys[:have], n_vis, scanned, upto)
+        assert n_vis == state[1] and r.scan_end <= scanned
+    assert r.advance_keys(keys[:have], n_vis, 0, 0, finish=True) == state[1]   # EOF adds no call (air.c:243-244)
+
+
 def test_resolver_non_emulated_tail_scans_everything(adsb, oracle):
     cap = capture_basic(seed=32, seconds=0.03, n_frames=40, pad=0)
     ref = oracle.decode(cap.samples, want_amp=True)
